@@ -1,0 +1,104 @@
+/*
+ * irb_b200.h -- C ABI of the B200-native partitioned-convolution engine (libirb_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of Flixor/IRBaboon: the uniformly partitioned FFT
+ * convolution engine and the spectral-division deconvolution that reuses its kernels.  The reference
+ * has no FFI of its own (it is a C++14 JUCE plugin); what a maintainer binds is its fp:: header surface,
+ * so each entry point below names the reference interface it stands behind (paths relative to the
+ * reference tree).  The C++ facade in irbaboon_b200/fp/ (same namespaces, names, defaults as the
+ * reference's fp/ headers) is a thin wrapper over these calls -- see INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  All audio is float32.  Every function
+ * returns 0 on success or a negative irb_status; irb_last_error() gives the message of the calling
+ * thread's most recent failure.  No exception crosses this boundary.  There is NO CPU fallback: if no
+ * sm_100 device is usable every compute entry point fails with IRB_ERR_CUDA.
+ *
+ * Threading: one thread drives a given irb_engine at a time (the audio callback, as in the reference);
+ * different engines are independent.  The offline functions are re-entrant.
+ */
+#ifndef IRB_B200_H
+#define IRB_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum irb_status {
+    IRB_OK = 0,
+    IRB_ERR_ARG = -1,      /* bad argument (size, null pointer, unsupported block size) */
+    IRB_ERR_LAYOUT = -2,   /* channel layout the reference rejects (fp/convolution.cpp:39-42): outputs are zeroed */
+    IRB_ERR_CUDA = -3,     /* CUDA runtime failure / no usable device */
+    IRB_ERR_STATE = -4     /* call not valid in the engine's current state */
+} irb_status;
+
+typedef struct irb_engine irb_engine;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+const char* irb_last_error(void);
+int irb_version(void);                       /* 100 * major + minor */
+int irb_device_count(void);                  /* CUDA devices visible; < 0 on failure */
+int irb_set_device(int device);              /* device used by the offline functions on this thread */
+int irb_max_block_size(void);                /* largest processBlockSize the block kernels take (2048) */
+
+/* pinned host buffers for the engine's host-side entry points (plain malloc'ed memory also works, slower) */
+void* irb_host_alloc(size_t bytes);
+void irb_host_free(void* p);
+
+/* ---- streaming engine -----------------------------------------------------------------------------
+ * Replaces the real-time UPOLA engine inlined in IRBaboonAudioProcessor::processBlock
+ * (Source/PluginProcessor.cpp:403-562; state PluginProcessor.h:194-217; setup :57-82,164-234) and its
+ * fp::CircularBufferArray rings (fp/CircularBufferArray.hpp:18-64), batched over n_channels independent
+ * stream-channels.  Device state per channel: a ring of max_partitions packed spectra (the frequency
+ * domain delay line, FDL), its head index, and block_size overlap samples.
+ */
+int irb_engine_create(irb_engine** out, int device, int block_size, int max_partitions, int n_channels, int n_irs);
+int irb_engine_destroy(irb_engine* e);
+/* run on a caller-owned CUDA stream (cudaStream_t / CUstream); NULL restores the engine's own stream */
+int irb_engine_set_stream(irb_engine* e, void* cuda_stream);
+
+/* Partition, zero-pad and transform an impulse response (fp/convolution.cpp:106-125 /
+ * PluginProcessor.cpp:455-461, done for all partitions at once).  n_taps <= block_size*max_partitions.
+ * right != NULL folds a stereo IR to (left+right)/2 first (tools::sumToMono, fp/tools.cpp:13-30). */
+int irb_engine_set_ir(irb_engine* e, int ir_id, const float* left, const float* right, int n_taps);
+/* channels [chan_begin, chan_end) convolve with ir_id.  Channels that share a kernel tile
+ * (irb_engine_tile_channels() consecutive channels) must share an IR. */
+int irb_engine_bind(irb_engine* e, int chan_begin, int chan_end, int ir_id);
+int irb_engine_tile_channels(const irb_engine* e);
+/* clear FDL rings, overlap buffers and heads (prepareToPlay, PluginProcessor.cpp:164-234) */
+int irb_engine_reset(irb_engine* e);
+
+/* One UPOLA step per block for every channel: forward FFT into the FDL, MAC over all partitions,
+ * inverse FFT, overlap-add.  in/out are [n_blocks][n_channels][block_size] float32.
+ *   _process        : HOST buffers; copies in, runs, copies out, returns when out is complete.
+ *   _process_device : DEVICE buffers on the engine's stream; asynchronous. */
+int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int n_blocks);
+int irb_engine_process_device(irb_engine* e, const float* in_dev, float* out_dev, int n_blocks);
+int irb_engine_synchronize(irb_engine* e);
+
+/* introspection (tests, benchmarks) */
+size_t irb_engine_state_bytes(const irb_engine* e);            /* device bytes held */
+int irb_engine_fft_size(const irb_engine* e);                  /* N = 2M actually used */
+int irb_engine_partitions(const irb_engine* e, int ir_id);     /* partitions of a loaded IR */
+/* copy one packed spectrum (M complex: bin 0 = {Re X[0], Re X[N/2]}) to the host:
+ * the IR partition `part` of ir_id, or the FDL slot `age` blocks old (0 = newest) of a channel */
+int irb_engine_read_ir_spectrum(irb_engine* e, int ir_id, int part, float* out_packed);
+int irb_engine_read_fdl_spectrum(irb_engine* e, int chan, int age, float* out_packed);
+/* kernel launches issued by this engine so far, and by the whole library */
+long long irb_engine_launch_count(const irb_engine* e);
+long long irb_launch_count(void);
+/* the pure FDL multiply-accumulate (no inverse FFT) on the current state into a device buffer of
+ * n_channels * M complex; used to time the roofline kernel in isolation */
+int irb_engine_mac_only_device(irb_engine* e, float* acc_dev);
+
+/* ---- offline functions ------------------------------------------------------------------------------
+ * fp::convolution::convolvePeriodic (fp/convolution.hpp:31, fp/convolution.cpp:14-242): planar
+ * x[ch_x][len_x], h[ch_h][len_h] -> out[ch_x][len_x+len_h-1].  Same channel layouts (mono/stereo x
+ * mono/stereo), partition count, iteration count and unflushed tail as the reference. */
+int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, int ch_h, int len_h, int block_size, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRB_B200_H */

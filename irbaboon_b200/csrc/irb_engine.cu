@@ -1,0 +1,452 @@
+// irb_engine.cu -- host side of libirb_b200.so: the C ABI declared in include/irb_b200.h over the
+// kernels in irb_kernels.cuh.  No CPU compute path exists in this file: every entry point either
+// launches sm_100a kernels or fails with IRB_ERR_CUDA.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <mutex>
+#include <new>
+#include <vector>
+#include <atomic>
+
+#include "../../include/irb_b200.h"
+#include "irb_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_device = 0;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(IRB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// FFT half-size M for a block size: N = smallest power of two >= 2B-1 (fp/convolution.cpp:45-48), M = N/2,
+// never below 16 (a longer zero-padded transform gives the same linear convolution).
+int half_size_for_block(int B) {
+    int N = 1;
+    while (N < 2 * B - 1) N *= 2;
+    int M = N / 2;
+    return M < 16 ? 16 : M;
+}
+constexpr int kMaxM = 2048;
+
+// twiddle tables, one per (device, M), built in double like the reference FFT's tables
+struct Twiddles {
+    std::mutex mu;
+    struct Entry { int dev, M; float2* d; };
+    std::vector<Entry> tab;
+    int get(int dev, int M, const float2** out) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& e : tab) if (e.dev == dev && e.M == M) { *out = e.d; return 0; }
+        const int N = 2 * M;
+        std::vector<float2> h(N);
+        for (int k = 0; k < N; ++k) {
+            const double ang = -2.0 * M_PI * (double) k / (double) N;
+            h[k].x = (float) cos(ang);
+            h[k].y = (float) sin(ang);
+        }
+        float2* d = nullptr;
+        CK(cudaMalloc(&d, sizeof(float2) * N));
+        CK(cudaMemcpy(d, h.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+        tab.push_back({dev, M, d});
+        *out = d;
+        return 0;
+    }
+} g_tw;
+
+// partitions per IR ring stage (= FDL loads batched per thread): 1 or 2; IRB_MAC_U overrides for tuning
+int mac_u_pref() {
+    static int u = [] { const char* s = getenv("IRB_MAC_U"); return s ? atoi(s) : 1; }();
+    return u;
+}
+
+template <int M>
+int launch_fwd_t(const irb::FwdArgs& a, cudaStream_t st) {
+    const int grid = (a.n_rows + irb::Tile<M>::ROWS - 1) / irb::Tile<M>::ROWS;
+    if (grid <= 0) return 0;
+    irb::k_fwd<M><<<grid, irb::kThreads, 0, st>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+template <int M, int U, bool INV>
+int launch_mac_u(const irb::MacArgs& a, cudaStream_t st) {
+    const int grid = (a.n_rows + irb::Tile<M>::ROWS - 1) / irb::Tile<M>::ROWS;
+    if (grid <= 0) return 0;
+    const size_t smem = sizeof(irb::MacSmem<M, U>);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CK(cudaFuncSetAttribute(irb::k_mac<M, U, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured_dev = dev;
+    }
+    irb::k_mac<M, U, INV><<<grid, irb::kThreads + 32, smem, st>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+template <int M, bool INV>
+int launch_mac_t(const irb::MacArgs& a, cudaStream_t st) {
+    if constexpr (M <= 512) { if (mac_u_pref() == 2) return launch_mac_u<M, 2, INV>(a, st); }
+    return launch_mac_u<M, 1, INV>(a, st);
+}
+#define IRB_DISPATCH_M(M_, EXPR)                                         \
+    switch (M_) {                                                        \
+        case 16: { constexpr int MM = 16; return EXPR; }                 \
+        case 32: { constexpr int MM = 32; return EXPR; }                 \
+        case 64: { constexpr int MM = 64; return EXPR; }                 \
+        case 128: { constexpr int MM = 128; return EXPR; }               \
+        case 256: { constexpr int MM = 256; return EXPR; }               \
+        case 512: { constexpr int MM = 512; return EXPR; }               \
+        case 1024: { constexpr int MM = 1024; return EXPR; }             \
+        case 2048: { constexpr int MM = 2048; return EXPR; }             \
+        default: return fail(IRB_ERR_ARG, "unsupported FFT half size %d", M_); \
+    }
+int launch_fwd(int M, const irb::FwdArgs& a, cudaStream_t st) { IRB_DISPATCH_M(M, launch_fwd_t<MM>(a, st)); }
+int launch_mac(int M, bool inv, const irb::MacArgs& a, cudaStream_t st) {
+    if (inv) { IRB_DISPATCH_M(M, (launch_mac_t<MM, true>(a, st))); }
+    IRB_DISPATCH_M(M, (launch_mac_t<MM, false>(a, st)));
+}
+int tile_rows(int M) { return irb::kTile / M; }
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes, bool zero) {
+        CK(cudaMalloc(&p, bytes ? bytes : 16));
+        if (zero) CK(cudaMemset(p, 0, bytes ? bytes : 16));
+        return 0;
+    }
+    template <typename T> T* as() const { return (T*) p; }
+};
+
+}  // namespace
+
+struct irb_engine {
+    int device = 0, B = 0, M = 0, ring = 0, n_chans = 0, n_irs = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    const float2* W = nullptr;
+    DevBuf fdl, H, ov, head, ir_of_chan, nparts, io_in, io_out, taps;
+    std::vector<int> h_ir_of_chan, h_nparts;
+    bool binding_dirty = true;
+    size_t bytes = 0;
+    long long launches = 0;
+};
+
+namespace {
+
+int engine_check_binding(irb_engine* e) {
+    if (!e->binding_dirty) return 0;
+    const int rows = tile_rows(e->M);
+    for (int c0 = 0; c0 < e->n_chans; c0 += rows)
+        for (int c = c0 + 1; c < c0 + rows && c < e->n_chans; ++c)
+            if (e->h_ir_of_chan[c] != e->h_ir_of_chan[c0])
+                return fail(IRB_ERR_STATE, "channels %d and %d share a kernel tile (%d channels) but are bound to different IRs", c0, c, rows);
+    CK(cudaMemcpyAsync(e->ir_of_chan.p, e->h_ir_of_chan.data(), sizeof(int) * e->n_chans, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->binding_dirty = false;
+    return 0;
+}
+
+int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
+    irb::FwdArgs f{};
+    f.src = in_dev; f.src2 = nullptr; f.src_chan_stride = e->B; f.L = e->B; f.B = e->B;
+    f.blocks_per_chan = 1; f.n_rows = e->n_chans;
+    f.dst = e->fdl.as<float2>(); f.dst_chan_stride = (long long) e->ring * e->M;
+    f.head = e->head.as<int>(); f.ring = e->ring; f.W = e->W;
+    int rc = launch_fwd(e->M, f, e->stream);
+    if (rc) return rc;
+    irb::MacArgs m{};
+    m.fdl = e->fdl.as<float2>(); m.fdl_chan_stride = (long long) e->ring * e->M;
+    m.head = e->head.as<int>(); m.ring = e->ring; m.blocks_per_chan = 1; m.n_rows = e->n_chans;
+    m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
+    m.ir_of_chan = e->ir_of_chan.as<int>(); m.nparts = e->nparts.as<int>(); m.W = e->W;
+    m.Y = nullptr; m.B = e->B; m.out = out_dev; m.out_chan_stride = e->B; m.Lout = e->B;
+    m.ov = e->ov.as<float>(); m.tail = nullptr;
+    rc = launch_mac(e->M, true, m, e->stream);
+    if (rc) return rc;
+    e->launches += 2;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* irb_last_error(void) { return g_err; }
+int irb_version(void) { return 100; }
+int irb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return fail(IRB_ERR_CUDA, "no CUDA device"); }
+    return n;
+}
+int irb_set_device(int device) {
+    CK(cudaSetDevice(device));
+    g_device = device;
+    return 0;
+}
+int irb_max_block_size(void) { return kMaxM; }
+void* irb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); fail(IRB_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void irb_host_free(void* p) { if (p) cudaFreeHost(p); }
+long long irb_launch_count(void) { return g_launches.load(); }
+
+int irb_engine_create(irb_engine** out, int device, int block_size, int max_partitions, int n_channels, int n_irs) {
+    if (!out) return fail(IRB_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (block_size < 1 || half_size_for_block(block_size) > kMaxM) return fail(IRB_ERR_ARG, "block_size %d outside [1, %d]", block_size, kMaxM);
+    if (max_partitions < 1 || n_channels < 1 || n_irs < 1) return fail(IRB_ERR_ARG, "max_partitions, n_channels and n_irs must be >= 1");
+    CK(cudaSetDevice(device));
+    irb_engine* e = new (std::nothrow) irb_engine;
+    if (!e) return fail(IRB_ERR_ARG, "out of host memory");
+    e->device = device; e->B = block_size; e->M = half_size_for_block(block_size);
+    e->ring = max_partitions; e->n_chans = n_channels; e->n_irs = n_irs;
+    int rc = g_tw.get(device, e->M, &e->W);
+    if (rc) { delete e; return rc; }
+    const size_t spec = sizeof(float2) * (size_t) e->M;
+    const size_t b_fdl = spec * e->ring * n_channels, b_H = spec * e->ring * n_irs, b_io = sizeof(float) * (size_t) e->B * n_channels;
+    if ((rc = e->fdl.alloc(b_fdl, true)) || (rc = e->H.alloc(b_H, true)) || (rc = e->ov.alloc(b_io, true)) ||
+        (rc = e->head.alloc(sizeof(int) * n_channels, false)) || (rc = e->ir_of_chan.alloc(sizeof(int) * n_channels, true)) ||
+        (rc = e->nparts.alloc(sizeof(int) * n_irs, true)) || (rc = e->io_in.alloc(b_io, true)) || (rc = e->io_out.alloc(b_io, true)) ||
+        (rc = e->taps.alloc(sizeof(float) * 2 * (size_t) e->B * e->ring, true))) {
+        delete e;
+        return rc;
+    }
+    e->bytes = b_fdl + b_H + 3 * b_io + sizeof(int) * (2 * (size_t) n_channels + n_irs) + sizeof(float) * 2 * (size_t) e->B * e->ring;
+    e->h_ir_of_chan.assign(n_channels, 0);
+    e->h_nparts.assign(n_irs, 0);
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return fail(IRB_ERR_CUDA, "cudaStreamCreate failed"); }
+    e->stream = e->own_stream;
+    *out = e;
+    return irb_engine_reset(e);
+}
+
+int irb_engine_destroy(irb_engine* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return 0;
+}
+
+int irb_engine_set_stream(irb_engine* e, void* cuda_stream) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t) cuda_stream : e->own_stream;
+    return 0;
+}
+
+int irb_engine_reset(irb_engine* e) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    CK(cudaSetDevice(e->device));
+    const size_t spec = sizeof(float2) * (size_t) e->M;
+    CK(cudaMemsetAsync(e->fdl.p, 0, spec * e->ring * e->n_chans, e->stream));
+    CK(cudaMemsetAsync(e->ov.p, 0, sizeof(float) * (size_t) e->B * e->n_chans, e->stream));
+    std::vector<int> h(e->n_chans, e->ring - 1);     // first block lands in slot 0
+    CK(cudaMemcpyAsync(e->head.p, h.data(), sizeof(int) * e->n_chans, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int irb_engine_set_ir(irb_engine* e, int ir_id, const float* left, const float* right, int n_taps) {
+    if (!e || !left) return fail(IRB_ERR_ARG, "engine or taps null");
+    if (ir_id < 0 || ir_id >= e->n_irs) return fail(IRB_ERR_ARG, "ir_id %d outside [0, %d)", ir_id, e->n_irs);
+    if (n_taps < 1 || (long long) n_taps > (long long) e->B * e->ring) return fail(IRB_ERR_ARG, "n_taps %d outside [1, %lld]", n_taps, (long long) e->B * e->ring);
+    CK(cudaSetDevice(e->device));
+    const int P = (int) std::ceil((float) n_taps / (float) e->B);          // fp/convolution.cpp:52
+    float* dl = e->taps.as<float>();
+    float* dr = dl + (size_t) e->B * e->ring;
+    CK(cudaMemcpyAsync(dl, left, sizeof(float) * n_taps, cudaMemcpyHostToDevice, e->stream));
+    if (right) CK(cudaMemcpyAsync(dr, right, sizeof(float) * n_taps, cudaMemcpyHostToDevice, e->stream));
+    const size_t spec = sizeof(float2) * (size_t) e->M;
+    float2* Hd = e->H.as<float2>() + (size_t) ir_id * e->ring * e->M;
+    CK(cudaMemsetAsync(Hd, 0, spec * e->ring, e->stream));
+    irb::FwdArgs f{};
+    f.src = dl; f.src2 = right ? dr : nullptr; f.src_chan_stride = 0; f.L = n_taps; f.B = e->B;
+    f.blocks_per_chan = P; f.n_rows = P; f.dst = Hd; f.dst_chan_stride = 0; f.head = nullptr; f.ring = e->ring; f.W = e->W;
+    int rc = launch_fwd(e->M, f, e->stream);
+    if (rc) return rc;
+    e->launches += 1;
+    e->h_nparts[ir_id] = P;
+    CK(cudaMemcpyAsync(e->nparts.as<int>() + ir_id, &e->h_nparts[ir_id], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int irb_engine_bind(irb_engine* e, int chan_begin, int chan_end, int ir_id) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    if (chan_begin < 0 || chan_end > e->n_chans || chan_begin > chan_end) return fail(IRB_ERR_ARG, "channel range [%d, %d) outside [0, %d)", chan_begin, chan_end, e->n_chans);
+    if (ir_id < 0 || ir_id >= e->n_irs) return fail(IRB_ERR_ARG, "ir_id %d outside [0, %d)", ir_id, e->n_irs);
+    for (int c = chan_begin; c < chan_end; ++c) e->h_ir_of_chan[c] = ir_id;
+    e->binding_dirty = true;
+    return 0;
+}
+int irb_engine_tile_channels(const irb_engine* e) { return e ? tile_rows(e->M) : fail(IRB_ERR_ARG, "engine is null"); }
+
+int irb_engine_process_device(irb_engine* e, const float* in_dev, float* out_dev, int n_blocks) {
+    if (!e || !in_dev || !out_dev) return fail(IRB_ERR_ARG, "null argument");
+    if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
+    CK(cudaSetDevice(e->device));
+    int rc = engine_check_binding(e);
+    if (rc) return rc;
+    const size_t blk = (size_t) e->B * e->n_chans;
+    for (int b = 0; b < n_blocks; ++b)
+        if ((rc = engine_step_device(e, in_dev + b * blk, out_dev + b * blk))) return rc;
+    return 0;
+}
+
+int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int n_blocks) {
+    if (!e || !in_host || !out_host) return fail(IRB_ERR_ARG, "null argument");
+    if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
+    CK(cudaSetDevice(e->device));
+    int rc = engine_check_binding(e);
+    if (rc) return rc;
+    const size_t blk = (size_t) e->B * e->n_chans;
+    for (int b = 0; b < n_blocks; ++b) {
+        CK(cudaMemcpyAsync(e->io_in.p, in_host + b * blk, sizeof(float) * blk, cudaMemcpyHostToDevice, e->stream));
+        if ((rc = engine_step_device(e, e->io_in.as<float>(), e->io_out.as<float>()))) return rc;
+        CK(cudaMemcpyAsync(out_host + b * blk, e->io_out.p, sizeof(float) * blk, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int irb_engine_synchronize(irb_engine* e) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+size_t irb_engine_state_bytes(const irb_engine* e) { return e ? e->bytes : 0; }
+int irb_engine_fft_size(const irb_engine* e) { return e ? 2 * e->M : fail(IRB_ERR_ARG, "engine is null"); }
+int irb_engine_partitions(const irb_engine* e, int ir_id) {
+    if (!e || ir_id < 0 || ir_id >= e->n_irs) return fail(IRB_ERR_ARG, "bad engine or ir_id");
+    return e->h_nparts[ir_id];
+}
+long long irb_engine_launch_count(const irb_engine* e) { return e ? e->launches : 0; }
+
+int irb_engine_read_ir_spectrum(irb_engine* e, int ir_id, int part, float* out_packed) {
+    if (!e || !out_packed || ir_id < 0 || ir_id >= e->n_irs || part < 0 || part >= e->ring) return fail(IRB_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out_packed, e->H.as<float2>() + ((size_t) ir_id * e->ring + part) * e->M, sizeof(float2) * e->M, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int irb_engine_read_fdl_spectrum(irb_engine* e, int chan, int age, float* out_packed) {
+    if (!e || !out_packed || chan < 0 || chan >= e->n_chans || age < 0 || age >= e->ring) return fail(IRB_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    int head = 0;
+    CK(cudaMemcpy(&head, e->head.as<int>() + chan, sizeof(int), cudaMemcpyDeviceToHost));
+    const int slot = ((head - age) % e->ring + e->ring) % e->ring;
+    CK(cudaMemcpy(out_packed, e->fdl.as<float2>() + ((size_t) chan * e->ring + slot) * e->M, sizeof(float2) * e->M, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int irb_engine_mac_only_device(irb_engine* e, float* acc_dev) {
+    if (!e || !acc_dev) return fail(IRB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->device));
+    int rc = engine_check_binding(e);
+    if (rc) return rc;
+    irb::MacArgs m{};
+    m.fdl = e->fdl.as<float2>(); m.fdl_chan_stride = (long long) e->ring * e->M;
+    m.head = e->head.as<int>(); m.ring = e->ring; m.blocks_per_chan = 1; m.n_rows = e->n_chans;
+    m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
+    m.ir_of_chan = e->ir_of_chan.as<int>(); m.nparts = e->nparts.as<int>(); m.W = e->W;
+    m.Y = (float2*) acc_dev; m.B = e->B;
+    rc = launch_mac(e->M, false, m, e->stream);
+    if (rc) return rc;
+    e->launches += 1;
+    return 0;
+}
+
+// fp::convolution::convolvePeriodic (fp/convolution.cpp:14-242) with every block processed at once:
+// all audio blocks are transformed in one launch, output block k sums X[k-p]*H[p] over the partitions
+// p <= k in ascending order (the reference's own order, :171-202), and the overlap of block k-1 is added
+// afterwards (:210-213).  Feeding zero blocks after the input ends is the reference's tail loop
+// (:150-153,166-167) because the partitions it skips there would only meet slots that hold zeros here.
+int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, int ch_h, int len_h, int block_size, float* out) {
+    if (!x || !h || !out) return fail(IRB_ERR_ARG, "null argument");
+    if (len_x < 1 || len_h < 1 || ch_x < 1 || ch_h < 1) return fail(IRB_ERR_ARG, "empty input");
+    const long long Lout = (long long) len_x + len_h - 1;
+    memset(out, 0, sizeof(float) * (size_t) ch_x * Lout);
+    if (!((ch_x == 1 || ch_x == 2) && (ch_h == 1 || ch_h == 2)))
+        return fail(IRB_ERR_LAYOUT, "audio has %d channels and the IR %d: only mono/stereo layouts exist (fp/convolution.cpp:28-42)", ch_x, ch_h);
+    const int B = block_size;
+    if (B < 1 || half_size_for_block(B) > kMaxM) return fail(IRB_ERR_ARG, "block_size %d outside [1, %d]", B, kMaxM);
+    if (Lout > 0x7fffffffLL) return fail(IRB_ERR_ARG, "output too long");
+    CK(cudaSetDevice(g_device));
+    const int M = half_size_for_block(B);
+    const float2* W = nullptr;
+    int rc = g_tw.get(g_device, M, &W);
+    if (rc) return rc;
+    const int P = (int) std::ceil((float) len_h / (float) B);
+    const int iters = len_x / B + P;                       // the do-while of :104-233
+    const int rows = tile_rows(M);
+    const int bpc = (iters + rows - 1) / rows * rows;      // padded so no tile straddles two channels
+    const bool fold = (ch_h == 2 && ch_x == 1);            // IRStereoAudioMono: (L+R)/2, :120-121
+    const int n_ir = (ch_h == 2 && ch_x == 2) ? 2 : 1;     // IRStereoAudioStereo is channel-wise, :176-181
+    const long long Lw = Lout < (long long) iters * B ? Lout : (long long) iters * B;   // the tail is never flushed, :233-238
+
+    cudaStream_t st = nullptr;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{st};
+    DevBuf dx, dh, dX, dH, dout, dtail, dnp, dir;
+    const size_t spec = sizeof(float2) * (size_t) M;
+    if ((rc = dx.alloc(sizeof(float) * (size_t) ch_x * len_x, false)) || (rc = dh.alloc(sizeof(float) * (size_t) ch_h * len_h, false)) ||
+        (rc = dX.alloc(spec * bpc * ch_x, false)) || (rc = dH.alloc(spec * P * n_ir, false)) ||
+        (rc = dout.alloc(sizeof(float) * (size_t) ch_x * Lout, true)) || (rc = dtail.alloc(sizeof(float) * (size_t) B * bpc * ch_x, false)) ||
+        (rc = dnp.alloc(sizeof(int) * 2, false)) || (rc = dir.alloc(sizeof(int) * 2, false)))
+        return rc;
+    CK(cudaMemcpyAsync(dx.p, x, sizeof(float) * (size_t) ch_x * len_x, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dh.p, h, sizeof(float) * (size_t) ch_h * len_h, cudaMemcpyHostToDevice, st));
+    const int np[2] = {P, P};
+    const int irmap[2] = {0, n_ir == 2 ? 1 : 0};
+    CK(cudaMemcpyAsync(dnp.p, np, sizeof(np), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dir.p, irmap, sizeof(irmap), cudaMemcpyHostToDevice, st));
+
+    irb::FwdArgs fh{};                                      // IR partitions
+    fh.src = dh.as<float>(); fh.src2 = fold ? dh.as<float>() + len_h : nullptr; fh.src_chan_stride = len_h; fh.L = len_h; fh.B = B;
+    fh.blocks_per_chan = P; fh.n_rows = P * n_ir; fh.dst = dH.as<float2>(); fh.dst_chan_stride = (long long) P * M; fh.W = W;
+    if ((rc = launch_fwd(M, fh, st))) return rc;
+    irb::FwdArgs fx{};                                      // audio blocks (blocks past the input are zero)
+    fx.src = dx.as<float>(); fx.src_chan_stride = len_x; fx.L = len_x; fx.B = B;
+    fx.blocks_per_chan = bpc; fx.n_rows = bpc * ch_x; fx.dst = dX.as<float2>(); fx.dst_chan_stride = (long long) bpc * M; fx.W = W;
+    if ((rc = launch_fwd(M, fx, st))) return rc;
+    irb::MacArgs m{};
+    m.fdl = dX.as<float2>(); m.fdl_chan_stride = (long long) bpc * M; m.head = nullptr; m.ring = bpc; m.blocks_per_chan = bpc;
+    m.n_rows = bpc * ch_x; m.H = dH.as<float2>(); m.ir_stride = (long long) P * M; m.ir_of_chan = dir.as<int>(); m.nparts = dnp.as<int>();
+    m.W = W; m.B = B; m.out = dout.as<float>(); m.out_chan_stride = Lout; m.Lout = (int) Lw; m.ov = nullptr; m.tail = dtail.as<float>();
+    if ((rc = launch_mac(M, true, m, st))) return rc;
+    {
+        const long long n = (long long) bpc * B * ch_x;
+        irb::k_ola_tail<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(dout.as<float>(), Lout, (int) Lw, dtail.as<float>(), B, bpc, ch_x);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(out, dout.p, sizeof(float) * (size_t) ch_x * Lout, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+"""ctypes binding of libirb_b200.so (include/irb_b200.h) -- the host-side driver used by tests and bench.py.
+
+This module is plumbing: it loads the C-ABI library, turns its status codes into exceptions and moves numpy
+arrays (or raw device pointers from torch) across the boundary.  All arithmetic happens in the CUDA library;
+there is no CPU fallback here -- if the library is missing, or no B200 is visible, calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libirb_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "irb_b200.h")
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_vp = ctypes.c_void_p
+_lib = None
+
+
+class IrbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("irb status %d: %s" % (code, msg))
+        self.code = code
+
+
+IRB_ERR_ARG, IRB_ERR_LAYOUT, IRB_ERR_CUDA, IRB_ERR_STATE = -1, -2, -3, -4
+
+_SIGS = {
+    "irb_last_error": (ctypes.c_char_p, []),
+    "irb_version": (ctypes.c_int, []),
+    "irb_device_count": (ctypes.c_int, []),
+    "irb_set_device": (ctypes.c_int, [ctypes.c_int]),
+    "irb_max_block_size": (ctypes.c_int, []),
+    "irb_host_alloc": (_vp, [ctypes.c_size_t]),
+    "irb_host_free": (None, [_vp]),
+    "irb_engine_create": (ctypes.c_int, [ctypes.POINTER(_vp)] + [ctypes.c_int] * 5),
+    "irb_engine_destroy": (ctypes.c_int, [_vp]),
+    "irb_engine_set_stream": (ctypes.c_int, [_vp, _vp]),
+    "irb_engine_set_ir": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int]),
+    "irb_engine_bind": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "irb_engine_tile_channels": (ctypes.c_int, [_vp]),
+    "irb_engine_reset": (ctypes.c_int, [_vp]),
+    "irb_engine_process": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
+    "irb_engine_process_device": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
+    "irb_engine_synchronize": (ctypes.c_int, [_vp]),
+    "irb_engine_state_bytes": (ctypes.c_size_t, [_vp]),
+    "irb_engine_fft_size": (ctypes.c_int, [_vp]),
+    "irb_engine_partitions": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "irb_engine_read_ir_spectrum": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_engine_read_fdl_spectrum": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_engine_launch_count": (ctypes.c_longlong, [_vp]),
+    "irb_launch_count": (ctypes.c_longlong, []),
+    "irb_engine_mac_only_device": (ctypes.c_int, [_vp, _vp]),
+    "irb_convolve_periodic": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+}
+
+
+def lib():
+    """Load libirb_b200.so; raises if it has not been built (python -m irbaboon_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(LIB_PATH + " is missing: run `python -m irbaboon_b200.build` (there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc < 0:
+        raise IrbError(rc, lib().irb_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+def _planar(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a[None, :] if a.ndim == 1 else a
+
+
+def device_count():
+    return _ck(lib().irb_device_count())
+
+
+def set_device(device):
+    _ck(lib().irb_set_device(int(device)))
+
+
+def launch_count():
+    return lib().irb_launch_count()
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """numpy array over cudaMallocHost memory (freed when the array's base is collected)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib().irb_host_alloc(n)
+    if not p:
+        raise IrbError(IRB_ERR_CUDA, lib().irb_last_error().decode())
+    buf = (ctypes.c_char * n).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED[arr.__array_interface__["data"][0]] = p
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr):
+    p = _PINNED.pop(arr.__array_interface__["data"][0], None)
+    if p:
+        lib().irb_host_free(p)
+
+
+def convolve_periodic(x, h, block_size=256):
+    """fp::convolution::convolvePeriodic (fp/convolution.cpp:14-242): planar [ch][n] float32 in and out."""
+    x, h = _planar(x), _planar(h)
+    out = np.zeros((x.shape[0], x.shape[1] + h.shape[1] - 1), np.float32)
+    rc = lib().irb_convolve_periodic(_ptr(x), x.shape[0], x.shape[1], _ptr(h), h.shape[0], h.shape[1], int(block_size), _ptr(out))
+    if rc == IRB_ERR_LAYOUT:
+        return out                      # the reference prints a DBG line and returns the cleared buffer
+    _ck(rc)
+    return out
+
+
+class Engine:
+    """Streaming UPOLA engine over n_channels independent stream-channels on one GPU."""
+
+    def __init__(self, block_size, max_partitions, n_channels, n_irs=1, device=0):
+        self._h = _vp()
+        _ck(lib().irb_engine_create(ctypes.byref(self._h), int(device), int(block_size), int(max_partitions), int(n_channels), int(n_irs)))
+        self.block_size, self.max_partitions, self.n_channels, self.n_irs, self.device = block_size, max_partitions, n_channels, n_irs, device
+        self.fft_size = lib().irb_engine_fft_size(self._h)
+
+    def close(self):
+        if self._h:
+            lib().irb_engine_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream):
+        _ck(lib().irb_engine_set_stream(self._h, _vp(int(cuda_stream)) if cuda_stream else None))
+
+    def set_ir(self, ir_id, taps):
+        """taps: [n] mono, or [2][n] stereo folded to (L+R)/2."""
+        t = _planar(taps)
+        if t.shape[0] == 1:
+            _ck(lib().irb_engine_set_ir(self._h, int(ir_id), _ptr(t), None, t.shape[1]))
+        elif t.shape[0] == 2:
+            l, r = np.ascontiguousarray(t[0]), np.ascontiguousarray(t[1])
+            _ck(lib().irb_engine_set_ir(self._h, int(ir_id), _ptr(l), _ptr(r), t.shape[1]))
+        else:
+            raise ValueError("IR must be mono or stereo")
+
+    def bind(self, chan_begin, chan_end, ir_id):
+        _ck(lib().irb_engine_bind(self._h, int(chan_begin), int(chan_end), int(ir_id)))
+
+    @property
+    def tile_channels(self):
+        return lib().irb_engine_tile_channels(self._h)
+
+    def reset(self):
+        _ck(lib().irb_engine_reset(self._h))
+
+    def process(self, x, out=None):
+        """x: host [n_blocks][n_channels][B] (or [n_channels][B]); returns the same shape."""
+        x = np.ascontiguousarray(x, np.float32)
+        shp = x.shape
+        nb = 1 if x.ndim == 2 else shp[0]
+        assert shp[-2:] == (self.n_channels, self.block_size), shp
+        if out is None:
+            out = np.empty(shp, np.float32)
+        _ck(lib().irb_engine_process(self._h, _ptr(x), _ptr(out), nb))
+        return out
+
+    def process_device(self, in_ptr, out_ptr, n_blocks=1):
+        _ck(lib().irb_engine_process_device(self._h, _vp(int(in_ptr)), _vp(int(out_ptr)), int(n_blocks)))
+
+    def mac_only_device(self, acc_ptr):
+        _ck(lib().irb_engine_mac_only_device(self._h, _vp(int(acc_ptr))))
+
+    def synchronize(self):
+        _ck(lib().irb_engine_synchronize(self._h))
+
+    def process_stream(self, x):
+        """Convenience for tests: planar audio x[n_channels][n] -> y[n_channels][n] block by block
+        (n is padded up to whole blocks with zeros and cut back)."""
+        x = _planar(x)
+        B = self.block_size
+        n = x.shape[1]
+        nb = (n + B - 1) // B
+        xp = np.zeros((self.n_channels, nb * B), np.float32)
+        xp[:, :n] = x
+        blocks = np.ascontiguousarray(xp.reshape(self.n_channels, nb, B).transpose(1, 0, 2))
+        y = self.process(blocks)
+        return np.ascontiguousarray(y.transpose(1, 0, 2)).reshape(self.n_channels, nb * B)[:, :n]
+
+    @property
+    def state_bytes(self):
+        return lib().irb_engine_state_bytes(self._h)
+
+    def partitions(self, ir_id=0):
+        return _ck(lib().irb_engine_partitions(self._h, int(ir_id)))
+
+    @property
+    def launches(self):
+        return lib().irb_engine_launch_count(self._h)
+
+    def ir_spectrum(self, ir_id, part):
+        out = np.zeros(self.fft_size, np.float32)
+        _ck(lib().irb_engine_read_ir_spectrum(self._h, int(ir_id), int(part), _ptr(out)))
+        return out
+
+    def fdl_spectrum(self, chan, age=0):
+        out = np.zeros(self.fft_size, np.float32)
+        _ck(lib().irb_engine_read_fdl_spectrum(self._h, int(chan), int(age), _ptr(out)))
+        return out
+
+
+def unpack_spectrum(packed):
+    """packed M complex (bin 0 = {Re X[0], Re X[M]}) -> M+1 complex bins."""
+    p = np.asarray(packed, np.float32)
+    M = p.size // 2
+    z = (p[0::2] + 1j * p[1::2]).astype(np.complex64)
+    out = np.zeros(M + 1, np.complex64)
+    out[1:M] = z[1:]
+    out[0] = z[0].real
+    out[M] = z[0].imag
+    return out
