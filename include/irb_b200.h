@@ -55,7 +55,9 @@ void irb_host_free(void* p);
  */
 int irb_engine_create(irb_engine** out, int device, int block_size, int max_partitions, int n_channels, int n_irs);
 int irb_engine_destroy(irb_engine* e);
-/* run on a caller-owned CUDA stream (cudaStream_t / CUstream); NULL restores the engine's own stream */
+/* run on a caller-owned CUDA stream (cudaStream_t / CUstream; NULL is the legacy default stream);
+ * IRB_OWN_STREAM restores the engine's own non-blocking stream */
+#define IRB_OWN_STREAM ((void*) (~(size_t) 0))
 int irb_engine_set_stream(irb_engine* e, void* cuda_stream);
 
 /* Partition, zero-pad and transform an impulse response (fp/convolution.cpp:106-125 /
@@ -76,6 +78,11 @@ int irb_engine_reset(irb_engine* e);
 int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int n_blocks);
 int irb_engine_process_device(irb_engine* e, const float* in_dev, float* out_dev, int n_blocks);
 int irb_engine_synchronize(irb_engine* e);
+
+/* Per-step device timing with CUDA events on the engine's stream: whole block step (k_fwd + k_mac) and the
+ * FDL-MAC kernel alone.  set_timing(1) clears the record; get_timings returns the number of steps copied. */
+int irb_engine_set_timing(irb_engine* e, int enable);
+int irb_engine_get_timings(irb_engine* e, float* step_ms, float* mac_ms, int max_steps);
 
 /* introspection (tests, benchmarks) */
 size_t irb_engine_state_bytes(const irb_engine* e);            /* device bytes held */

@@ -140,11 +140,28 @@ struct irb_engine {
     int device = 0, B = 0, M = 0, ring = 0, n_chans = 0, n_irs = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     const float2* W = nullptr;
-    DevBuf fdl, H, ov, head, ir_of_chan, nparts, io_in, io_out, taps;
+    DevBuf fdl, H, ov, head, ir_of_chan, nparts, io_in[2], io_out[2], taps;
     std::vector<int> h_ir_of_chan, h_nparts;
     bool binding_dirty = true;
     size_t bytes = 0;
     long long launches = 0;
+    // host path: copy streams + events so block b+1 uploads and block b-1 downloads while block b computes
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    // optional per-step device timing: events before k_fwd, before k_mac, after k_mac
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;
+    int t_rec = 0;
+    ~irb_engine() {
+        for (auto ev : tev) cudaEventDestroy(ev);
+        for (int i = 0; i < 2; ++i) {
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+    }
 };
 
 namespace {
@@ -162,7 +179,11 @@ int engine_check_binding(irb_engine* e) {
     return 0;
 }
 
+constexpr int kTimingCap = 16384;
+
 int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
+    const bool rec = e->timing && e->t_rec < kTimingCap;
+    if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec], e->stream));
     irb::FwdArgs f{};
     f.src = in_dev; f.src2 = nullptr; f.src_chan_stride = e->B; f.L = e->B; f.B = e->B;
     f.blocks_per_chan = 1; f.n_rows = e->n_chans;
@@ -170,6 +191,7 @@ int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
     f.head = e->head.as<int>(); f.ring = e->ring; f.W = e->W;
     int rc = launch_fwd(e->M, f, e->stream);
     if (rc) return rc;
+    if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec + 1], e->stream));
     irb::MacArgs m{};
     m.fdl = e->fdl.as<float2>(); m.fdl_chan_stride = (long long) e->ring * e->M;
     m.head = e->head.as<int>(); m.ring = e->ring; m.blocks_per_chan = 1; m.n_rows = e->n_chans;
@@ -179,6 +201,7 @@ int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
     m.ov = e->ov.as<float>(); m.tail = nullptr;
     rc = launch_mac(e->M, true, m, e->stream);
     if (rc) return rc;
+    if (rec) { CK(cudaEventRecord(e->tev[3 * e->t_rec + 2], e->stream)); e->t_rec++; }
     e->launches += 2;
     return 0;
 }
@@ -224,15 +247,23 @@ int irb_engine_create(irb_engine** out, int device, int block_size, int max_part
     const size_t b_fdl = spec * e->ring * n_channels, b_H = spec * e->ring * n_irs, b_io = sizeof(float) * (size_t) e->B * n_channels;
     if ((rc = e->fdl.alloc(b_fdl, true)) || (rc = e->H.alloc(b_H, true)) || (rc = e->ov.alloc(b_io, true)) ||
         (rc = e->head.alloc(sizeof(int) * n_channels, false)) || (rc = e->ir_of_chan.alloc(sizeof(int) * n_channels, true)) ||
-        (rc = e->nparts.alloc(sizeof(int) * n_irs, true)) || (rc = e->io_in.alloc(b_io, true)) || (rc = e->io_out.alloc(b_io, true)) ||
+        (rc = e->nparts.alloc(sizeof(int) * n_irs, true)) || (rc = e->io_in[0].alloc(b_io, true)) || (rc = e->io_out[0].alloc(b_io, true)) ||
+        (rc = e->io_in[1].alloc(b_io, true)) || (rc = e->io_out[1].alloc(b_io, true)) ||
         (rc = e->taps.alloc(sizeof(float) * 2 * (size_t) e->B * e->ring, true))) {
         delete e;
         return rc;
     }
-    e->bytes = b_fdl + b_H + 3 * b_io + sizeof(int) * (2 * (size_t) n_channels + n_irs) + sizeof(float) * 2 * (size_t) e->B * e->ring;
+    e->bytes = b_fdl + b_H + 5 * b_io + sizeof(int) * (2 * (size_t) n_channels + n_irs) + sizeof(float) * 2 * (size_t) e->B * e->ring;
     e->h_ir_of_chan.assign(n_channels, 0);
     e->h_nparts.assign(n_irs, 0);
-    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return fail(IRB_ERR_CUDA, "cudaStreamCreate failed"); }
+    bool ok = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+        ok = cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { delete e; return fail(IRB_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())); }
     e->stream = e->own_stream;
     *out = e;
     return irb_engine_reset(e);
@@ -251,7 +282,7 @@ int irb_engine_set_stream(irb_engine* e, void* cuda_stream) {
     if (!e) return fail(IRB_ERR_ARG, "engine is null");
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
-    e->stream = cuda_stream ? (cudaStream_t) cuda_stream : e->own_stream;
+    e->stream = cuda_stream == IRB_OWN_STREAM ? e->own_stream : (cudaStream_t) cuda_stream;
     return 0;
 }
 
@@ -321,13 +352,48 @@ int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int
     int rc = engine_check_binding(e);
     if (rc) return rc;
     const size_t blk = (size_t) e->B * e->n_chans;
+    // three-stage pipeline over double-buffered device staging: upload b+1 | compute b | download b-1
     for (int b = 0; b < n_blocks; ++b) {
-        CK(cudaMemcpyAsync(e->io_in.p, in_host + b * blk, sizeof(float) * blk, cudaMemcpyHostToDevice, e->stream));
-        if ((rc = engine_step_device(e, e->io_in.as<float>(), e->io_out.as<float>()))) return rc;
-        CK(cudaMemcpyAsync(out_host + b * blk, e->io_out.p, sizeof(float) * blk, cudaMemcpyDeviceToHost, e->stream));
+        const int q = b & 1;
+        if (b >= 2) CK(cudaStreamWaitEvent(e->s_in, e->ev_done[q], 0));            // compute b-2 has consumed io_in[q]
+        CK(cudaMemcpyAsync(e->io_in[q].p, in_host + b * blk, sizeof(float) * blk, cudaMemcpyHostToDevice, e->s_in));
+        CK(cudaEventRecord(e->ev_in[q], e->s_in));
+        CK(cudaStreamWaitEvent(e->stream, e->ev_in[q], 0));
+        if (b >= 2) CK(cudaStreamWaitEvent(e->stream, e->ev_out[q], 0));           // download b-2 has drained io_out[q]
+        if ((rc = engine_step_device(e, e->io_in[q].as<float>(), e->io_out[q].as<float>()))) return rc;
+        CK(cudaEventRecord(e->ev_done[q], e->stream));
+        CK(cudaStreamWaitEvent(e->s_out, e->ev_done[q], 0));
+        CK(cudaMemcpyAsync(out_host + b * blk, e->io_out[q].p, sizeof(float) * blk, cudaMemcpyDeviceToHost, e->s_out));
+        CK(cudaEventRecord(e->ev_out[q], e->s_out));
     }
+    CK(cudaStreamSynchronize(e->s_out));
     CK(cudaStreamSynchronize(e->stream));
     return 0;
+}
+
+int irb_engine_set_timing(irb_engine* e, int enable) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (enable && e->tev.empty()) {
+        e->tev.resize(3 * (size_t) kTimingCap, nullptr);
+        for (auto& ev : e->tev) CK(cudaEventCreate(&ev));
+    }
+    e->timing = enable != 0;
+    e->t_rec = 0;
+    return 0;
+}
+
+int irb_engine_get_timings(irb_engine* e, float* step_ms, float* mac_ms, int max_steps) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    const int n = e->t_rec < max_steps ? e->t_rec : max_steps;
+    for (int i = 0; i < n; ++i) {
+        if (step_ms) CK(cudaEventElapsedTime(step_ms + i, e->tev[3 * i], e->tev[3 * i + 2]));
+        if (mac_ms) CK(cudaEventElapsedTime(mac_ms + i, e->tev[3 * i + 1], e->tev[3 * i + 2]));
+    }
+    return n;
 }
 
 int irb_engine_synchronize(irb_engine* e) {

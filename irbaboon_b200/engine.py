@@ -44,6 +44,8 @@ _SIGS = {
     "irb_engine_process": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "irb_engine_process_device": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "irb_engine_synchronize": (ctypes.c_int, [_vp]),
+    "irb_engine_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "irb_engine_get_timings": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "irb_engine_state_bytes": (ctypes.c_size_t, [_vp]),
     "irb_engine_fft_size": (ctypes.c_int, [_vp]),
     "irb_engine_partitions": (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -157,7 +159,9 @@ class Engine:
         self.close()
 
     def set_stream(self, cuda_stream):
-        _ck(lib().irb_engine_set_stream(self._h, _vp(int(cuda_stream)) if cuda_stream else None))
+        """cuda_stream: a cudaStream_t handle as int (0 = legacy default stream); None = the engine's own stream."""
+        h = _vp(ctypes.c_size_t(-1).value) if cuda_stream is None else _vp(int(cuda_stream))
+        _ck(lib().irb_engine_set_stream(self._h, h))
 
     def set_ir(self, ir_id, taps):
         """taps: [n] mono, or [2][n] stereo folded to (L+R)/2."""
@@ -196,6 +200,16 @@ class Engine:
 
     def mac_only_device(self, acc_ptr):
         _ck(lib().irb_engine_mac_only_device(self._h, _vp(int(acc_ptr))))
+
+    def set_timing(self, enable=True):
+        _ck(lib().irb_engine_set_timing(self._h, int(bool(enable))))
+
+    def timings(self, max_steps=16384):
+        """(step_ms, mac_ms) device times of the steps recorded since set_timing(True)."""
+        a = np.zeros(max_steps, np.float32)
+        b = np.zeros(max_steps, np.float32)
+        n = _ck(lib().irb_engine_get_timings(self._h, _ptr(a), _ptr(b), max_steps))
+        return a[:n].copy(), b[:n].copy()
 
     def synchronize(self):
         _ck(lib().irb_engine_synchronize(self._h))
