@@ -105,6 +105,33 @@ int irb_engine_mac_only_device(irb_engine* e, float* acc_dev);
  * mono/stereo), partition count, iteration count and unflushed tail as the reference. */
 int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, int ch_h, int len_h, int block_size, float* out);
 
+
+/* fp::convolution::convolveNonPeriodic (fp/convolution.hpp:32, fp/convolution.cpp:246-347): one real FFT of
+ * N = pow2 >= len_x+len_h-1 per signal, per-bin product, inverse; out[ch_x][len_x+len_h-1].  IRB_ERR_LAYOUT for the
+ * layouts the reference rejects (it returns a cleared copy of the input there, :271-275). */
+int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h, int ch_h, int len_h, float* out);
+
+/* fp::convolution::deconvolve (fp/convolution.hpp:38, fp/convolution.cpp:351-403): spectral division
+ * FFT(num)/FFT(den) at N = nextPowerOfTwo(max(len_num, len_den)) (circular), optional 3x 1/13-octave
+ * averagingFilter, inverse FFT, ir::shifteroo when the phase is dropped.  out[N] (or [batch][N]).
+ * _batch divides `batch` numerators [batch][len_num] by one denominator: the batched ESS IR capture. */
+int irb_deconvolve(const float* num, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase, int include_amplitude,
+                   float* out);
+int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase,
+                         int include_amplitude, float* out);
+/* fp::ir::invertFilter (fp/ir.hpp:20, fp/ir.cpp:13-18); out[nextPowerOfTwo(len)] */
+int irb_invert_filter(const float* x, int len, int sample_rate, float* out);
+/* fp::convolution::averagingFilter (fp/convolution.hpp:44, fp/convolution.cpp:406-546), in place on an interleaved
+ * spectrum spec[ch][fft_size]; a fft_size that is not a power of two leaves it untouched (:412-415).  The last two
+ * flags are INCLUDE flags, as the reference's body treats them. */
+int irb_averaging_filter(float* spec, int ch, int fft_size, double octave_fraction, double sample_rate, int log_avg, int include_phase, int include_amplitude);
+/* fp::tools::fftTransform / fftInvTransform (fp/tools.hpp:88-89, fp/tools.cpp:321-369) */
+int irb_fft_transform(const float* x, int ch, int len, int format_ampl_phase, float* out /* [ch][2N] */);
+int irb_fft_inv_transform(const float* spec, int ch, int fft_size, float* out /* [ch][fft_size/2] */);
+/* fp::ExpSineSweep::generate / generateInv (fp/ExpSineSweep.hpp:27-33, fp/ExpSineSweep.cpp:26-41,59-79), FP64.
+ * Returns the sweep length (int)(sample_rate*duration); out == NULL only queries it. */
+int irb_ess_generate(double duration_s, double sample_rate, double f1, double f2, double gain_db, int inverse, double* out, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,10 +11,10 @@
 #include <vector>
 #include <atomic>
 
-#include "../../include/irb_b200.h"
+#include "irb_common.hpp"
 #include "irb_kernels.cuh"
 
-namespace {
+namespace irbh {
 
 thread_local char g_err[512] = "";
 thread_local int g_device = 0;
@@ -27,11 +27,37 @@ int fail(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
-#define CK(call)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess) return fail(IRB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
+int current_device() { return g_device; }
+
+// twiddle tables, one per (device, M), built in double like the reference FFT's tables
+int twiddles(int dev, int M, const float2** out) {
+    struct Entry { int dev, M; float2* d; };
+    static std::mutex mu;
+    static std::vector<Entry> tab;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : tab) if (e.dev == dev && e.M == M) { *out = e.d; return 0; }
+    const int N = 2 * M;
+    std::vector<float2> h(N);
+    for (int k = 0; k < N; ++k) {
+        const double ang = -2.0 * M_PI * (double) k / (double) N;
+        h[k].x = (float) cos(ang);
+        h[k].y = (float) sin(ang);
+    }
+    float2* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(float2) * N));
+    CK(cudaMemcpy(d, h.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+    tab.push_back({dev, M, d});
+    *out = d;
+    return 0;
+}
+
+}  // namespace irbh
+
+namespace {
+
+using irbh::fail;
+using irbh::DevBuf;
+using irbh::g_launches;
 
 // FFT half-size M for a block size: N = smallest power of two >= 2B-1 (fp/convolution.cpp:45-48), M = N/2,
 // never below 16 (a longer zero-padded transform gives the same linear convolution).
@@ -42,30 +68,6 @@ int half_size_for_block(int B) {
     return M < 16 ? 16 : M;
 }
 constexpr int kMaxM = 2048;
-
-// twiddle tables, one per (device, M), built in double like the reference FFT's tables
-struct Twiddles {
-    std::mutex mu;
-    struct Entry { int dev, M; float2* d; };
-    std::vector<Entry> tab;
-    int get(int dev, int M, const float2** out) {
-        std::lock_guard<std::mutex> lk(mu);
-        for (auto& e : tab) if (e.dev == dev && e.M == M) { *out = e.d; return 0; }
-        const int N = 2 * M;
-        std::vector<float2> h(N);
-        for (int k = 0; k < N; ++k) {
-            const double ang = -2.0 * M_PI * (double) k / (double) N;
-            h[k].x = (float) cos(ang);
-            h[k].y = (float) sin(ang);
-        }
-        float2* d = nullptr;
-        CK(cudaMalloc(&d, sizeof(float2) * N));
-        CK(cudaMemcpy(d, h.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
-        tab.push_back({dev, M, d});
-        *out = d;
-        return 0;
-    }
-} g_tw;
 
 // partitions per IR ring stage (= FDL loads batched per thread): 1 or 2; IRB_MAC_U overrides for tuning
 int mac_u_pref() {
@@ -123,16 +125,6 @@ int launch_mac(int M, bool inv, const irb::MacArgs& a, cudaStream_t st) {
 }
 int tile_rows(int M) { return irb::kTile / M; }
 
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes, bool zero) {
-        CK(cudaMalloc(&p, bytes ? bytes : 16));
-        if (zero) CK(cudaMemset(p, 0, bytes ? bytes : 16));
-        return 0;
-    }
-    template <typename T> T* as() const { return (T*) p; }
-};
 
 }  // namespace
 
@@ -210,7 +202,7 @@ int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
 
 extern "C" {
 
-const char* irb_last_error(void) { return g_err; }
+const char* irb_last_error(void) { return irbh::g_err; }
 int irb_version(void) { return 100; }
 int irb_device_count(void) {
     int n = 0;
@@ -219,7 +211,7 @@ int irb_device_count(void) {
 }
 int irb_set_device(int device) {
     CK(cudaSetDevice(device));
-    g_device = device;
+    irbh::g_device = device;
     return 0;
 }
 int irb_max_block_size(void) { return kMaxM; }
@@ -241,7 +233,7 @@ int irb_engine_create(irb_engine** out, int device, int block_size, int max_part
     if (!e) return fail(IRB_ERR_ARG, "out of host memory");
     e->device = device; e->B = block_size; e->M = half_size_for_block(block_size);
     e->ring = max_partitions; e->n_chans = n_channels; e->n_irs = n_irs;
-    int rc = g_tw.get(device, e->M, &e->W);
+    int rc = irbh::twiddles(device, e->M, &e->W);
     if (rc) { delete e; return rc; }
     const size_t spec = sizeof(float2) * (size_t) e->M;
     const size_t b_fdl = spec * e->ring * n_channels, b_H = spec * e->ring * n_irs, b_io = sizeof(float) * (size_t) e->B * n_channels;
@@ -461,10 +453,10 @@ int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, i
     const int B = block_size;
     if (B < 1 || half_size_for_block(B) > kMaxM) return fail(IRB_ERR_ARG, "block_size %d outside [1, %d]", B, kMaxM);
     if (Lout > 0x7fffffffLL) return fail(IRB_ERR_ARG, "output too long");
-    CK(cudaSetDevice(g_device));
+    CK(cudaSetDevice(irbh::g_device));
     const int M = half_size_for_block(B);
     const float2* W = nullptr;
-    int rc = g_tw.get(g_device, M, &W);
+    int rc = irbh::twiddles(irbh::g_device, M, &W);
     if (rc) return rc;
     const int P = (int) std::ceil((float) len_h / (float) B);
     const int iters = len_x / B + P;                       // the do-while of :104-233

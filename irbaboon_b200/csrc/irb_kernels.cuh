@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
 }
 
 // offline: out[chan][blk*B + m] += tail[chan][blk-1][m]   (the overlap of the previous block)
-__global__ void k_ola_tail(float* out, long long out_chan_stride, int Lout, const float* tail, int B, int blocks_per_chan, int n_chans) {
+static __global__ void k_ola_tail(float* out, long long out_chan_stride, int Lout, const float* tail, int B, int blocks_per_chan, int n_chans) {
     const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     const long long per_chan = (long long) blocks_per_chan * B;
     if (i >= per_chan * n_chans) return;

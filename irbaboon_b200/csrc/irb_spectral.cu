@@ -1,0 +1,369 @@
+// irb_spectral.cu -- host side of the single-large-FFT entry points of include/irb_b200.h:
+// irb_convolve_nonperiodic, irb_deconvolve(_batch), irb_averaging_filter, irb_fft_transform,
+// irb_fft_inv_transform, irb_invert_filter, irb_ess_generate.  Every arithmetic step is a kernel of
+// irb_spectral.cuh; the host only sizes buffers, copies and launches.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "irb_common.hpp"
+#include "irb_spectral.cuh"
+
+namespace {
+
+using irbh::DevBuf;
+using irbh::fail;
+using irbh::g_launches;
+
+constexpr int kMinM = 8;                 // smallest half size the Stockham passes take (N = 16)
+constexpr int kMaxBigM = 1 << 20;        // N up to 2^21
+
+template <int L, bool INV>
+int launch_line_t(const irb::LineArgs& a, int batch, cudaStream_t st) {
+    using T = irb::LineTile<L>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CK(cudaFuncSetAttribute(irb::k_line_fft<L, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T::SMEM));
+        configured_dev = dev;
+    }
+    dim3 grid((a.n_lines + T::C - 1) / T::C, batch);
+    irb::k_line_fft<L, INV><<<grid, irb::kThreads, T::SMEM, st>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int launch_line(int L, bool inv, const irb::LineArgs& a, int batch, cudaStream_t st) {
+#define IRB_LINE_CASE(LL) case LL: return inv ? launch_line_t<LL, true>(a, batch, st) : launch_line_t<LL, false>(a, batch, st);
+    switch (L) {
+        IRB_LINE_CASE(8) IRB_LINE_CASE(16) IRB_LINE_CASE(32) IRB_LINE_CASE(64) IRB_LINE_CASE(128) IRB_LINE_CASE(256)
+        IRB_LINE_CASE(512) IRB_LINE_CASE(1024) IRB_LINE_CASE(2048)
+        default: return fail(IRB_ERR_ARG, "unsupported FFT line length %d", L);
+    }
+#undef IRB_LINE_CASE
+}
+
+// M-point complex FFT plan: one pass for M <= 2048, else M = M1 * M2 (both in [64, 1024])
+struct Plan {
+    int M = 0, M1 = 1, M2 = 0;
+    const float2 *W1 = nullptr, *W2 = nullptr, *WN = nullptr;   // WN: table of the N = 2M roots when M <= 2048, else null (computed in double)
+    int init(int dev, int M_) {
+        M = M_;
+        if (M < kMinM || M > kMaxBigM || (M & (M - 1))) return fail(IRB_ERR_ARG, "FFT half size %d outside [%d, %d] or not a power of two", M, kMinM, kMaxBigM);
+        int rc;
+        if (M <= 2048) {
+            M1 = 1; M2 = M;
+            if ((rc = irbh::twiddles(dev, M, &W2))) return rc;
+            WN = W2;                                             // the same table: 2M roots
+        } else {
+            int lg = 0;
+            while ((1 << lg) < M) ++lg;
+            M1 = 1 << (lg / 2);
+            M2 = M / M1;
+            if ((rc = irbh::twiddles(dev, M1, &W1)) || (rc = irbh::twiddles(dev, M2, &W2))) return rc;
+        }
+        return 0;
+    }
+    // batch items at in + b*in_stride -> out + b*out_stride (float2 units); real_len >= 0: `in` is real data.
+    // tmp: M complex per batch item (two-pass only; may alias neither in nor out)
+    int run(const void* in, long long in_stride, int real_len, float2* out, long long out_stride, float2* tmp, int batch, bool inv, float scale,
+            cudaStream_t st) const {
+        irb::LineArgs a{};
+        if (M1 == 1) {                                           // batch items are the lines
+            a.in = in; a.out = out; a.in_elem_stride = 1; a.in_line_stride = in_stride; a.in_batch_stride = 0;
+            a.out_elem_stride = 1; a.out_line_stride = out_stride; a.out_batch_stride = 0;
+            a.n_lines = batch; a.in_real_len = real_len; a.tw_M = 0; a.scale = scale; a.W = W2;
+            if (real_len >= 0 && batch > 1) {
+                // the real-input bounds check is per batch item: run items one grid.y slice each
+                a.in_line_stride = 0; a.in_batch_stride = in_stride; a.out_line_stride = 0; a.out_batch_stride = out_stride; a.n_lines = 1;
+                return launch_line(M2, inv, a, batch, st);
+            }
+            return launch_line(M2, inv, a, 1, st);
+        }
+        // pass 1: M2 column transforms of length M1 (element n1 of line n2 at n1*M2 + n2), twiddle exp(-+2 pi i n2 k1 / M)
+        a.in = in; a.out = tmp; a.in_elem_stride = M2; a.in_line_stride = 1; a.in_batch_stride = in_stride;
+        a.out_elem_stride = M2; a.out_line_stride = 1; a.out_batch_stride = M;
+        a.n_lines = M2; a.in_real_len = real_len; a.tw_M = M; a.scale = 1.0f; a.W = W1;
+        int rc = launch_line(M1, inv, a, batch, st);
+        if (rc) return rc;
+        // pass 2: M1 row transforms of length M2 (line k1 at k1*M2), bin k1 + M1*k2 written in natural order
+        a.in = tmp; a.out = out; a.in_elem_stride = 1; a.in_line_stride = M2; a.in_batch_stride = M;
+        a.out_elem_stride = M1; a.out_line_stride = 1; a.out_batch_stride = out_stride;
+        a.n_lines = M1; a.in_real_len = -1; a.tw_M = 0; a.scale = scale; a.W = W2;
+        return launch_line(M2, inv, a, batch, st);
+    }
+};
+
+inline dim3 grid1(long long n, int batch) { return dim3((unsigned) ((n + 255) / 256), (unsigned) batch); }
+#define LAUNCHED() do { g_launches++; CK(cudaGetLastError()); } while (0)
+
+// three smoothing passes on interleaved spectra S[batch][>= M+1] (fp/convolution.cpp:389-394 calls this 3x with 1/13 octave)
+int averaging_pass(float2* S, long long s_stride, int batch, int M, double octave_fraction, double sample_rate, int log_avg, int include_phase,
+                   int include_ampl, float* la, float* rs, int* lo, int* hi, cudaStream_t st) {
+    const double fract_per_side = octave_fraction / 2.0;
+    const double nyquist = sample_rate / 2;
+    const double freq_per_bin = nyquist / (double) M;                  // fp/convolution.cpp:425 (N/2 complex bins up to Nyquist)
+    const double c_side = pow(2.0, fract_per_side);
+    const long long stride = M + 1;
+    irb::k_avg_prepare<<<grid1(M + 1, batch), 256, 0, st>>>(S, s_stride, la, stride, lo, hi, M, log_avg, freq_per_bin, c_side);
+    LAUNCHED();
+    if (log_avg) irb::k_avg_scan<<<batch, 32, 0, st>>>(la, stride, lo, hi, rs, stride, M);
+    else irb::k_avg_linear_sum<<<grid1(M + 1, batch), 256, 0, st>>>(la, stride, lo, hi, rs, stride, M);
+    LAUNCHED();
+    irb::k_avg_apply<<<grid1(M + 1, batch), 256, 0, st>>>(S, s_stride, rs, stride, lo, hi, M, log_avg, include_phase, include_ampl);
+    LAUNCHED();
+    return 0;
+}
+
+struct SmoothBufs {
+    DevBuf la, rs, lo, hi;
+    int alloc(int M, int batch) {
+        int rc;
+        if ((rc = la.alloc(sizeof(float) * (size_t) (M + 1) * batch, false)) || (rc = rs.alloc(sizeof(float) * (size_t) (M + 1) * batch, false)) ||
+            (rc = lo.alloc(sizeof(int) * (size_t) (M + 1), false)) || (rc = hi.alloc(sizeof(int) * (size_t) (M + 1), false)))
+            return rc;
+        return 0;
+    }
+};
+
+int fft_size_for(int len, int* N) {
+    int n = irbh::next_pow2(len);
+    if (n < 2 * kMinM) return fail(IRB_ERR_ARG, "length %d gives an FFT of %d points; the device transforms start at %d", len, n, 2 * kMinM);
+    if (n > 2 * kMaxBigM) return fail(IRB_ERR_ARG, "length %d needs an FFT above 2^21 points", len);
+    *N = n;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// fp::convolution::convolveNonPeriodic (fp/convolution.cpp:246-347)
+int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h, int ch_h, int len_h, float* out) {
+    if (!x || !h || !out) return fail(IRB_ERR_ARG, "null argument");
+    if (len_x < 1 || len_h < 1 || ch_x < 1 || ch_h < 1) return fail(IRB_ERR_ARG, "empty input");
+    if (!((ch_x == 1 || ch_x == 2) && (ch_h == 1 || ch_h == 2)))
+        return fail(IRB_ERR_LAYOUT, "audio has %d channels and the IR %d: only mono/stereo layouts exist (fp/convolution.cpp:259-275)", ch_x, ch_h);
+    const long long Lout = (long long) len_x + len_h - 1;
+    int N = 1;
+    while (N < Lout) { N *= 2; if (N > 2 * kMaxBigM) return fail(IRB_ERR_ARG, "result of %lld samples needs an FFT above 2^21 points", Lout); }
+    if (N < 2 * kMinM) N = 2 * kMinM;                    // a longer zero-padded transform yields the same linear convolution
+    const int M = N / 2, dev = irbh::current_device();
+    CK(cudaSetDevice(dev));
+    Plan plan;
+    int rc = plan.init(dev, M);
+    if (rc) return rc;
+    irbh::StreamGuard sg;
+    if ((rc = sg.create())) return rc;
+    cudaStream_t st = sg.s;
+    const bool fold = ch_h == 2 && ch_x == 1;            // IRStereoAudioMono -> sumToMono (:302)
+    const int n_ir = (ch_h == 2 && ch_x == 2) ? 2 : 1;   // IRStereoAudioStereo is channel-wise (:320-323)
+    const long long lxe = (len_x + 1) & ~1LL, lhe = (len_h + 1) & ~1LL;     // even strides keep float2 loads aligned
+    DevBuf dx, dh, dhf, Zx, Zh, tmp, dy;
+    if ((rc = dx.alloc(sizeof(float) * lxe * ch_x, true)) || (rc = dh.alloc(sizeof(float) * lhe * ch_h, true)) || (rc = dhf.alloc(sizeof(float) * lhe, true)) ||
+        (rc = Zx.alloc(sizeof(float2) * (size_t) M * ch_x, false)) || (rc = Zh.alloc(sizeof(float2) * (size_t) M * n_ir, false)) ||
+        (rc = tmp.alloc(sizeof(float2) * (size_t) M * 2, false)) || (rc = dy.alloc(sizeof(float2) * (size_t) M * ch_x, false)))
+        return rc;
+    for (int c = 0; c < ch_x; ++c) CK(cudaMemcpyAsync(dx.as<float>() + c * lxe, x + (size_t) c * len_x, sizeof(float) * len_x, cudaMemcpyHostToDevice, st));
+    for (int c = 0; c < ch_h; ++c) CK(cudaMemcpyAsync(dh.as<float>() + c * lhe, h + (size_t) c * len_h, sizeof(float) * len_h, cudaMemcpyHostToDevice, st));
+    const float* hsrc = dh.as<float>();
+    if (fold) {
+        irb::k_fold_mono<<<grid1(len_h, 1), 256, 0, st>>>(dh.as<float>(), dh.as<float>() + lhe, dhf.as<float>(), len_h);
+        LAUNCHED();
+        hsrc = dhf.as<float>();
+    }
+    if ((rc = plan.run(dx.p, lxe / 2, len_x, Zx.as<float2>(), M, tmp.as<float2>(), ch_x, false, 1.0f, st))) return rc;
+    if ((rc = plan.run(hsrc, lhe / 2, len_h, Zh.as<float2>(), M, tmp.as<float2>(), n_ir, false, 1.0f, st))) return rc;
+    // per channel: bins of the audio times bins of its IR (fp/convolution.cpp:326-335), in place on Zx
+    irb::k_spec_fused<false><<<grid1(M / 2 + 1, ch_x), 256, 0, st>>>(Zx.as<float2>(), M, Zh.as<float2>(), n_ir == 2 ? M : 0, Zx.as<float2>(), M, M, plan.WN);
+    LAUNCHED();
+    if ((rc = plan.run(Zx.p, M, -1, dy.as<float2>(), M, tmp.as<float2>(), ch_x, true, 1.0f / (float) N, st))) return rc;
+    for (int c = 0; c < ch_x; ++c)
+        CK(cudaMemcpyAsync(out + (size_t) c * Lout, dy.as<float>() + (size_t) c * N, sizeof(float) * Lout, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// fp::convolution::deconvolve (fp/convolution.cpp:351-403) for `batch` numerators against one denominator.
+// nums: [batch][len_num] (channel 0 of each capture, as tools::fftTransform reads only channel 0, fp/tools.cpp:328)
+// out: [batch][N], N = nextPowerOfTwo(max(len_num, len_den))
+int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase,
+                         int include_amplitude, float* out) {
+    if (!nums || !den || !out) return fail(IRB_ERR_ARG, "null argument");
+    if (batch < 1 || len_num < 1 || len_den < 1) return fail(IRB_ERR_ARG, "empty input");
+    int N = 0, rc;
+    if ((rc = fft_size_for(len_num > len_den ? len_num : len_den, &N))) return rc;
+    const int M = N / 2, dev = irbh::current_device();
+    CK(cudaSetDevice(dev));
+    Plan plan;
+    if ((rc = plan.init(dev, M))) return rc;
+    irbh::StreamGuard sg;
+    if ((rc = sg.create())) return rc;
+    cudaStream_t st = sg.s;
+    const long long lne = (len_num + 1) & ~1LL, lde = (len_den + 1) & ~1LL;
+    // work on chunks of the batch so that device memory stays bounded (about 6 N floats per item)
+    const int chunk = (int) std::max<long long>(1, std::min<long long>(batch, (8LL << 30) / (sizeof(float) * 8LL * N)));
+    DevBuf dn, dd, Zn, Zd, tmp, S, Sd, dy, dy2;
+    SmoothBufs sm;
+    if ((rc = dn.alloc(sizeof(float) * lne * chunk, true)) || (rc = dd.alloc(sizeof(float) * lde, true)) || (rc = Zn.alloc(sizeof(float2) * (size_t) M * chunk, false)) ||
+        (rc = Zd.alloc(sizeof(float2) * (size_t) M, false)) || (rc = tmp.alloc(sizeof(float2) * (size_t) M * chunk, false)) ||
+        (rc = dy.alloc(sizeof(float2) * (size_t) M * chunk, false)))
+        return rc;
+    if (smoothing && ((rc = S.alloc(sizeof(float2) * (size_t) (M + 1) * chunk, false)) || (rc = Sd.alloc(sizeof(float2) * (size_t) (M + 1), false)) || (rc = sm.alloc(M, chunk))))
+        return rc;
+    if (!include_phase && (rc = dy2.alloc(sizeof(float) * (size_t) N * chunk, false))) return rc;
+    CK(cudaMemcpyAsync(dd.p, den, sizeof(float) * len_den, cudaMemcpyHostToDevice, st));
+    if ((rc = plan.run(dd.p, lde / 2, len_den, Zd.as<float2>(), M, tmp.as<float2>(), 1, false, 1.0f, st))) return rc;
+    if (smoothing) {
+        irb::k_spec_split<<<grid1(M + 1, 1), 256, 0, st>>>(Zd.as<float2>(), M, Sd.as<float2>(), M + 1, M, 0, plan.WN);
+        LAUNCHED();
+    }
+    for (int b0 = 0; b0 < batch; b0 += chunk) {
+        const int nb = std::min(chunk, batch - b0);
+        CK(cudaMemcpy2DAsync(dn.p, sizeof(float) * lne, nums + (size_t) b0 * len_num, sizeof(float) * len_num, sizeof(float) * len_num, nb, cudaMemcpyHostToDevice, st));
+        if ((rc = plan.run(dn.p, lne / 2, len_num, Zn.as<float2>(), M, tmp.as<float2>(), nb, false, 1.0f, st))) return rc;
+        if (!smoothing) {
+            irb::k_spec_fused<true><<<grid1(M / 2 + 1, nb), 256, 0, st>>>(Zn.as<float2>(), M, Zd.as<float2>(), 0, Zn.as<float2>(), M, M, plan.WN);
+            LAUNCHED();
+        } else {
+            irb::k_spec_split<<<grid1(M + 1, nb), 256, 0, st>>>(Zn.as<float2>(), M, S.as<float2>(), M + 1, M, 0, plan.WN);
+            LAUNCHED();
+            irb::k_spec_binop<true><<<grid1(M + 1, nb), 256, 0, st>>>(S.as<float2>(), M + 1, Sd.as<float2>(), 0, M);
+            LAUNCHED();
+            const float smooth_per_avg = 1.0 / 13.0;                                  // fp/convolution.cpp:390 (a float there)
+            for (int i = 0; i < 3; ++i)
+                if ((rc = averaging_pass(S.as<float2>(), M + 1, nb, M, (double) smooth_per_avg, sample_rate, 1, include_phase, include_amplitude, sm.la.as<float>(),
+                                         sm.rs.as<float>(), sm.lo.as<int>(), sm.hi.as<int>(), st)))
+                    return rc;
+            irb::k_spec_merge<<<grid1(M, nb), 256, 0, st>>>(S.as<float2>(), M + 1, Zn.as<float2>(), M, M, plan.WN);
+            LAUNCHED();
+        }
+        if ((rc = plan.run(Zn.p, M, -1, dy.as<float2>(), M, tmp.as<float2>(), nb, true, 1.0f / (float) N, st))) return rc;
+        const float* res = dy.as<float>();
+        if (!include_phase) {                                                        // ir::shifteroo, fp/convolution.cpp:400
+            irb::k_shifteroo<<<grid1(N, nb), 256, 0, st>>>(dy.as<float>(), dy2.as<float>(), N, N);
+            LAUNCHED();
+            res = dy2.as<float>();
+        }
+        CK(cudaMemcpyAsync(out + (size_t) b0 * N, res, sizeof(float) * (size_t) N * nb, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int irb_deconvolve(const float* num, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase, int include_amplitude,
+                   float* out) {
+    return irb_deconvolve_batch(num, 1, len_num, den, len_den, sample_rate, smoothing, include_phase, include_amplitude, out);
+}
+
+// fp::ir::invertFilter (fp/ir.cpp:13-18): deconvolve(generatePulse(len), x, sr) with the default flags
+int irb_invert_filter(const float* x, int len, int sample_rate, float* out) {
+    if (!x || !out || len < 1) return fail(IRB_ERR_ARG, "bad argument");
+    std::vector<float> pulse((size_t) len, 0.0f);
+    pulse[0] = 1.0f;                                                                 // tools::generatePulse, fp/tools.cpp:235-241
+    return irb_deconvolve_batch(pulse.data(), 1, len, x, len, (double) sample_rate, 1, 1, 1, out);
+}
+
+// fp::tools::fftTransform (fp/tools.cpp:321-346): x[ch][len] -> out[ch][2N]; only channel 0 carries data (:328)
+int irb_fft_transform(const float* x, int ch, int len, int format_ampl_phase, float* out) {
+    if (!x || !out || ch < 1 || len < 1) return fail(IRB_ERR_ARG, "bad argument");
+    int N = 0, rc;
+    if ((rc = fft_size_for(len, &N))) return rc;
+    const int M = N / 2, dev = irbh::current_device();
+    CK(cudaSetDevice(dev));
+    Plan plan;
+    if ((rc = plan.init(dev, M))) return rc;
+    irbh::StreamGuard sg;
+    if ((rc = sg.create())) return rc;
+    cudaStream_t st = sg.s;
+    DevBuf dx, Z, tmp, S;
+    if ((rc = dx.alloc(sizeof(float) * ((size_t) len + 1), true)) || (rc = Z.alloc(sizeof(float2) * (size_t) M, false)) || (rc = tmp.alloc(sizeof(float2) * (size_t) M, false)) ||
+        (rc = S.alloc(sizeof(float2) * (size_t) N, true)))
+        return rc;
+    CK(cudaMemcpyAsync(dx.p, x, sizeof(float) * len, cudaMemcpyHostToDevice, st));
+    if ((rc = plan.run(dx.p, 0, len, Z.as<float2>(), M, tmp.as<float2>(), 1, false, 1.0f, st))) return rc;
+    irb::k_spec_split<<<grid1(M + 1, 1), 256, 0, st>>>(Z.as<float2>(), M, S.as<float2>(), N, M, 1, plan.WN);
+    LAUNCHED();
+    if (format_ampl_phase) { irb::k_spec_ampl_phase<<<grid1(M + 1, 1), 256, 0, st>>>(S.as<float2>(), N, M); LAUNCHED(); }
+    memset(out, 0, sizeof(float) * 2 * (size_t) N * ch);                              // channels >= 1 transform silence
+    CK(cudaMemcpyAsync(out, S.p, sizeof(float) * 2 * (size_t) N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// fp::tools::fftInvTransform (fp/tools.cpp:351-369): spec[ch][fft_size] (interleaved, bins 0..N/2 used) -> out[ch][N], N = fft_size/2
+int irb_fft_inv_transform(const float* spec, int ch, int fft_size, float* out) {
+    if (!spec || !out || ch < 1 || fft_size < 2) return fail(IRB_ERR_ARG, "bad argument");
+    const int N = fft_size / 2, M = N / 2, dev = irbh::current_device();
+    int rc;
+    if (N != irbh::next_pow2(N) || M < kMinM) return fail(IRB_ERR_ARG, "fft_size %d: N must be a power of two >= %d", fft_size, 2 * kMinM);
+    CK(cudaSetDevice(dev));
+    Plan plan;
+    if ((rc = plan.init(dev, M))) return rc;
+    irbh::StreamGuard sg;
+    if ((rc = sg.create())) return rc;
+    cudaStream_t st = sg.s;
+    DevBuf S, Z, tmp, dy;
+    if ((rc = S.alloc(sizeof(float) * (size_t) fft_size * ch, false)) || (rc = Z.alloc(sizeof(float2) * (size_t) M * ch, false)) ||
+        (rc = tmp.alloc(sizeof(float2) * (size_t) M * ch, false)) || (rc = dy.alloc(sizeof(float2) * (size_t) M * ch, false)))
+        return rc;
+    CK(cudaMemcpyAsync(S.p, spec, sizeof(float) * (size_t) fft_size * ch, cudaMemcpyHostToDevice, st));
+    irb::k_spec_merge<<<grid1(M, ch), 256, 0, st>>>(S.as<float2>(), N, Z.as<float2>(), M, M, plan.WN);
+    LAUNCHED();
+    if ((rc = plan.run(Z.p, M, -1, dy.as<float2>(), M, tmp.as<float2>(), ch, true, 1.0f / (float) N, st))) return rc;
+    CK(cudaMemcpyAsync(out, dy.p, sizeof(float) * (size_t) N * ch, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// fp::convolution::averagingFilter (fp/convolution.cpp:406-546), in place on spec[ch][fft_size]
+int irb_averaging_filter(float* spec, int ch, int fft_size, double octave_fraction, double sample_rate, int log_avg, int include_phase, int include_amplitude) {
+    if (!spec || ch < 1 || fft_size < 4) return fail(IRB_ERR_ARG, "bad argument");
+    if (fft_size & (fft_size - 1)) return 0;                                          // not a power of two: untouched (:412-415)
+    const int N = fft_size / 2, M = N / 2, dev = irbh::current_device();
+    CK(cudaSetDevice(dev));
+    irbh::StreamGuard sg;
+    int rc;
+    if ((rc = sg.create())) return rc;
+    cudaStream_t st = sg.s;
+    DevBuf S;
+    SmoothBufs sm;
+    if ((rc = S.alloc(sizeof(float) * (size_t) fft_size * ch, false)) || (rc = sm.alloc(M, ch))) return rc;
+    CK(cudaMemcpyAsync(S.p, spec, sizeof(float) * (size_t) fft_size * ch, cudaMemcpyHostToDevice, st));
+    if ((rc = averaging_pass(S.as<float2>(), N, ch, M, octave_fraction, sample_rate, log_avg, include_phase, include_amplitude, sm.la.as<float>(), sm.rs.as<float>(),
+                             sm.lo.as<int>(), sm.hi.as<int>(), st)))
+        return rc;
+    CK(cudaMemcpyAsync(spec, S.p, sizeof(float) * (size_t) fft_size * ch, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// fp::ExpSineSweep::generate / generateInv (fp/ExpSineSweep.cpp:26-41,59-79,212-220) in FP64 on the device.
+// Returns the sweep length (int) (sample_rate * duration); writes min(length, capacity) doubles when out != NULL.
+int irb_ess_generate(double duration_s, double sample_rate, double f1, double f2, double gain_db, int inverse, double* out, int capacity) {
+    const double T = sample_rate * duration_s;
+    const double w1 = f1 / sample_rate * 2 * M_PI, w2 = f2 / sample_rate * 2 * M_PI;
+    if (!(T >= 1.0) || !(f1 > 0) || !(f2 > f1) || T > 2147483647.0) return fail(IRB_ERR_ARG, "bad sweep parameters");
+    const double K = T * w1 / log(w2 / w1), L = T / log(w2 / w1);
+    const int n = (int) T;
+    if (!out) return n;
+    const int m = std::min(n, capacity);
+    if (m <= 0) return n;
+    const double g = pow(10.0, gain_db / 20.0);                                       // tools::dBToLin(double), fp/tools.cpp:93-95
+    const double kdecay = pow(10.0, (-6.0 * log2(w2 / w1)) / 20.0 / T);               // fp/ExpSineSweep.cpp:70
+    CK(cudaSetDevice(irbh::current_device()));
+    irbh::StreamGuard sg;
+    int rc;
+    if ((rc = sg.create())) return rc;
+    DevBuf d;
+    if ((rc = d.alloc(sizeof(double) * (size_t) n, false))) return rc;
+    irb::k_ess<<<grid1(n, 1), 256, 0, sg.s>>>(d.as<double>(), n, g, K, L, inverse, kdecay);
+    LAUNCHED();
+    CK(cudaMemcpyAsync(out, d.p, sizeof(double) * (size_t) m, cudaMemcpyDeviceToHost, sg.s));
+    CK(cudaStreamSynchronize(sg.s));
+    return n;
+}
+
+}  // extern "C"

@@ -55,6 +55,14 @@ _SIGS = {
     "irb_launch_count": (ctypes.c_longlong, []),
     "irb_engine_mac_only_device": (ctypes.c_int, [_vp, _vp]),
     "irb_convolve_periodic": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_convolve_nonperiodic": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_deconvolve": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_deconvolve_batch": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_invert_filter": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_averaging_filter": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "irb_fft_transform": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_fft_inv_transform": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_ess_generate": (ctypes.c_int, [ctypes.c_double] * 5 + [ctypes.c_int, _vp, ctypes.c_int]),
 }
 
 
@@ -129,6 +137,83 @@ def convolve_periodic(x, h, block_size=256):
     if rc == IRB_ERR_LAYOUT:
         return out                      # the reference prints a DBG line and returns the cleared buffer
     _ck(rc)
+    return out
+
+
+def next_pow2(x):
+    """tools::nextPowerOfTwo (fp/tools.cpp:189-196): x itself when already a power of two."""
+    if x > 0 and (x & (x - 1)) == 0:
+        return x
+    r = 1
+    while r <= x:
+        r *= 2
+    return r
+
+
+def convolve_nonperiodic(x, h):
+    """fp::convolution::convolveNonPeriodic (fp/convolution.cpp:246-347)."""
+    x, h = _planar(x), _planar(h)
+    out = np.zeros((x.shape[0], x.shape[1] + h.shape[1] - 1), np.float32)
+    rc = lib().irb_convolve_nonperiodic(_ptr(x), x.shape[0], x.shape[1], _ptr(h), h.shape[0], h.shape[1], _ptr(out))
+    if rc == IRB_ERR_LAYOUT:
+        return np.zeros_like(x)         # the reference returns a cleared copy of the input (fp/convolution.cpp:271-275)
+    _ck(rc)
+    return out
+
+
+def deconvolve(num, den, sample_rate=48000.0, smoothing=True, include_phase=True, include_amplitude=True):
+    """fp::convolution::deconvolve (fp/convolution.cpp:351-403); channel 0 of each input is used.  -> [1][N]"""
+    num, den = np.ascontiguousarray(_planar(num)[0]), np.ascontiguousarray(_planar(den)[0])
+    N = next_pow2(max(len(num), len(den)))
+    out = np.zeros((1, N), np.float32)
+    _ck(lib().irb_deconvolve(_ptr(num), len(num), _ptr(den), len(den), float(sample_rate), int(smoothing), int(include_phase), int(include_amplitude), _ptr(out)))
+    return out
+
+
+def deconvolve_batch(nums, den, sample_rate=48000.0, smoothing=False, include_phase=True, include_amplitude=True):
+    """`batch` captures nums[batch][len] divided by one sweep den[len_den] -> [batch][N]."""
+    nums = np.ascontiguousarray(nums, np.float32)
+    den = np.ascontiguousarray(den, np.float32).reshape(-1)
+    N = next_pow2(max(nums.shape[1], len(den)))
+    out = np.zeros((nums.shape[0], N), np.float32)
+    _ck(lib().irb_deconvolve_batch(_ptr(nums), nums.shape[0], nums.shape[1], _ptr(den), len(den), float(sample_rate), int(smoothing), int(include_phase),
+                                   int(include_amplitude), _ptr(out)))
+    return out
+
+
+def invert_filter(x, sample_rate=48000):
+    x = np.ascontiguousarray(_planar(x)[0])
+    out = np.zeros((1, next_pow2(len(x))), np.float32)
+    _ck(lib().irb_invert_filter(_ptr(x), len(x), int(sample_rate), _ptr(out)))
+    return out
+
+
+def averaging_filter(spec, octave_fraction, sample_rate, log_avg=True, include_phase=True, include_amplitude=True):
+    s = _planar(spec).copy()
+    _ck(lib().irb_averaging_filter(_ptr(s), s.shape[0], s.shape[1], float(octave_fraction), float(sample_rate), int(log_avg), int(include_phase), int(include_amplitude)))
+    return s
+
+
+def fft_transform(x, format_ampl_phase=False):
+    x = _planar(x)
+    N = next_pow2(x.shape[1])
+    out = np.zeros((x.shape[0], 2 * N), np.float32)
+    _ck(lib().irb_fft_transform(_ptr(x), x.shape[0], x.shape[1], int(format_ampl_phase), _ptr(out)))
+    return out
+
+
+def fft_inv_transform(spec):
+    s = _planar(spec)
+    out = np.zeros((s.shape[0], s.shape[1] // 2), np.float32)
+    _ck(lib().irb_fft_inv_transform(_ptr(s), s.shape[0], s.shape[1], _ptr(out)))
+    return out
+
+
+def ess(duration_s, sample_rate, f1, f2, gain_db=0.0, inverse=False):
+    """fp::ExpSineSweep::generate / generateInv in FP64 on the device -> float64 array."""
+    n = _ck(lib().irb_ess_generate(duration_s, sample_rate, f1, f2, gain_db, int(inverse), None, 0))
+    out = np.zeros(n, np.float64)
+    _ck(lib().irb_ess_generate(duration_s, sample_rate, f1, f2, gain_db, int(inverse), _ptr(out), n))
     return out
 
 
