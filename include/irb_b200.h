@@ -64,8 +64,9 @@ int irb_engine_set_stream(irb_engine* e, void* cuda_stream);
  * PluginProcessor.cpp:455-461, done for all partitions at once).  n_taps <= block_size*max_partitions.
  * right != NULL folds a stereo IR to (left+right)/2 first (tools::sumToMono, fp/tools.cpp:13-30). */
 int irb_engine_set_ir(irb_engine* e, int ir_id, const float* left, const float* right, int n_taps);
-/* channels [chan_begin, chan_end) convolve with ir_id.  Channels that share a kernel tile
- * (irb_engine_tile_channels() consecutive channels) must share an IR. */
+/* channels [chan_begin, chan_end) convolve with ir_id.  When every kernel tile (irb_engine_tile_channels()
+ * consecutive channels) is bound to one IR the tile shares the staged IR spectra; otherwise the per-stream-IR
+ * kernel is used (each channel stages its own partitions; twice the memory traffic). */
 int irb_engine_bind(irb_engine* e, int chan_begin, int chan_end, int ir_id);
 int irb_engine_tile_channels(const irb_engine* e);
 /* clear FDL rings, overlap buffers and heads (prepareToPlay, PluginProcessor.cpp:164-234) */
@@ -95,6 +96,9 @@ int irb_engine_read_fdl_spectrum(irb_engine* e, int chan, int age, float* out_pa
 /* kernel launches issued by this engine so far, and by the whole library */
 long long irb_engine_launch_count(const irb_engine* e);
 long long irb_launch_count(void);
+/* device time (CUDA events, ms) of the kernels of the calling thread's most recent offline call
+ * (irb_convolve_periodic / _nonperiodic / irb_deconvolve*), host<->device copies excluded */
+double irb_last_compute_ms(void);
 /* the pure FDL multiply-accumulate (no inverse FFT) on the current state into a device buffer of
  * n_channels * M complex; used to time the roofline kernel in isolation */
 int irb_engine_mac_only_device(irb_engine* e, float* acc_dev);

@@ -33,6 +33,29 @@ struct DevBuf {
     template <typename T> T* as() const { return (T*) p; }
 };
 
+// device time of the kernels of this thread's most recent offline call (irb_last_compute_ms)
+void set_last_compute_ms(double ms);
+
+// brackets the kernel section(s) of an offline call with CUDA events and accumulates their elapsed time
+struct ComputeTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t st = nullptr;
+    double total = 0.0;
+    bool open = false;
+    ~ComputeTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    int init(cudaStream_t s) { st = s; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); return 0; }
+    int begin() { CK(cudaEventRecord(a, st)); open = true; return 0; }
+    int end() { CK(cudaEventRecord(b, st)); return 0; }
+    int collect() {          // call after the stream was synchronised
+        if (!open) return 0;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        total += ms; open = false;
+        set_last_compute_ms(total);
+        return 0;
+    }
+};
+
 struct StreamGuard {
     cudaStream_t s = nullptr;
     ~StreamGuard() { if (s) cudaStreamDestroy(s); }

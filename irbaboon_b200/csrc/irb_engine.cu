@@ -28,6 +28,8 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 int current_device() { return g_device; }
+thread_local double g_last_compute_ms = 0.0;
+void set_last_compute_ms(double ms) { g_last_compute_ms = ms; }
 
 // twiddle tables, one per (device, M), built in double like the reference FFT's tables
 int twiddles(int dev, int M, const float2** out) {
@@ -84,25 +86,26 @@ int launch_fwd_t(const irb::FwdArgs& a, cudaStream_t st) {
     CK(cudaGetLastError());
     return 0;
 }
-template <int M, int U, bool INV>
+template <int M, int U, bool INV, bool PRI = false>
 int launch_mac_u(const irb::MacArgs& a, cudaStream_t st) {
     const int grid = (a.n_rows + irb::Tile<M>::ROWS - 1) / irb::Tile<M>::ROWS;
     if (grid <= 0) return 0;
-    const size_t smem = sizeof(irb::MacSmem<M, U>);
+    const size_t smem = sizeof(irb::MacSmem<M, U, PRI>);
     static thread_local int configured_dev = -1;
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        CK(cudaFuncSetAttribute(irb::k_mac<M, U, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CK(cudaFuncSetAttribute(irb::k_mac<M, U, INV, PRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         configured_dev = dev;
     }
-    irb::k_mac<M, U, INV><<<grid, irb::kThreads + 32, smem, st>>>(a);
+    irb::k_mac<M, U, INV, PRI><<<grid, irb::kThreads + 32, smem, st>>>(a);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
 }
 template <int M, bool INV>
-int launch_mac_t(const irb::MacArgs& a, cudaStream_t st) {
+int launch_mac_t(const irb::MacArgs& a, bool per_row_ir, cudaStream_t st) {
+    if (per_row_ir) return launch_mac_u<M, 1, INV, true>(a, st);
     if constexpr (M <= 512) { if (mac_u_pref() == 2) return launch_mac_u<M, 2, INV>(a, st); }
     return launch_mac_u<M, 1, INV>(a, st);
 }
@@ -119,9 +122,9 @@ int launch_mac_t(const irb::MacArgs& a, cudaStream_t st) {
         default: return fail(IRB_ERR_ARG, "unsupported FFT half size %d", M_); \
     }
 int launch_fwd(int M, const irb::FwdArgs& a, cudaStream_t st) { IRB_DISPATCH_M(M, launch_fwd_t<MM>(a, st)); }
-int launch_mac(int M, bool inv, const irb::MacArgs& a, cudaStream_t st) {
-    if (inv) { IRB_DISPATCH_M(M, (launch_mac_t<MM, true>(a, st))); }
-    IRB_DISPATCH_M(M, (launch_mac_t<MM, false>(a, st)));
+int launch_mac(int M, bool inv, bool per_row_ir, const irb::MacArgs& a, cudaStream_t st) {
+    if (inv) { IRB_DISPATCH_M(M, (launch_mac_t<MM, true>(a, per_row_ir, st))); }
+    IRB_DISPATCH_M(M, (launch_mac_t<MM, false>(a, per_row_ir, st)));
 }
 int tile_rows(int M) { return irb::kTile / M; }
 
@@ -135,6 +138,7 @@ struct irb_engine {
     DevBuf fdl, H, ov, head, ir_of_chan, nparts, io_in[2], io_out[2], taps;
     std::vector<int> h_ir_of_chan, h_nparts;
     bool binding_dirty = true;
+    bool per_row_ir = false;           // some kernel tile mixes IRs: use the per-row-IR MAC kernel
     size_t bytes = 0;
     long long launches = 0;
     // host path: copy streams + events so block b+1 uploads and block b-1 downloads while block b computes
@@ -161,10 +165,10 @@ namespace {
 int engine_check_binding(irb_engine* e) {
     if (!e->binding_dirty) return 0;
     const int rows = tile_rows(e->M);
-    for (int c0 = 0; c0 < e->n_chans; c0 += rows)
+    e->per_row_ir = false;
+    for (int c0 = 0; c0 < e->n_chans && !e->per_row_ir; c0 += rows)
         for (int c = c0 + 1; c < c0 + rows && c < e->n_chans; ++c)
-            if (e->h_ir_of_chan[c] != e->h_ir_of_chan[c0])
-                return fail(IRB_ERR_STATE, "channels %d and %d share a kernel tile (%d channels) but are bound to different IRs", c0, c, rows);
+            if (e->h_ir_of_chan[c] != e->h_ir_of_chan[c0]) { e->per_row_ir = true; break; }
     CK(cudaMemcpyAsync(e->ir_of_chan.p, e->h_ir_of_chan.data(), sizeof(int) * e->n_chans, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->binding_dirty = false;
@@ -191,7 +195,7 @@ int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
     m.ir_of_chan = e->ir_of_chan.as<int>(); m.nparts = e->nparts.as<int>(); m.W = e->W;
     m.Y = nullptr; m.B = e->B; m.out = out_dev; m.out_chan_stride = e->B; m.Lout = e->B;
     m.ov = e->ov.as<float>(); m.tail = nullptr;
-    rc = launch_mac(e->M, true, m, e->stream);
+    rc = launch_mac(e->M, true, e->per_row_ir, m, e->stream);
     if (rc) return rc;
     if (rec) { CK(cudaEventRecord(e->tev[3 * e->t_rec + 2], e->stream)); e->t_rec++; }
     e->launches += 2;
@@ -222,6 +226,7 @@ void* irb_host_alloc(size_t bytes) {
 }
 void irb_host_free(void* p) { if (p) cudaFreeHost(p); }
 long long irb_launch_count(void) { return g_launches.load(); }
+double irb_last_compute_ms(void) { return irbh::g_last_compute_ms; }
 
 int irb_engine_create(irb_engine** out, int device, int block_size, int max_partitions, int n_channels, int n_irs) {
     if (!out) return fail(IRB_ERR_ARG, "out is null");
@@ -432,7 +437,7 @@ int irb_engine_mac_only_device(irb_engine* e, float* acc_dev) {
     m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
     m.ir_of_chan = e->ir_of_chan.as<int>(); m.nparts = e->nparts.as<int>(); m.W = e->W;
     m.Y = (float2*) acc_dev; m.B = e->B;
-    rc = launch_mac(e->M, false, m, e->stream);
+    rc = launch_mac(e->M, false, e->per_row_ir, m, e->stream);
     if (rc) return rc;
     e->launches += 1;
     return 0;
@@ -483,6 +488,8 @@ int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, i
     CK(cudaMemcpyAsync(dnp.p, np, sizeof(np), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dir.p, irmap, sizeof(irmap), cudaMemcpyHostToDevice, st));
 
+    irbh::ComputeTimer tm;
+    if ((rc = tm.init(st)) || (rc = tm.begin())) return rc;
     irb::FwdArgs fh{};                                      // IR partitions
     fh.src = dh.as<float>(); fh.src2 = fold ? dh.as<float>() + len_h : nullptr; fh.src_chan_stride = len_h; fh.L = len_h; fh.B = B;
     fh.blocks_per_chan = P; fh.n_rows = P * n_ir; fh.dst = dH.as<float2>(); fh.dst_chan_stride = (long long) P * M; fh.W = W;
@@ -495,16 +502,17 @@ int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, i
     m.fdl = dX.as<float2>(); m.fdl_chan_stride = (long long) bpc * M; m.head = nullptr; m.ring = bpc; m.blocks_per_chan = bpc;
     m.n_rows = bpc * ch_x; m.H = dH.as<float2>(); m.ir_stride = (long long) P * M; m.ir_of_chan = dir.as<int>(); m.nparts = dnp.as<int>();
     m.W = W; m.B = B; m.out = dout.as<float>(); m.out_chan_stride = Lout; m.Lout = (int) Lw; m.ov = nullptr; m.tail = dtail.as<float>();
-    if ((rc = launch_mac(M, true, m, st))) return rc;
+    if ((rc = launch_mac(M, true, false, m, st))) return rc;
     {
         const long long n = (long long) bpc * B * ch_x;
         irb::k_ola_tail<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(dout.as<float>(), Lout, (int) Lw, dtail.as<float>(), B, bpc, ch_x);
         g_launches++;
         CK(cudaGetLastError());
     }
+    if ((rc = tm.end())) return rc;
     CK(cudaMemcpyAsync(out, dout.p, sizeof(float) * (size_t) ch_x * Lout, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    return 0;
+    return tm.collect();
 }
 
 }  // extern "C"

@@ -200,27 +200,38 @@ struct MacArgs {
     float* tail;               // offline: second halves [row][B]
 };
 
-template <int M, int U>
+// PRI = per-row IR: every row of the tile stages its OWN partition spectrum (per-stream IRs, BASELINE config 4);
+// otherwise the whole tile shares one IR and a ring stage holds U consecutive partitions of it.
+template <int M, int U, bool PRI>
 struct MacSmem {
-    float2 spec[kTile];                 // tile in both layouts (inverse path)
-    float2 h[kStages][U][M];            // IR ring
+    float2 spec[kTile];                                  // tile in both layouts (inverse path)
+    float2 h[kStages][PRI ? kTile / M : U][M];           // IR ring
     uint64_t full[kStages], empty[kStages];
 };
 
-template <int M, int U, bool INV>
-__global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const MacArgs a) {
+template <int M, int U, bool INV, bool PRI>
+__global__ void __launch_bounds__(kThreads + 32, (U == 1 && !PRI) ? 3 : 2) k_mac(const MacArgs a) {
+    static_assert(!PRI || U == 1, "per-row IR stages one partition per row");
     using T = Tile<M>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    MacSmem<M, U>& sm = *reinterpret_cast<MacSmem<M, U>*>(smem_raw);
+    MacSmem<M, U, PRI>& sm = *reinterpret_cast<MacSmem<M, U, PRI>*>(smem_raw);
     const int tid = threadIdx.x;
     const int row0 = blockIdx.x * T::ROWS;
 
-    // the tile's IR: by contract every row of a tile is bound to the same IR (the host groups rows)
+    // shared mode: by contract every row of a tile is bound to the same IR (the host checks / pads)
     const int chan_first = row0 / a.blocks_per_chan;
     const int ir = a.ir_of_chan ? a.ir_of_chan[chan_first] : 0;
     const int np = a.nparts[ir];
     // number of partitions any row of this tile needs
     int pmax = np;
+    if (PRI) {
+        pmax = 0;
+        for (int r = 0; r < T::ROWS && row0 + r < a.n_rows; ++r) {
+            const int chan = (row0 + r) / a.blocks_per_chan;
+            const int n = a.nparts[a.ir_of_chan ? a.ir_of_chan[chan] : 0];
+            pmax = n > pmax ? n : pmax;
+        }
+    }
     if (!a.head) {          // offline: row = chan*blocks_per_chan + blk, blocks_per_chan % ROWS == 0 (host pads)
         int last = row0 + T::ROWS - 1;
         if (last >= a.n_rows) last = a.n_rows - 1;
@@ -237,7 +248,29 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
 
     if (tid >= kThreads) {
         // ===== TMA producer warp: stream the IR partition spectra through the ring =====
-        if (tid == kThreads) {
+        if (PRI) {
+            // one bulk copy per (row, partition); lanes split the rows of the tile
+            const int lane = tid - kThreads;
+            for (int g = 0; g < ngroups; ++g) {
+                const int st = g % kStages;
+                if (g >= kStages) mbar_wait(&sm.empty[st], ((g / kStages) - 1) & 1);
+                uint32_t mine = 0;
+                for (int r = lane; r < T::ROWS && row0 + r < a.n_rows; r += 32) {
+                    const int chan = (row0 + r) / a.blocks_per_chan;
+                    if (g < a.nparts[a.ir_of_chan ? a.ir_of_chan[chan] : 0]) mine += M * sizeof(float2);
+                }
+                uint32_t total = mine;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                if (lane == 0) mbar_expect_tx(&sm.full[st], total);
+                __syncwarp();
+                for (int r = lane; r < T::ROWS && row0 + r < a.n_rows; r += 32) {
+                    const int chan = (row0 + r) / a.blocks_per_chan;
+                    const int irr = a.ir_of_chan ? a.ir_of_chan[chan] : 0;
+                    if (g < a.nparts[irr]) tma_bulk_g2s(&sm.h[st][r][0], a.H + irr * a.ir_stride + (long long) g * M, M * sizeof(float2), &sm.full[st]);
+                }
+            }
+        } else if (tid == kThreads) {
             const float2* hsrc = a.H + ir * a.ir_stride;
             for (int g = 0; g < ngroups; ++g) {
                 const int st = g % kStages;
@@ -263,7 +296,8 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
         if (row < a.n_rows) {
             const int chan = row / a.blocks_per_chan, blk = row % a.blocks_per_chan;
             const int hd = a.head ? a.head[chan] : blk;
-            nvalid[s] = a.head ? np : (blk + 1 < np ? blk + 1 : np);
+            const int npr = PRI ? a.nparts[a.ir_of_chan ? a.ir_of_chan[chan] : 0] : np;
+            nvalid[s] = a.head ? npr : (blk + 1 < npr ? blk + 1 : npr);
             slot[s] = hd;
             xptr[s] = reinterpret_cast<const float4*>(a.fdl + chan * a.fdl_chan_stride + (long long) hd * M) + c0;
         }
@@ -302,11 +336,20 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
 #pragma unroll
                 for (int vv = 0; vv < T::V; ++vv) {
                     const int c = c0 + vv * T::TPR;
-                    const float4 h = *reinterpret_cast<const float4*>(&sm.h[st][u][2 * c]);
-                    // bin 0 is the packed {DC, Nyquist} pair: two real products instead of a complex one
-                    const float h0i = c == 0 ? 0.f : h.y, h0q = c == 0 ? h.y : h.x;
+                    float4 h;
+                    float h0i, h0q;
+                    if (!PRI) {
+                        h = *reinterpret_cast<const float4*>(&sm.h[st][u][2 * c]);
+                        // bin 0 is the packed {DC, Nyquist} pair: two real products instead of a complex one
+                        h0i = c == 0 ? 0.f : h.y; h0q = c == 0 ? h.y : h.x;
+                    }
 #pragma unroll
                     for (int s = 0; s < T::K; ++s) {
+                        if (PRI) {
+                            if (g >= nvalid[s]) continue;      // this row's IR is shorter: its stage slot was not filled
+                            h = *reinterpret_cast<const float4*>(&sm.h[st][s * T::G + g_][2 * c]);
+                            h0i = c == 0 ? 0.f : h.y; h0q = c == 0 ? h.y : h.x;
+                        }
                         const float4 xv = x[u][s][vv];
                         float4& ac = acc[s][vv];
                         ac.x = fmaf(xv.x, h.x, fmaf(-xv.y, h0i, ac.x));

@@ -168,6 +168,8 @@ int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h
         return rc;
     for (int c = 0; c < ch_x; ++c) CK(cudaMemcpyAsync(dx.as<float>() + c * lxe, x + (size_t) c * len_x, sizeof(float) * len_x, cudaMemcpyHostToDevice, st));
     for (int c = 0; c < ch_h; ++c) CK(cudaMemcpyAsync(dh.as<float>() + c * lhe, h + (size_t) c * len_h, sizeof(float) * len_h, cudaMemcpyHostToDevice, st));
+    irbh::ComputeTimer tm;
+    if ((rc = tm.init(st)) || (rc = tm.begin())) return rc;
     const float* hsrc = dh.as<float>();
     if (fold) {
         irb::k_fold_mono<<<grid1(len_h, 1), 256, 0, st>>>(dh.as<float>(), dh.as<float>() + lhe, dhf.as<float>(), len_h);
@@ -180,10 +182,11 @@ int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h
     irb::k_spec_fused<false><<<grid1(M / 2 + 1, ch_x), 256, 0, st>>>(Zx.as<float2>(), M, Zh.as<float2>(), n_ir == 2 ? M : 0, Zx.as<float2>(), M, M, plan.WN);
     LAUNCHED();
     if ((rc = plan.run(Zx.p, M, -1, dy.as<float2>(), M, tmp.as<float2>(), ch_x, true, 1.0f / (float) N, st))) return rc;
+    if ((rc = tm.end())) return rc;
     for (int c = 0; c < ch_x; ++c)
         CK(cudaMemcpyAsync(out + (size_t) c * Lout, dy.as<float>() + (size_t) c * N, sizeof(float) * Lout, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    return 0;
+    return tm.collect();
 }
 
 // fp::convolution::deconvolve (fp/convolution.cpp:351-403) for `batch` numerators against one denominator.
@@ -214,6 +217,9 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
     if (smoothing && ((rc = S.alloc(sizeof(float2) * (size_t) (M + 1) * chunk, false)) || (rc = Sd.alloc(sizeof(float2) * (size_t) (M + 1), false)) || (rc = sm.alloc(M, chunk))))
         return rc;
     if (!include_phase && (rc = dy2.alloc(sizeof(float) * (size_t) N * chunk, false))) return rc;
+    irbh::ComputeTimer tm;
+    if ((rc = tm.init(st))) return rc;
+    irbh::set_last_compute_ms(0.0);
     CK(cudaMemcpyAsync(dd.p, den, sizeof(float) * len_den, cudaMemcpyHostToDevice, st));
     if ((rc = plan.run(dd.p, lde / 2, len_den, Zd.as<float2>(), M, tmp.as<float2>(), 1, false, 1.0f, st))) return rc;
     if (smoothing) {
@@ -223,6 +229,7 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
     for (int b0 = 0; b0 < batch; b0 += chunk) {
         const int nb = std::min(chunk, batch - b0);
         CK(cudaMemcpy2DAsync(dn.p, sizeof(float) * lne, nums + (size_t) b0 * len_num, sizeof(float) * len_num, sizeof(float) * len_num, nb, cudaMemcpyHostToDevice, st));
+        if ((rc = tm.begin())) return rc;
         if ((rc = plan.run(dn.p, lne / 2, len_num, Zn.as<float2>(), M, tmp.as<float2>(), nb, false, 1.0f, st))) return rc;
         if (!smoothing) {
             irb::k_spec_fused<true><<<grid1(M / 2 + 1, nb), 256, 0, st>>>(Zn.as<float2>(), M, Zd.as<float2>(), 0, Zn.as<float2>(), M, M, plan.WN);
@@ -247,8 +254,10 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
             LAUNCHED();
             res = dy2.as<float>();
         }
+        if ((rc = tm.end())) return rc;
         CK(cudaMemcpyAsync(out + (size_t) b0 * N, res, sizeof(float) * (size_t) N * nb, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if ((rc = tm.collect())) return rc;
     }
     return 0;
 }

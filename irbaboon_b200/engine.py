@@ -53,6 +53,7 @@ _SIGS = {
     "irb_engine_read_fdl_spectrum": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_engine_launch_count": (ctypes.c_longlong, [_vp]),
     "irb_launch_count": (ctypes.c_longlong, []),
+    "irb_last_compute_ms": (ctypes.c_double, []),
     "irb_engine_mac_only_device": (ctypes.c_int, [_vp, _vp]),
     "irb_convolve_periodic": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_convolve_nonperiodic": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp]),
@@ -106,6 +107,10 @@ def set_device(device):
 
 def launch_count():
     return lib().irb_launch_count()
+
+
+def last_compute_ms():
+    return lib().irb_last_compute_ms()
 
 
 def pinned_empty(shape, dtype=np.float32):
@@ -170,12 +175,14 @@ def deconvolve(num, den, sample_rate=48000.0, smoothing=True, include_phase=True
     return out
 
 
-def deconvolve_batch(nums, den, sample_rate=48000.0, smoothing=False, include_phase=True, include_amplitude=True):
+def deconvolve_batch(nums, den, sample_rate=48000.0, smoothing=False, include_phase=True, include_amplitude=True, out=None):
     """`batch` captures nums[batch][len] divided by one sweep den[len_den] -> [batch][N]."""
     nums = np.ascontiguousarray(nums, np.float32)
     den = np.ascontiguousarray(den, np.float32).reshape(-1)
     N = next_pow2(max(nums.shape[1], len(den)))
-    out = np.zeros((nums.shape[0], N), np.float32)
+    if out is None:
+        out = np.zeros((nums.shape[0], N), np.float32)
+    assert out.shape == (nums.shape[0], N) and out.dtype == np.float32 and out.flags.c_contiguous
     _ck(lib().irb_deconvolve_batch(_ptr(nums), nums.shape[0], nums.shape[1], _ptr(den), len(den), float(sample_rate), int(smoothing), int(include_phase),
                                    int(include_amplitude), _ptr(out)))
     return out

@@ -153,13 +153,41 @@ def test_streaming_engine_two_irs_by_tile(eng, orc):
         _check(y[c:c + 1], want)
 
 
-def test_streaming_engine_rejects_mixed_irs_inside_a_tile(eng):
-    with eng.Engine(512, 2, 8, 2) as e:
-        e.set_ir(0, np.ones(10, np.float32))
-        e.set_ir(1, np.ones(10, np.float32))
-        e.bind(1, 2, 1)
-        with pytest.raises(eng.IrbError):
-            e.process(np.zeros((8, 512), np.float32))
+@pytest.mark.parametrize("B,C", [(1024, 5), (512, 7), (256, 3), (64, 40)])
+def test_streaming_engine_per_stream_irs(eng, orc, B, C):
+    """BASELINE config 4 shape at test size: every stream has its own IR (different lengths too), so kernel tiles mix
+    IRs and the per-row-IR MAC kernel runs."""
+    n = 10 * B
+    lens = [3 * B + 17 * c + 1 for c in range(C)]
+    P = max(-(-l // B) for l in lens)
+    irs = [synth.decaying_ir(2100 + c, lens[c], c) for c in range(C)]
+    x = np.stack([synth.white_noise(1004, c, n) for c in range(C)])
+    with eng.Engine(B, P, C, C) as e:
+        for c in range(C):
+            e.set_ir(c, irs[c])
+            e.bind(c, c + 1, c)
+        y = e.process_stream(x)
+    for c in range(C):
+        want = orc.convolve_periodic(x[c], irs[c], B)[:, :n]
+        _check(y[c:c + 1], want)
+
+
+def test_streaming_engine_rebinding_switches_kernels(eng, orc):
+    B, C, n = 512, 8, 6 * 512
+    h0, h1 = synth.decaying_ir(2000, 1500), synth.decaying_ir(2001, 900, 1)
+    x = np.stack([synth.white_noise(1002, c, n) for c in range(C)])
+    with eng.Engine(B, 3, C, 2) as e:
+        e.set_ir(0, h0)
+        e.set_ir(1, h1)
+        e.bind(1, 2, 1)                      # channel 1 differs from its tile mates -> per-row kernel
+        y = e.process_stream(x)
+        for c in range(C):
+            _check(y[c:c + 1], orc.convolve_periodic(x[c], h1 if c == 1 else h0, B)[:, :n])
+        e.reset()
+        e.bind(0, C, 0)                      # uniform again -> shared-IR kernel
+        y = e.process_stream(x)
+        for c in range(C):
+            _check(y[c:c + 1], orc.convolve_periodic(x[c], h0, B)[:, :n])
 
 
 def test_streaming_reset_restores_initial_state(eng):
