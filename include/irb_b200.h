@@ -132,6 +132,9 @@ int irb_averaging_filter(float* spec, int ch, int fft_size, double octave_fracti
 /* fp::tools::fftTransform / fftInvTransform (fp/tools.hpp:88-89, fp/tools.cpp:321-369) */
 int irb_fft_transform(const float* x, int ch, int len, int format_ampl_phase, float* out /* [ch][2N] */);
 int irb_fft_inv_transform(const float* spec, int ch, int fft_size, float* out /* [ch][fft_size/2] */);
+/* fp::ir::IRtoRealFFTRaw (fp/ir.hpp:36, fp/ir.cpp:106-147): partitioned packed spectra of an IR, the engine's own
+ * FDL/IR wire format; out[(len/part_size + 1) * 2*part_size] */
+int irb_ir_to_real_fft_raw(const float* x, int len, int part_size, float* out);
 /* fp::ExpSineSweep::generate / generateInv (fp/ExpSineSweep.hpp:27-33, fp/ExpSineSweep.cpp:26-41,59-79), FP64.
  * Returns the sweep length (int)(sample_rate*duration); out == NULL only queries it. */
 int irb_ess_generate(double duration_s, double sample_rate, double f1, double f2, double gain_db, int inverse, double* out, int capacity);

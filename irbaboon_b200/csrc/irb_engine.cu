@@ -443,6 +443,31 @@ int irb_engine_mac_only_device(irb_engine* e, float* acc_dev) {
     return 0;
 }
 
+// fp::ir::IRtoRealFFTRaw (fp/ir.cpp:106-147): the IR cut into len/part_size + 1 partitions of part_size samples, each
+// zero-padded to 2*part_size, transformed, stored as {Re X[0], Re X[N/2], re1, im1, ...} -- exactly the packed spectrum
+// rows of the engine.  out: (len/part_size + 1) * 2*part_size floats.  part_size must be a power of two in [16, 2048].
+int irb_ir_to_real_fft_raw(const float* x, int len, int part_size, float* out) {
+    if (!x || !out || len < 1) return fail(IRB_ERR_ARG, "bad argument");
+    if (part_size < 16 || part_size > kMaxM || (part_size & (part_size - 1))) return fail(IRB_ERR_ARG, "part_size %d must be a power of two in [16, %d]", part_size, kMaxM);
+    const int M = part_size, parts = len / part_size + 1, dev = irbh::g_device;
+    CK(cudaSetDevice(dev));
+    const float2* W = nullptr;
+    int rc = irbh::twiddles(dev, M, &W);
+    if (rc) return rc;
+    irbh::StreamGuard sg;
+    if ((rc = sg.create())) return rc;
+    DevBuf dx, dH;
+    if ((rc = dx.alloc(sizeof(float) * (size_t) len, false)) || (rc = dH.alloc(sizeof(float2) * (size_t) M * parts, true))) return rc;
+    CK(cudaMemcpyAsync(dx.p, x, sizeof(float) * (size_t) len, cudaMemcpyHostToDevice, sg.s));
+    irb::FwdArgs f{};
+    f.src = dx.as<float>(); f.src_chan_stride = 0; f.L = len; f.B = part_size; f.blocks_per_chan = parts; f.n_rows = parts;
+    f.dst = dH.as<float2>(); f.dst_chan_stride = 0; f.W = W;
+    if ((rc = launch_fwd(M, f, sg.s))) return rc;
+    CK(cudaMemcpyAsync(out, dH.p, sizeof(float2) * (size_t) M * parts, cudaMemcpyDeviceToHost, sg.s));
+    CK(cudaStreamSynchronize(sg.s));
+    return 0;
+}
+
 // fp::convolution::convolvePeriodic (fp/convolution.cpp:14-242) with every block processed at once:
 // all audio blocks are transformed in one launch, output block k sums X[k-p]*H[p] over the partitions
 // p <= k in ascending order (the reference's own order, :171-202), and the overlap of block k-1 is added

@@ -63,6 +63,7 @@ _SIGS = {
     "irb_averaging_filter": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "irb_fft_transform": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_fft_inv_transform": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_ir_to_real_fft_raw": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_ess_generate": (ctypes.c_int, [ctypes.c_double] * 5 + [ctypes.c_int, _vp, ctypes.c_int]),
 }
 
@@ -213,6 +214,14 @@ def fft_inv_transform(spec):
     s = _planar(spec)
     out = np.zeros((s.shape[0], s.shape[1] // 2), np.float32)
     _ck(lib().irb_fft_inv_transform(_ptr(s), s.shape[0], s.shape[1], _ptr(out)))
+    return out
+
+
+def ir_to_real_fft_raw(x, part_size):
+    """fp::ir::IRtoRealFFTRaw (fp/ir.cpp:106-147): packed partition spectra, (len/part + 1) * 2*part floats."""
+    x = np.ascontiguousarray(_planar(x)[0])
+    out = np.zeros((len(x) // part_size + 1) * 2 * part_size, np.float32)
+    _ck(lib().irb_ir_to_real_fft_raw(_ptr(x), len(x), int(part_size), _ptr(out)))
     return out
 
 

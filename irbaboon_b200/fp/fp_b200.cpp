@@ -161,3 +161,268 @@ void StreamingConvolver::process(const float* in, float* out, int nBlocks) {
 
 }  // namespace b200
 }  // namespace fp
+
+// =====================================================================================================
+// tools / ir / ExpSineSweep / remaining convolution functions
+// =====================================================================================================
+#include "ExpSineSweep.hpp"
+#include "ir.hpp"
+#include "tools.hpp"
+
+namespace fp {
+
+// ---- tools (fp/tools.cpp) -- small host helpers kept for source compatibility ---------------------------
+void tools::sumToMono(AudioBuffer<float>* buffer) {
+    if (buffer->getNumChannels() != 2) { DBG("sumToMono() error: input is not stereo\n"); return; }
+    float* l = buffer->getWritePointer(0);
+    float* r = buffer->getWritePointer(1);
+    for (int i = 0; i < buffer->getNumSamples(); ++i) { l[i] += r[i]; l[i] /= 2.0f; r[i] = 0.0f; }
+}
+void tools::makeStereo(AudioBuffer<float>* buffer) {
+    if (buffer->getNumChannels() != 1) { DBG("makeStereo() error: input is not mono\n"); return; }
+    buffer->setSize(2, buffer->getNumSamples(), true);
+    buffer->copyFrom(1, 0, *buffer, 0, 0, buffer->getNumSamples());
+}
+void tools::complexDivPolar(float* a, float* b, float c, float d) {
+    float amplA = std::sqrt((*a) * (*a) + (*b) * (*b)), phaseA = std::atan2(*b, *a);
+    const float amplB = std::sqrt(c * c + d * d), phaseB = std::atan2(d, c);
+    amplA /= amplB;
+    phaseA -= phaseB;
+    *a = amplA * std::cos(phaseA);
+    *b = amplA * std::sin(phaseA);
+}
+float tools::dBToLin(float dB) { return std::pow(10.0f, dB / 20.0f); }
+double tools::dBToLin(double dB) { return std::pow(10.0, dB / 20.0); }
+float tools::linTodB(float lin) { return lin == 0.0f ? -333.0f : 20.0f * std::log(lin) / std::log(10.0f); }
+double tools::linTodB(double lin) { return lin == 0.0 ? -333.0 : 20.0 * std::log(lin) / std::log(10.0); }
+void tools::normalize(AudioBuffer<float>* buffer, float dBGoalLevel, bool printGain) {
+    const float gain = dBToLin(dBGoalLevel) / buffer->getMagnitude(0, buffer->getNumSamples());
+    buffer->applyGain(gain);
+    if (printGain) std::printf("normalize gain: %g, dB: %9.6f\n", gain, linTodB(gain));
+}
+bool tools::isPowerOfTwo(int x) { return x != 0 && (x & (x - 1)) == 0; }
+int tools::nextPowerOfTwo(int x, int result) {
+    if (!isPowerOfTwo(result)) result = 1;
+    if (isPowerOfTwo(x)) return x;
+    while (result <= x) result *= 2;
+    return result;
+}
+void tools::roundToZero(float* x, float threshold) {
+    if (threshold < 0.0f) { DBG("tools::roundToZero error: threshold should be positive\n"); return; }
+    if (!std::signbit(*x) && *x < threshold) *x = 0.0f;
+    if (std::signbit(*x) && *x > -threshold) *x = 0.0f;
+}
+void tools::roundTo1TenQuadrillionth(float* x) {
+    if (!std::signbit(*x) && *x < 1e-16) *x = 1e-16;
+    if (std::signbit(*x) && *x > -1e-16) *x = -1e-16;
+}
+float tools::binAmpl(float* binPtr) { return (float) std::sqrt(std::pow((double) binPtr[0], 2.0) + std::pow((double) binPtr[1], 2.0)); }
+float tools::binPhase(float* binPtr) { return std::atan2(binPtr[1], binPtr[0]); }
+AudioBuffer<float> tools::generatePulse(int numSamples, int pulseOffset) {
+    AudioBuffer<float> pulse(1, numSamples);
+    pulse.clear();
+    if (pulseOffset >= numSamples || pulseOffset < 0) pulseOffset = 0;
+    pulse.setSample(0, pulseOffset, 1.0f);
+    return pulse;
+}
+void tools::linearFade(AudioBuffer<float>* buffer, bool fadeIn, int startSample, int numSamples) {
+    if (startSample + numSamples > buffer->getNumSamples()) { DBG("linearFade: startSample + numSamples exceeds buffer size.\n"); return; }
+    const float step = 1.0 / numSamples;
+    for (int c = 0; c < buffer->getNumChannels(); ++c)
+        for (int i = startSample; i < startSample + numSamples; ++i) {
+            const float gain = fadeIn ? (i - startSample) * step : 1.0 - (i - startSample) * step;
+            buffer->setSample(c, i, buffer->getSample(c, i) * gain);
+        }
+}
+void tools::sineFill(AudioBuffer<float>* buffer, float freq, float sampleRate, float ampl) {
+    if (ampl > 1.0 || ampl <= 0.0) ampl = 1.0;
+    for (int c = 0; c < buffer->getNumChannels(); ++c)
+        for (int i = 0; i < buffer->getNumSamples(); ++i) buffer->setSample(c, i, ampl * std::cos(M_PI * 2 * freq * i / sampleRate));
+}
+AudioBuffer<float> tools::fftTransform(AudioBuffer<float>& buffer, bool formatAmplPhase) {
+    const int ch = buffer.getNumChannels(), n = buffer.getNumSamples(), N = nextPowerOfTwo(n);
+    AudioBuffer<float> out(ch, 2 * N);
+    out.clear();
+    std::vector<float> x = pack(buffer), y((size_t) ch * 2 * N);
+    if (irb_fft_transform(x.data(), ch, n, formatAmplPhase ? 1 : 0, y.data()) != IRB_OK) raise("fp::tools::fftTransform");
+    for (int c = 0; c < ch; ++c) out.copyFrom(c, 0, y.data() + (size_t) c * 2 * N, 2 * N);
+    return out;
+}
+AudioBuffer<float> tools::fftInvTransform(AudioBuffer<float>& buffer) {
+    const int ch = buffer.getNumChannels(), fftSize = buffer.getNumSamples(), N = fftSize / 2;
+    AudioBuffer<float> out(ch, N);
+    std::vector<float> s = pack(buffer), y((size_t) ch * N);
+    if (irb_fft_inv_transform(s.data(), ch, fftSize, y.data()) != IRB_OK) raise("fp::tools::fftInvTransform");
+    for (int c = 0; c < ch; ++c) out.copyFrom(c, 0, y.data() + (size_t) c * N, N);
+    return out;
+}
+
+// ---- convolution (rest) -------------------------------------------------------------------------------
+AudioBuffer<float> convolution::convolveNonPeriodic(AudioBuffer<float>& buffer1, AudioBuffer<float>& buffer2) {
+    const int chx = buffer1.getNumChannels(), lx = buffer1.getNumSamples(), chh = buffer2.getNumChannels(), lh = buffer2.getNumSamples();
+    const int lout = lx + lh - 1;
+    std::vector<float> x = pack(buffer1), h = pack(buffer2), y((size_t) std::max(chx, 1) * std::max(lout, 1));
+    const int rc = irb_convolve_nonperiodic(x.data(), chx, lx, h.data(), chh, lh, y.data());
+    if (rc == IRB_ERR_LAYOUT) {
+        std::printf("Either buffer1 or buffer2 is not mono nor stereo. Abort abort \n");
+        AudioBuffer<float> cleared(buffer1);
+        cleared.clear();
+        return cleared;
+    }
+    if (rc != IRB_OK) raise("fp::convolution::convolveNonPeriodic");
+    AudioBuffer<float> out(chx, lout);
+    for (int c = 0; c < chx; ++c) out.copyFrom(c, 0, y.data() + (size_t) c * lout, lout);
+    return out;
+}
+AudioBuffer<float> convolution::deconvolve(AudioBuffer<float>* numeratorBuffer, AudioBuffer<float>* denominatorBuffer, double sampleRate, bool smoothing,
+                                           bool includePhase, bool includeAmplitude) {
+    const int ln = numeratorBuffer->getNumSamples(), ld = denominatorBuffer->getNumSamples();
+    const int N = tools::nextPowerOfTwo(std::max(ln, ld));
+    AudioBuffer<float> out(1, N);
+    if (irb_deconvolve(numeratorBuffer->getReadPointer(0), ln, denominatorBuffer->getReadPointer(0), ld, sampleRate, smoothing, includePhase, includeAmplitude,
+                       out.getWritePointer(0)) != IRB_OK)
+        raise("fp::convolution::deconvolve");
+    return out;
+}
+void convolution::averagingFilter(AudioBuffer<float>* buffer, double octaveFraction, double sampleRate, bool logAvg, bool includePhase, bool includeAmplitude) {
+    const int ch = buffer->getNumChannels(), fftSize = buffer->getNumSamples();
+    if (!tools::isPowerOfTwo(fftSize)) { DBG("applyBucket() error: input buffer size is not power of 2.\n"); return; }
+    std::vector<float> s = pack(*buffer);
+    if (irb_averaging_filter(s.data(), ch, fftSize, octaveFraction, sampleRate, logAvg, includePhase, includeAmplitude) != IRB_OK) raise("fp::convolution::averagingFilter");
+    for (int c = 0; c < ch; ++c) buffer->copyFrom(c, 0, s.data() + (size_t) c * fftSize, fftSize);
+}
+
+// ---- ir (fp/ir.cpp) ----------------------------------------------------------------------------------------
+AudioBuffer<float> ir::invertFilter(AudioBuffer<float>& buffer, int samplerate) {
+    const int n = buffer.getNumSamples();
+    AudioBuffer<float> out(1, tools::nextPowerOfTwo(n));
+    if (irb_invert_filter(buffer.getReadPointer(0), n, samplerate, out.getWritePointer(0)) != IRB_OK) raise("fp::ir::invertFilter");
+    return out;
+}
+void ir::shifteroo(AudioBuffer<float>* buffer) {
+    const int n = buffer->getNumSamples();
+    if (n < 2) return;
+    const int second = n / 2, first = n - second;
+    AudioBuffer<float> moved(buffer->getNumChannels(), n);
+    for (int c = 0; c < buffer->getNumChannels(); ++c) {
+        moved.copyFrom(c, 0, *buffer, c, first, second);
+        moved.copyFrom(c, second, *buffer, c, 0, first);
+    }
+    *buffer = moved;
+}
+AudioBuffer<float> ir::IRchop(AudioBuffer<float>& buffer, int IRlength, float thresholdLeveldB, int consecutiveSamplesBelowThreshold) {
+    const int n = buffer.getNumSamples();
+    const float* p = buffer.getReadPointer(0);
+    const float peak = buffer.getMagnitude(0, n);
+    int cursor = 0;
+    while (cursor < n && std::fabs(p[cursor]) != peak) ++cursor;          // first sample carrying the peak magnitude
+    if (cursor == n) cursor = 0;
+    const float peakdB = tools::linTodB(std::fabs(peak));
+    int below = 0, walked = 0;
+    while (below < consecutiveSamplesBelowThreshold) {                       // walk backwards (with wrap) to a quiet run
+        below = (tools::linTodB(std::fabs(p[cursor])) - peakdB < thresholdLeveldB) ? below + 1 : 0;
+        if (--cursor < 0) cursor = n - 1;
+        if (++walked == IRlength) break;
+    }
+    const int start = cursor;
+    const int head = (IRlength + start > n - 1) ? n - start : IRlength;
+    AudioBuffer<float> IR(1, IRlength);
+    IR.clear();
+    IR.copyFrom(0, 0, buffer, 0, start, head);
+    if (head < IRlength) IR.copyFrom(0, head, buffer, 0, 0, IRlength - head);  // the part folded around the end
+    const int fadeOut = IRlength / 4;
+    tools::linearFade(&IR, false, IRlength - 1 - fadeOut, fadeOut);
+    tools::linearFade(&IR, true, 0, walked / 4);
+    return IR;
+}
+AudioBuffer<float> ir::IRtoRealFFTRaw(AudioBuffer<float>& buffer, int irPartSize) {
+    const int n = buffer.getNumSamples(), parts = n / irPartSize + 1;
+    AudioBuffer<float> out(1, parts * 2 * irPartSize);
+    if (irb_ir_to_real_fft_raw(buffer.getReadPointer(0), n, irPartSize, out.getWritePointer(0)) != IRB_OK) raise("fp::ir::IRtoRealFFTRaw");
+    return out;
+}
+
+// ---- ExpSineSweep (fp/ExpSineSweep.cpp) ---------------------------------------------------------------------
+ExpSineSweep::ExpSineSweep() {}
+ExpSineSweep::~ExpSineSweep() {}
+void ExpSineSweep::assignParameters(double durationSecs, double sampleRate, double lowFreq, double highFreq) {
+    SR = sampleRate;
+    T = SR * durationSecs;
+    w1 = lowFreq / SR * 2 * M_PI;
+    w2 = highFreq / SR * 2 * M_PI;
+    K = T * w1 / std::log(w2 / w1);
+    L = T / std::log(w2 / w1);
+}
+void ExpSineSweep::generate(double durationSecs, double sampleRate, double lowFreq, double highFreq, double dBGain) {
+    assignParameters(durationSecs, sampleRate, lowFreq, highFreq);
+    genDuration = durationSecs; genLow = lowFreq; genHigh = highFreq; gendB = dBGain;
+    const int n = (int) T;
+    sweep.setSize(1, n);
+    if (n > 0 && irb_ess_generate(durationSecs, sampleRate, lowFreq, highFreq, dBGain, 0, sweep.getWritePointer(0), n) < 0) raise("fp::ExpSineSweep::generate");
+}
+AudioBuffer<double> ExpSineSweep::getSweep() { return sweep; }
+AudioBuffer<float> ExpSineSweep::getSweepFloat() { AudioBuffer<float> f; f.makeCopyOf(sweep); return f; }
+void ExpSineSweep::generateInv() {
+    if (sweep.getNumSamples() == 0) { DBG("ExpSineSweep::generateInv(): seems like generate() has not been used first to create sweep attribute. \n"); return; }
+    // the reference reverses the CURRENT sweep buffer (fades included) and applies -6 dB/oct sample by sample
+    sweepInv.makeCopyOf(sweep);
+    sweepInv.reverse(0, sweepInv.getNumSamples());
+    k = std::pow(10.0, (-6.0 * std::log2(w2 / w1)) / 20.0 / T);
+    kend = std::pow(k, T);
+    double* p = sweepInv.getWritePointer(0);
+    double gain = k;
+    for (int i = 0; i < sweepInv.getNumSamples(); ++i) { p[i] *= gain; gain *= k; }
+}
+void ExpSineSweep::generateInv(double durationSecs, double sampleRate, double lowFreq, double highFreq, double dBGain) {
+    generate(durationSecs, sampleRate, lowFreq, highFreq, dBGain);
+    generateInv();
+}
+AudioBuffer<double> ExpSineSweep::getSweepInv() { return sweepInv; }
+AudioBuffer<float> ExpSineSweep::getSweepInvFloat() { AudioBuffer<float> f; f.makeCopyOf(sweepInv); return f; }
+double ExpSineSweep::getFreqAtSampleIndexHelper(int index) {
+    if (index < 0 || index >= (int) T) { DBG("index out of bounds. \n"); return -1; }
+    const double lowFreq = w1 * SR / (2 * M_PI), totalOct = std::log(w2 / w1) / std::log(2);
+    return lowFreq * std::pow(2.0, (double) index / T * totalOct);
+}
+int ExpSineSweep::getSampleHelper(double freq) {
+    const double lowFreq = w1 * SR / (2 * M_PI);
+    const double oct = std::log(freq / lowFreq) / std::log(2), totalOct = std::log(w2 / w1) / std::log(2);
+    const int t = (int) std::round(oct / totalOct * T);
+    if (t < 0 || t >= T) { DBG("Specified frequency is out of bounds for this sweep. \n"); return -1; }
+    return t;
+}
+int ExpSineSweep::getSampleIndexAtFreq(double freq) {
+    if (sweep.getNumSamples() == 0) { DBG("sweep has not been generated yet. Try overloaded function? \n"); return -1; }
+    return getSampleHelper(freq);
+}
+int ExpSineSweep::getSampleIndexAtFreq(double freq, double durationSecs, double sampleRate, double lowFreq, double highFreq) {
+    assignParameters(durationSecs, sampleRate, lowFreq, highFreq);
+    return getSampleHelper(freq);
+}
+double ExpSineSweep::getFreqAtSampleIndex(int index) {
+    if (sweep.getNumSamples() == 0) { DBG("sweep has not been generated yet. Try overloaded function? \n"); return -1; }
+    return getFreqAtSampleIndexHelper(index);
+}
+double ExpSineSweep::getFreqAtSampleIndex(int index, double durationSecs, double sampleRate, double lowFreq, double highFreq) {
+    assignParameters(durationSecs, sampleRate, lowFreq, highFreq);
+    return getFreqAtSampleIndexHelper(index);
+}
+void ExpSineSweep::linFadeout(double freq) {
+    if (sweep.getNumSamples() == 0) { DBG("Sweep has not been generated yet. \n"); return; }
+    const int index = getSampleIndexAtFreq(freq), len = sweep.getNumSamples() - index;
+    for (int i = index; i < sweep.getNumSamples(); ++i) sweep.setSample(0, i, sweep.getSample(0, i) * (len - (i - index)) / len);
+}
+void ExpSineSweep::dBFadeout(double freq) {
+    if (sweep.getNumSamples() == 0) { DBG("Sweep has not been generated yet. \n"); return; }
+    const int index = getSampleIndexAtFreq(freq), len = sweep.getNumSamples() - index;
+    const double perSample = tools::dBToLin(-80.0 / len);
+    double g = perSample;
+    for (int i = index; i < sweep.getNumSamples(); ++i) { sweep.setSample(0, i, sweep.getSample(0, i) * g); g *= perSample; }
+}
+void ExpSineSweep::brickwallFadeout(double freq) {
+    if (sweep.getNumSamples() == 0) { DBG("Sweep has not been generated yet. \n"); return; }
+    const int index = getSampleIndexAtFreq(freq);
+    sweep.clear(index, sweep.getNumSamples() - index);
+}
+
+}  // namespace fp

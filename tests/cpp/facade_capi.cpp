@@ -44,3 +44,85 @@ int fac_convolve_periodic(const float* x, int chx, int Lx, const float* h, int c
     }
 }
 }
+
+// ---- the rest of the fp:: surface ---------------------------------------------------------------------------
+#include "../../irbaboon_b200/fp/ExpSineSweep.hpp"
+#include "../../irbaboon_b200/fp/ir.hpp"
+#include "../../irbaboon_b200/fp/tools.hpp"
+extern "C" {
+int fac_convolve_nonperiodic(const float* x, int chx, int Lx, const float* h, int chh, int Lh, float* out) {
+    AudioBuffer<float> bx(chx, Lx), bh(chh, Lh);
+    fill(bx, x); fill(bh, h);
+    try { AudioBuffer<float> r = fp::convolution::convolveNonPeriodic(bx, bh); dump(r, out); return r.getNumSamples(); } catch (const std::exception&) { return -1; }
+}
+int fac_deconvolve(const float* num, int Ln, const float* den, int Ld, double sr, int smoothing, int phase, int ampl, float* out) {
+    AudioBuffer<float> bn(1, Ln), bd(1, Ld);
+    fill(bn, num); fill(bd, den);
+    try { AudioBuffer<float> r = fp::convolution::deconvolve(&bn, &bd, sr, smoothing, phase, ampl); dump(r, out); return r.getNumSamples(); } catch (const std::exception&) { return -1; }
+}
+int fac_averaging_filter(float* spec, int ch, int fftSize, double oct, double sr, int logAvg, int phase, int ampl) {
+    AudioBuffer<float> b(ch, fftSize);
+    fill(b, spec);
+    try { fp::convolution::averagingFilter(&b, oct, sr, logAvg, phase, ampl); dump(b, spec); return 0; } catch (const std::exception&) { return -1; }
+}
+int fac_fft_roundtrip(const float* x, int ch, int L, float* spec, float* back) {
+    AudioBuffer<float> b(ch, L);
+    fill(b, x);
+    try {
+        AudioBuffer<float> s = fp::tools::fftTransform(b);
+        dump(s, spec);
+        AudioBuffer<float> r = fp::tools::fftInvTransform(s);
+        dump(r, back);
+        return s.getNumSamples();
+    } catch (const std::exception&) { return -1; }
+}
+int fac_invert_filter(const float* x, int L, int sr, float* out) {
+    AudioBuffer<float> b(1, L);
+    fill(b, x);
+    try { AudioBuffer<float> r = fp::ir::invertFilter(b, sr); dump(r, out); return r.getNumSamples(); } catch (const std::exception&) { return -1; }
+}
+int fac_ir_to_real_fft_raw(const float* x, int L, int part, float* out) {
+    AudioBuffer<float> b(1, L);
+    fill(b, x);
+    try { AudioBuffer<float> r = fp::ir::IRtoRealFFTRaw(b, part); dump(r, out); return r.getNumSamples(); } catch (const std::exception&) { return -1; }
+}
+int fac_ir_chop(const float* x, int L, int IRlength, float thr, int consecutive, float* out) {
+    AudioBuffer<float> b(1, L);
+    fill(b, x);
+    AudioBuffer<float> r = fp::ir::IRchop(b, IRlength, thr, consecutive);
+    dump(r, out);
+    return r.getNumSamples();
+}
+void fac_shifteroo(float* buf, int ch, int n) { AudioBuffer<float> b(ch, n); fill(b, buf); fp::ir::shifteroo(&b); dump(b, buf); }
+void fac_sum_to_mono(float* buf, int ch, int n) { AudioBuffer<float> b(ch, n); fill(b, buf); fp::tools::sumToMono(&b); dump(b, buf); }
+void fac_linear_fade(float* buf, int ch, int n, int fadeIn, int start, int count) { AudioBuffer<float> b(ch, n); fill(b, buf); fp::tools::linearFade(&b, fadeIn, start, count); dump(b, buf); }
+void fac_normalize(float* buf, int ch, int n, float dB) { AudioBuffer<float> b(ch, n); fill(b, buf); fp::tools::normalize(&b, dB); dump(b, buf); }
+void fac_sine_fill(float* buf, int ch, int n, float f, float sr, float a) { AudioBuffer<float> b(ch, n); fp::tools::sineFill(&b, f, sr, a); dump(b, buf); }
+void fac_generate_pulse(int n, int off, float* out) { AudioBuffer<float> r = fp::tools::generatePulse(n, off); dump(r, out); }
+void fac_complex_ops(float* v) {   // v = {a, b, c, d} -> {mul.re, mul.im, div.re, div.im, polar.re, polar.im, ampl, phase}
+    float a = v[0], b = v[1]; fp::tools::complexMul(&a, &b, v[2], v[3]); float m0 = a, m1 = b;
+    a = v[0]; b = v[1]; fp::tools::complexDivCartesian(&a, &b, v[2], v[3]); float d0 = a, d1 = b;
+    a = v[0]; b = v[1]; fp::tools::complexDivPolar(&a, &b, v[2], v[3]);
+    float bin[2] = {v[0], v[1]};
+    float am = fp::tools::binAmpl(bin), ph = fp::tools::binPhase(bin);
+    v[0] = m0; v[1] = m1; v[2] = d0; v[3] = d1; v[4] = a; v[5] = b; v[6] = am; v[7] = ph;
+}
+float fac_db_to_lin(float dB) { return fp::tools::dBToLin(dB); }
+float fac_lin_to_db(float lin) { return fp::tools::linTodB(lin); }
+int fac_next_pow2(int x) { return fp::tools::nextPowerOfTwo(x); }
+void fac_round(float* v) { fp::tools::roundToZero(v, 1e-11f); fp::tools::roundTo1TenQuadrillionth(v + 1); }
+// mode 0 sweep, 1 inverse; fadeKind 0 none, 1 lin, 2 dB, 3 brickwall (applied before the inverse is built)
+int fac_ess(double dur, double sr, double f1, double f2, double dB, int mode, int fadeKind, double fadeFreq, double* out) {
+    fp::ExpSineSweep s;
+    try { s.generate(dur, sr, f1, f2, dB); } catch (const std::exception&) { return -1; }
+    if (fadeKind == 1) s.linFadeout(fadeFreq);
+    if (fadeKind == 2) s.dBFadeout(fadeFreq);
+    if (fadeKind == 3) s.brickwallFadeout(fadeFreq);
+    AudioBuffer<double> r;
+    if (mode == 1) { s.generateInv(); r = s.getSweepInv(); } else r = s.getSweep();
+    if (out) std::copy_n(r.getReadPointer(0), r.getNumSamples(), out);
+    return r.getNumSamples();
+}
+int fac_ess_index_at_freq(double freq, double dur, double sr, double f1, double f2) { fp::ExpSineSweep s; return s.getSampleIndexAtFreq(freq, dur, sr, f1, f2); }
+double fac_ess_freq_at_index(int idx, double dur, double sr, double f1, double f2) { fp::ExpSineSweep s; return s.getFreqAtSampleIndex(idx, dur, sr, f1, f2); }
+}

@@ -152,3 +152,141 @@ def test_facade_fails_loudly_without_a_gpu(fac, eng):
     h = np.ones((1, 10), np.float32)
     out = np.zeros((1, 109), np.float32)
     assert fac.fac_convolve_periodic(x.ctypes.data_as(_f32p), 1, 100, h.ctypes.data_as(_f32p), 1, 10, 16, out.ctypes.data_as(_f32p)) == -1
+
+
+# ---- host-side helpers of the facade against the reference's own functions (CPU) ---------------------------------
+def _fp(a):
+    return a.ctypes.data_as(_f32p)
+
+
+def test_tools_scalar_helpers_match_reference(fac, ref):
+    R = ref.lib
+    rng = np.random.default_rng(3)
+    fac.fac_db_to_lin.restype = R.ref_db_to_lin.restype = ctypes.c_float
+    fac.fac_lin_to_db.restype = R.ref_lin_to_db.restype = ctypes.c_float
+    R.ref_bin_ampl.restype = R.ref_bin_phase.restype = ctypes.c_float
+    for _ in range(50):
+        v = rng.standard_normal(4).astype(np.float32)
+        mine = np.zeros(8, np.float32); mine[:4] = v
+        fac.fac_complex_ops(_fp(mine))
+        a, b = ctypes.c_float(v[0]), ctypes.c_float(v[1])
+        R.ref_complex_mul(ctypes.byref(a), ctypes.byref(b), ctypes.c_float(v[2]), ctypes.c_float(v[3]))
+        assert (mine[0], mine[1]) == (a.value, b.value)
+        a, b = ctypes.c_float(v[0]), ctypes.c_float(v[1])
+        R.ref_complex_div_cartesian(ctypes.byref(a), ctypes.byref(b), ctypes.c_float(v[2]), ctypes.c_float(v[3]))
+        assert (mine[2], mine[3]) == (a.value, b.value)
+        a, b = ctypes.c_float(v[0]), ctypes.c_float(v[1])
+        R.ref_complex_div_polar(ctypes.byref(a), ctypes.byref(b), ctypes.c_float(v[2]), ctypes.c_float(v[3]))
+        assert np.allclose([mine[4], mine[5]], [a.value, b.value], rtol=1e-6, atol=1e-7)
+        bin_ = (ctypes.c_float * 2)(v[0], v[1])
+        assert mine[6] == R.ref_bin_ampl(bin_) and mine[7] == R.ref_bin_phase(bin_)
+    for x in (-60.0, -3.0, 0.0, 6.0):
+        assert fac.fac_db_to_lin(ctypes.c_float(x)) == R.ref_db_to_lin(ctypes.c_float(x))
+    for x in (0.0, 1e-3, 1.0, 2.5):
+        assert fac.fac_lin_to_db(ctypes.c_float(x)) == R.ref_lin_to_db(ctypes.c_float(x))
+    for x in (0, 1, 2, 3, 5, 64, 65, 1000, 65536, 70000):
+        assert fac.fac_next_pow2(x) == R.ref_next_pow2(x)
+    for val in (5e-12, -5e-12, 1e-10, -1e-10, 0.0, 1e-17, -1e-17, 3.0):
+        mine = np.array([val, val], np.float32)
+        fac.fac_round(_fp(mine))
+        a, b = ctypes.c_float(val), ctypes.c_float(val)
+        R.ref_round_to_zero(ctypes.byref(a), ctypes.c_float(1e-11)); R.ref_round_to_1e16(ctypes.byref(b))
+        assert (mine[0], mine[1]) == (a.value, b.value)
+
+
+def test_tools_buffer_helpers_match_reference(fac, ref):
+    R = ref.lib
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((2, 100)).astype(np.float32)
+    for name, args in (("sum_to_mono", ()), ("linear_fade", (1, 10, 50)), ("linear_fade", (0, 40, 60)), ("linear_fade", (0, 90, 20))):
+        a, b = x.copy(), x.copy()
+        getattr(fac, "fac_" + name)(_fp(a), 2, 100, *args)
+        getattr(R, "ref_" + name)(_fp(b), 2, 100, *args)
+        assert np.array_equal(a, b), name
+    a, b = x.copy(), x.copy()
+    fac.fac_normalize(_fp(a), 2, 100, ctypes.c_float(-6.0)); R.ref_normalize(_fp(b), 2, 100, ctypes.c_float(-6.0))
+    assert np.array_equal(a, b)
+    a, b = np.zeros((2, 64), np.float32), np.zeros((2, 64), np.float32)
+    fac.fac_sine_fill(_fp(a), 2, 64, ctypes.c_float(1000.0), ctypes.c_float(48000.0), ctypes.c_float(0.5))
+    R.ref_sine_fill(_fp(b), 2, 64, ctypes.c_float(1000.0), ctypes.c_float(48000.0), ctypes.c_float(0.5))
+    assert np.array_equal(a, b)
+    for n, off in ((16, 0), (16, 5), (16, 16), (16, -1)):
+        a, b = np.ones(n, np.float32), np.ones(n, np.float32)
+        fac.fac_generate_pulse(n, off, _fp(a)); R.ref_generate_pulse(n, off, _fp(b))
+        assert np.array_equal(a, b)
+    for n in (2, 9, 10):
+        a = np.arange(2 * n, dtype=np.float32).reshape(2, n); b = a.copy()
+        fac.fac_shifteroo(_fp(a), 2, n); R.ref_shifteroo(_fp(b), 2, n)
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("seed,L,irlen,thr,cons", [(0, 4000, 1000, -30.0, 20), (1, 4000, 3999, -20.0, 5), (2, 500, 400, -60.0, 50), (3, 2048, 512, -10.0, 3)])
+def test_ir_chop_matches_reference(fac, ref, seed, L, irlen, thr, cons):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal(L) * np.exp(-np.arange(L) / (L / 8.0))).astype(np.float32)
+    x = np.roll(x, L // 3 if seed % 2 == 0 else L - 40)          # peak in the middle / near the end (wrap-around copy)
+    got = np.zeros(irlen, np.float32)
+    assert fac.fac_ir_chop(_fp(x), L, irlen, ctypes.c_float(thr), cons, _fp(got)) == irlen
+    assert np.array_equal(got, ref.ir_chop(x, irlen, thr, cons)[0])
+
+
+def test_exp_sine_sweep_helpers_match_reference(fac, ref):
+    args = (0.25, 48000.0, 20.0, 20000.0)
+    fac.fac_ess_freq_at_index.restype = ctypes.c_double
+    fac.fac_ess_index_at_freq.argtypes = [ctypes.c_double] * 5
+    fac.fac_ess_freq_at_index.argtypes = [ctypes.c_int] + [ctypes.c_double] * 4
+    for f in (20.0, 100.0, 1000.0, 19999.0, 5.0, 30000.0):
+        assert fac.fac_ess_index_at_freq(f, *args) == ref.ess_index_at_freq(f, *args)
+    for i in (0, 1, 5999, 11999, -1, 12000):
+        assert fac.fac_ess_freq_at_index(i, *args) == ref.ess_freq_at_index(i, *args)
+
+
+# ---- GPU-backed functions through the facade -------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_facade_spectral_functions_on_gpu(fac, orc):
+    x = synth.white_noise(1001, 0, 3000)
+    h = synth.decaying_ir(2000, 900)
+    out = np.zeros(3899, np.float32)
+    assert fac.fac_convolve_nonperiodic(_fp(x), 1, 3000, _fp(h), 1, 900, _fp(out)) == 3899
+    e, l2 = parity(out[None, :], orc.convolve_nonperiodic(x, h))
+    assert e <= TOL and l2 <= TOL
+    x3 = np.ones((3, 20), np.float32)
+    out3 = np.ones((3, 20), np.float32)
+    assert fac.fac_convolve_nonperiodic(_fp(x3), 3, 20, _fp(h), 1, 900, _fp(out3)) == 20 and not out3.any()    # cleared copy of the input
+    fac.fac_deconvolve.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int, ctypes.c_double] + [ctypes.c_int] * 3 + [_f32p]
+    y = orc.convolve_nonperiodic(x, h)[0]
+    num, den = np.pad(y, (0, 4096 - len(y))), np.pad(x, (0, 1096))
+    for smoothing, tol in ((0, TOL), (1, 1e-4)):
+        got = np.zeros(4096, np.float32)
+        assert fac.fac_deconvolve(_fp(num), 4096, _fp(den), 4096, 48000.0, smoothing, 1, 1, _fp(got)) == 4096
+        e, l2 = parity(got[None, :], orc.deconvolve(num, den, 48000.0, bool(smoothing)))
+        assert e <= 2 * TOL and l2 <= tol
+    spec, back = np.zeros((1, 8192), np.float32), np.zeros((1, 4096), np.float32)
+    assert fac.fac_fft_roundtrip(_fp(x), 1, 3000, _fp(spec), _fp(back)) == 8192
+    assert np.abs(spec - orc.fft_transform(x)).max() <= 1e-5 * np.abs(spec).max() and np.abs(back[0, :3000] - x).max() <= 2e-6
+    inv = np.zeros(1024, np.float32)
+    assert fac.fac_invert_filter(_fp(h), 900, 48000, _fp(inv)) == 1024
+    e, l2 = parity(inv[None, :], orc.invert_filter(h, 48000))
+    assert e <= 2e-5 and l2 <= 1e-4
+    fac.fac_averaging_filter.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double] + [ctypes.c_int] * 3
+    s0 = orc.fft_transform(x)
+    mine = s0.copy()
+    assert fac.fac_averaging_filter(_fp(mine), 1, 8192, 1.0 / 13.0, 48000.0, 1, 1, 1) == 0
+    e, l2 = parity(mine[:, :4098], orc.averaging_filter(s0, 1.0 / 13.0, 48000.0)[:, :4098])
+    assert e <= 2e-5 and l2 <= 5e-5
+
+
+@pytest.mark.gpu
+def test_facade_ir_to_real_fft_raw_and_sweep_on_gpu(fac, ref):
+    h = synth.decaying_ir(2000, 1000)
+    want = ref.ir_to_real_fft_raw(h, 256)
+    got = np.zeros_like(want)
+    assert fac.fac_ir_to_real_fft_raw(_fp(h), 1000, 256, _fp(got)) == len(want)
+    assert np.abs(got - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
+    fac.fac_ess.argtypes = [ctypes.c_double] * 5 + [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+    for mode in (0, 1):
+        for kind, ff in ((0, 0.0), (1, 15000.0), (2, 15000.0), (3, 15000.0)):
+            want = ref.ess(0.25, 48000.0, 20.0, 20000.0, -3.0, bool(mode), kind, ff)
+            got = np.zeros(len(want), np.float64)
+            assert fac.fac_ess(0.25, 48000.0, 20.0, 20000.0, -3.0, mode, kind, ff, got.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == len(want)
+            assert np.abs(got - want).max() <= 1e-9
