@@ -62,6 +62,9 @@ def c2(eng, synth, args):
         for c in range(C):
             e.set_ir(c, synth.decaying_ir(2000 + c, Lh, c))
             e.bind(c, c + 1, c)                                   # channel-wise stereo IR (IRStereoAudioStereo)
+        if args.c2_split:
+            e.set_mac_split(*[int(v) for v in args.c2_split.split(",")])
+        plan = e.mac_plan()
         x = eng.pinned_empty((nblk, C, B))
         y = eng.pinned_empty((nblk, C, B))
         rng = np.random.default_rng(1002)
@@ -78,7 +81,7 @@ def c2(eng, synth, args):
         eng.pinned_free(x); eng.pinned_free(y)
     period = 1e3 * B / SR
     return {"config": "c2", "what": "stereo, B=256, 4 s stereo IR (750 partitions/channel), one stream, one irb_engine_process call per block",
-            "blocks": nblk, "block_period_ms": period,
+            "blocks": nblk, "block_period_ms": period, "mac_plan": {"slots_kernel": plan[0], "split_in_tile": plan[1], "cluster": plan[2]},
             "device_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)), "max": float(step_ms.max())},
             "roundtrip_ms": {"p50": float(np.percentile(rt, 50) * 1e3), "p99": float(np.percentile(rt, 99) * 1e3), "max": float(rt.max() * 1e3)},
             "mac_kernel_ms_mean": float(mac_ms.mean()), "realtime": bool(np.percentile(rt, 99) * 1e3 < period)}
@@ -167,6 +170,7 @@ def main():
     ap.add_argument("--configs", default="c1,c2,c4,c5")
     ap.add_argument("--out", default="")
     ap.add_argument("--c2-blocks", type=int, default=10000)
+    ap.add_argument("--c2-split", default="", help="force the few-row MAC split 'split_in,cluster' (default: automatic)")
     ap.add_argument("--c4-streams", type=int, default=8192)
     ap.add_argument("--c4-steps", type=int, default=30)
     ap.add_argument("--c5-captures", type=int, default=256)

@@ -64,11 +64,23 @@ int irb_engine_set_stream(irb_engine* e, void* cuda_stream);
  * PluginProcessor.cpp:455-461, done for all partitions at once).  n_taps <= block_size*max_partitions.
  * right != NULL folds a stereo IR to (left+right)/2 first (tools::sumToMono, fp/tools.cpp:13-30). */
 int irb_engine_set_ir(irb_engine* e, int ir_id, const float* left, const float* right, int n_taps);
+/* Switch an IR the way the plug-in does (IRtoConvolve, PluginProcessor.cpp:411-414): nothing is transformed here; each
+ * following block step re-transforms ONE partition of the staged taps, round-robin (:455-461), inside the step's own
+ * forward-FFT launch, so the new IR replaces the old one partition by partition over `partitions` blocks.  The first
+ * call for an ir_id fixes its partition count (n_partitions, or ceil(n_taps/block_size) when 0; later calls with 0
+ * keep it) and, if nothing was loaded before, starts from cleared spectra as prepareToPlay does (:225-226).  Taps beyond
+ * n_partitions*block_size are never read; shorter IRs are zero-extended. */
+int irb_engine_stage_ir(irb_engine* e, int ir_id, const float* left, const float* right, int n_taps, int n_partitions);
 /* channels [chan_begin, chan_end) convolve with ir_id.  When every kernel tile (irb_engine_tile_channels()
  * consecutive channels) is bound to one IR the tile shares the staged IR spectra; otherwise the per-stream-IR
  * kernel is used (each channel stages its own partitions; twice the memory traffic). */
 int irb_engine_bind(irb_engine* e, int chan_begin, int chan_end, int ir_id);
 int irb_engine_tile_channels(const irb_engine* e);
+/* How the next block step will launch the MAC: *slots_kernel = 1 when the per-slot kernel runs (mixed IRs in a tile, or
+ * few rows), *split_in = tile slots sharing a row, *cluster = CTAs per cluster splitting the partitions further. */
+int irb_engine_mac_plan(irb_engine* e, int* slots_kernel, int* split_in, int* cluster);
+/* Force the split (powers of two; clamped to what the tile allows; 1,1 = one CTA per tile) or return to automatic (0,0). */
+int irb_engine_set_mac_split(irb_engine* e, int split_in, int cluster);
 /* clear FDL rings, overlap buffers and heads (prepareToPlay, PluginProcessor.cpp:164-234) */
 int irb_engine_reset(irb_engine* e);
 
@@ -78,6 +90,12 @@ int irb_engine_reset(irb_engine* e);
  *   _process_device : DEVICE buffers on the engine's stream; asynchronous. */
 int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int n_blocks);
 int irb_engine_process_device(irb_engine* e, const float* in_dev, float* out_dev, int n_blocks);
+/* The block order of ONE plug-in callback (PluginProcessor.cpp:421-518): all n_blocks blocks are transformed into the
+ * FDL first, then convolved one after the other, each preceded by one round-robin IR refresh.  Identical to
+ * _process for n_blocks == 1; for n_blocks > 1 it reproduces the reference when the host block exceeds
+ * processBlockSize (its oldest partitions then meet FDL slots already overwritten by the callback's later blocks
+ * unless max_partitions >= partitions + n_blocks - 1).  HOST buffers [n_blocks][n_channels][block_size]. */
+int irb_engine_process_callback(irb_engine* e, const float* in_host, float* out_host, int n_blocks);
 int irb_engine_synchronize(irb_engine* e);
 
 /* Per-step device timing with CUDA events on the engine's stream: whole block step (k_fwd + k_mac) and the

@@ -1,11 +1,13 @@
 // irb_engine.cu -- host side of libirb_b200.so: the C ABI declared in include/irb_b200.h over the
 // kernels in irb_kernels.cuh.  No CPU compute path exists in this file: every entry point either
 // launches sm_100a kernels or fails with IRB_ERR_CUDA.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -79,33 +81,59 @@ int mac_u_pref() {
 
 template <int M>
 int launch_fwd_t(const irb::FwdArgs& a, cudaStream_t st) {
-    const int grid = (a.n_rows + irb::Tile<M>::ROWS - 1) / irb::Tile<M>::ROWS;
+    constexpr int R = irb::Tile<M>::ROWS;
+    const int grid = (a.n_rows + R - 1) / R + (a.n_rr + R - 1) / R;
     if (grid <= 0) return 0;
     irb::k_fwd<M><<<grid, irb::kThreads, 0, st>>>(a);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
 }
-template <int M, int U, bool INV, bool PRI = false>
+template <int M, int U, bool INV>
 int launch_mac_u(const irb::MacArgs& a, cudaStream_t st) {
     const int grid = (a.n_rows + irb::Tile<M>::ROWS - 1) / irb::Tile<M>::ROWS;
     if (grid <= 0) return 0;
-    const size_t smem = sizeof(irb::MacSmem<M, U, PRI>);
+    const size_t smem = sizeof(irb::MacSmem<M, U>);
     static thread_local int configured_dev = -1;
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        CK(cudaFuncSetAttribute(irb::k_mac<M, U, INV, PRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CK(cudaFuncSetAttribute(irb::k_mac<M, U, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         configured_dev = dev;
     }
-    irb::k_mac<M, U, INV, PRI><<<grid, irb::kThreads + 32, smem, st>>>(a);
+    irb::k_mac<M, U, INV><<<grid, irb::kThreads + 32, smem, st>>>(a);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
 }
+// slot kernel: a.split_in slots per row inside a tile, clusters of `cl` CTAs splitting the partitions further
 template <int M, bool INV>
-int launch_mac_t(const irb::MacArgs& a, bool per_row_ir, cudaStream_t st) {
-    if (per_row_ir) return launch_mac_u<M, 1, INV, true>(a, st);
+int launch_slots_t(const irb::MacArgs& a, int cl, cudaStream_t st) {
+    const int rpt = irb::Tile<M>::ROWS / a.split_in;
+    const int tiles = (a.n_rows + rpt - 1) / rpt;
+    if (tiles <= 0) return 0;
+    const size_t smem = sizeof(irb::SlotSmem<M>);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CK(cudaFuncSetAttribute(irb::k_mac_slots<M, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CK(cudaFuncSetAttribute(irb::k_mac_slots<M, INV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        configured_dev = dev;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned) (tiles * cl)); cfg.blockDim = dim3(irb::kThreads + 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned) cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, irb::k_mac_slots<M, INV>, a));
+    g_launches++;
+    return 0;
+}
+template <int M, bool INV>
+int launch_mac_t(const irb::MacArgs& a, bool slots, int cl, cudaStream_t st) {
+    if (slots) return launch_slots_t<M, INV>(a, cl, st);
     if constexpr (M <= 512) { if (mac_u_pref() == 2) return launch_mac_u<M, 2, INV>(a, st); }
     return launch_mac_u<M, 1, INV>(a, st);
 }
@@ -122,9 +150,9 @@ int launch_mac_t(const irb::MacArgs& a, bool per_row_ir, cudaStream_t st) {
         default: return fail(IRB_ERR_ARG, "unsupported FFT half size %d", M_); \
     }
 int launch_fwd(int M, const irb::FwdArgs& a, cudaStream_t st) { IRB_DISPATCH_M(M, launch_fwd_t<MM>(a, st)); }
-int launch_mac(int M, bool inv, bool per_row_ir, const irb::MacArgs& a, cudaStream_t st) {
-    if (inv) { IRB_DISPATCH_M(M, (launch_mac_t<MM, true>(a, per_row_ir, st))); }
-    IRB_DISPATCH_M(M, (launch_mac_t<MM, false>(a, per_row_ir, st)));
+int launch_mac(int M, bool inv, bool slots, int cl, const irb::MacArgs& a, cudaStream_t st) {
+    if (inv) { IRB_DISPATCH_M(M, (launch_mac_t<MM, true>(a, slots, cl, st))); }
+    IRB_DISPATCH_M(M, (launch_mac_t<MM, false>(a, slots, cl, st)));
 }
 int tile_rows(int M) { return irb::kTile / M; }
 
@@ -138,7 +166,19 @@ struct irb_engine {
     DevBuf fdl, H, ov, head, ir_of_chan, nparts, io_in[2], io_out[2], taps;
     std::vector<int> h_ir_of_chan, h_nparts;
     bool binding_dirty = true;
-    bool per_row_ir = false;           // some kernel tile mixes IRs: use the per-row-IR MAC kernel
+    bool per_row_ir = false;           // some kernel tile mixes IRs: every slot stages its own IR partitions (k_mac_slots)
+    // launch plan of the MAC (recomputed when bindings or IR lengths change): with few rows the partitions of a row
+    // are split over split_in slots of a tile and cluster_dim CTAs of a cluster (k_mac_slots)
+    bool plan_dirty = true;
+    int split_in = 1, cluster_dim = 1;
+    int force_split_in = 0, force_cluster = 0;      // irb_engine_set_mac_split
+    int num_sms = 148;
+    // round-robin IR refresh (Source/PluginProcessor.cpp:455-461): staged taps per IR, positions on the device
+    std::vector<std::unique_ptr<DevBuf>> rr_buf;
+    std::vector<int> h_rr_list;
+    DevBuf rr_ptrs, rr_pos, rr_list;
+    std::unique_ptr<DevBuf> cb_in, cb_out;          // irb_engine_process_callback staging, grown on demand
+    int cb_blocks = 0;
     size_t bytes = 0;
     long long launches = 0;
     // host path: copy streams + events so block b+1 uploads and block b-1 downloads while block b computes
@@ -162,43 +202,89 @@ struct irb_engine {
 
 namespace {
 
+int floor_pow2(long long x) { int r = 1; while (2LL * r <= x) r *= 2; return r; }
+
 int engine_check_binding(irb_engine* e) {
-    if (!e->binding_dirty) return 0;
-    const int rows = tile_rows(e->M);
-    e->per_row_ir = false;
-    for (int c0 = 0; c0 < e->n_chans && !e->per_row_ir; c0 += rows)
-        for (int c = c0 + 1; c < c0 + rows && c < e->n_chans; ++c)
-            if (e->h_ir_of_chan[c] != e->h_ir_of_chan[c0]) { e->per_row_ir = true; break; }
-    CK(cudaMemcpyAsync(e->ir_of_chan.p, e->h_ir_of_chan.data(), sizeof(int) * e->n_chans, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    e->binding_dirty = false;
+    if (e->binding_dirty) {
+        const int rows = tile_rows(e->M);
+        e->per_row_ir = false;
+        for (int c0 = 0; c0 < e->n_chans && !e->per_row_ir; c0 += rows)
+            for (int c = c0 + 1; c < c0 + rows && c < e->n_chans; ++c)
+                if (e->h_ir_of_chan[c] != e->h_ir_of_chan[c0]) { e->per_row_ir = true; break; }
+        CK(cudaMemcpyAsync(e->ir_of_chan.p, e->h_ir_of_chan.data(), sizeof(int) * e->n_chans, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->binding_dirty = false;
+        e->plan_dirty = true;
+    }
+    if (e->plan_dirty) {
+        // Few rows: fill the GPU by splitting each row's partitions.  Target two CTAs per SM; at least 4 partitions
+        // per slot; the reduced tile (1024/split_in float4) must divide among the CTAs of a cluster.
+        const int rows = tile_rows(e->M);
+        const int tiles = (e->n_chans + rows - 1) / rows;
+        int split_in = 1, cl = 1;
+        if (tiles * 2 <= e->num_sms) {
+            int max_np = 1;
+            for (int c = 0; c < e->n_chans; ++c) max_np = std::max(max_np, e->h_nparts[e->h_ir_of_chan[c]]);
+            long long want = floor_pow2(std::max<long long>(1, 2LL * e->num_sms * rows / e->n_chans));
+            want = std::min<long long>(want, floor_pow2(std::max(1, max_np / 4)));
+            split_in = (int) std::min<long long>(want, rows);
+            cl = (int) std::min<long long>(want / split_in, 16);
+        }
+        if (e->force_split_in > 0) { split_in = e->force_split_in; cl = e->force_cluster; }
+        split_in = std::max(1, std::min(floor_pow2(split_in), rows));
+        cl = std::max(1, std::min(floor_pow2(cl), std::min(16, 1024 / split_in)));
+        e->split_in = split_in; e->cluster_dim = cl;
+        e->plan_dirty = false;
+    }
     return 0;
 }
 
-constexpr int kTimingCap = 16384;
-
-int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
-    const bool rec = e->timing && e->t_rec < kTimingCap;
-    if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec], e->stream));
-    irb::FwdArgs f{};
-    f.src = in_dev; f.src2 = nullptr; f.src_chan_stride = e->B; f.L = e->B; f.B = e->B;
-    f.blocks_per_chan = 1; f.n_rows = e->n_chans;
-    f.dst = e->fdl.as<float2>(); f.dst_chan_stride = (long long) e->ring * e->M;
-    f.head = e->head.as<int>(); f.ring = e->ring; f.W = e->W;
-    int rc = launch_fwd(e->M, f, e->stream);
-    if (rc) return rc;
-    if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec + 1], e->stream));
-    irb::MacArgs m{};
+void fill_mac_args(irb_engine* e, irb::MacArgs& m) {
     m.fdl = e->fdl.as<float2>(); m.fdl_chan_stride = (long long) e->ring * e->M;
     m.head = e->head.as<int>(); m.ring = e->ring; m.blocks_per_chan = 1; m.n_rows = e->n_chans;
     m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
     m.ir_of_chan = e->ir_of_chan.as<int>(); m.nparts = e->nparts.as<int>(); m.W = e->W;
-    m.Y = nullptr; m.B = e->B; m.out = out_dev; m.out_chan_stride = e->B; m.Lout = e->B;
-    m.ov = e->ov.as<float>(); m.tail = nullptr;
-    rc = launch_mac(e->M, true, e->per_row_ir, m, e->stream);
+    m.B = e->B; m.split_in = e->split_in;
+}
+bool use_slots(const irb_engine* e) { return e->per_row_ir || e->split_in > 1 || e->cluster_dim > 1; }
+
+constexpr int kTimingCap = 16384;
+
+// forward FFT of one block of every channel into the FDL (advances the heads) and/or the round-robin IR refresh rows
+int engine_launch_fwd(irb_engine* e, const float* in_dev, bool audio, bool refresh) {
+    irb::FwdArgs f{};
+    f.src = in_dev; f.src2 = nullptr; f.src_chan_stride = e->B; f.L = e->B; f.B = e->B;
+    f.blocks_per_chan = 1; f.n_rows = audio ? e->n_chans : 0;
+    f.dst = e->fdl.as<float2>(); f.dst_chan_stride = (long long) e->ring * e->M;
+    f.head = e->head.as<int>(); f.ring = e->ring; f.W = e->W;
+    // one IR partition of every staged IR is re-transformed per block, in the same launch
+    f.n_rr = refresh ? (int) e->h_rr_list.size() : 0; f.rr_list = e->rr_list.as<int>(); f.rr_taps = e->rr_ptrs.as<const float*>();
+    f.rr_pos = e->rr_pos.as<int>(); f.nparts = e->nparts.as<int>(); f.H = e->H.as<float2>(); f.ir_stride = (long long) e->ring * e->M;
+    if (f.n_rows == 0 && f.n_rr == 0) return 0;
+    int rc = launch_fwd(e->M, f, e->stream);
     if (rc) return rc;
+    e->launches += 1;
+    return 0;
+}
+int engine_launch_mac(irb_engine* e, float* out_dev, int head_back) {
+    irb::MacArgs m{};
+    fill_mac_args(e, m);
+    m.Y = nullptr; m.out = out_dev; m.out_chan_stride = e->B; m.Lout = e->B;
+    m.ov = e->ov.as<float>(); m.tail = nullptr; m.head_back = head_back;
+    int rc = launch_mac(e->M, true, use_slots(e), e->cluster_dim, m, e->stream);
+    if (rc) return rc;
+    e->launches += 1;
+    return 0;
+}
+
+int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
+    const bool rec = e->timing && e->t_rec < kTimingCap;
+    if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec], e->stream));
+    int rc = engine_launch_fwd(e, in_dev, true, true);
+    if (rc) return rc;
+    if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec + 1], e->stream));
+    if ((rc = engine_launch_mac(e, out_dev, 0))) return rc;
     if (rec) { CK(cudaEventRecord(e->tev[3 * e->t_rec + 2], e->stream)); e->t_rec++; }
-    e->launches += 2;
     return 0;
 }
 
@@ -246,11 +332,14 @@ int irb_engine_create(irb_engine** out, int device, int block_size, int max_part
         (rc = e->head.alloc(sizeof(int) * n_channels, false)) || (rc = e->ir_of_chan.alloc(sizeof(int) * n_channels, true)) ||
         (rc = e->nparts.alloc(sizeof(int) * n_irs, true)) || (rc = e->io_in[0].alloc(b_io, true)) || (rc = e->io_out[0].alloc(b_io, true)) ||
         (rc = e->io_in[1].alloc(b_io, true)) || (rc = e->io_out[1].alloc(b_io, true)) ||
-        (rc = e->taps.alloc(sizeof(float) * 2 * (size_t) e->B * e->ring, true))) {
+        (rc = e->taps.alloc(sizeof(float) * 2 * (size_t) e->B * e->ring, true)) || (rc = e->rr_ptrs.alloc(sizeof(float*) * n_irs, true)) ||
+        (rc = e->rr_pos.alloc(sizeof(int) * n_irs, true)) || (rc = e->rr_list.alloc(sizeof(int) * n_irs, true))) {
         delete e;
         return rc;
     }
-    e->bytes = b_fdl + b_H + 5 * b_io + sizeof(int) * (2 * (size_t) n_channels + n_irs) + sizeof(float) * 2 * (size_t) e->B * e->ring;
+    e->rr_buf.resize(n_irs);
+    if (cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || e->num_sms < 1) { cudaGetLastError(); e->num_sms = 148; }
+    e->bytes = b_fdl + b_H + 5 * b_io + sizeof(int) * (2 * (size_t) n_channels + 3 * (size_t) n_irs) + sizeof(float*) * n_irs + sizeof(float) * 2 * (size_t) e->B * e->ring;
     e->h_ir_of_chan.assign(n_channels, 0);
     e->h_nparts.assign(n_irs, 0);
     bool ok = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -291,6 +380,10 @@ int irb_engine_reset(irb_engine* e) {
     CK(cudaMemsetAsync(e->ov.p, 0, sizeof(float) * (size_t) e->B * e->n_chans, e->stream));
     std::vector<int> h(e->n_chans, e->ring - 1);     // first block lands in slot 0
     CK(cudaMemcpyAsync(e->head.p, h.data(), sizeof(int) * e->n_chans, cudaMemcpyHostToDevice, e->stream));
+    // staged IRs start over like irFftBufferArray.clearAndResize in prepareToPlay (PluginProcessor.cpp:226): spectra
+    // cleared, write position 0; their partitions come back one per block
+    for (int ir : e->h_rr_list) CK(cudaMemsetAsync(e->H.as<float2>() + (size_t) ir * e->ring * e->M, 0, spec * e->ring, e->stream));
+    CK(cudaMemsetAsync(e->rr_pos.p, 0, sizeof(int) * e->n_irs, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -314,8 +407,67 @@ int irb_engine_set_ir(irb_engine* e, int ir_id, const float* left, const float* 
     int rc = launch_fwd(e->M, f, e->stream);
     if (rc) return rc;
     e->launches += 1;
+    if (e->rr_buf[ir_id]) {            // a staged (round-robin) IR: the refresh must keep producing these taps
+        float* rb = e->rr_buf[ir_id]->as<float>();
+        CK(cudaMemsetAsync(rb, 0, sizeof(float) * (size_t) e->B * e->ring, e->stream));
+        if (right) { irb::k_fold_mono<<<(n_taps + 255) / 256, 256, 0, e->stream>>>(dl, dr, rb, n_taps); g_launches++; CK(cudaGetLastError()); }
+        else CK(cudaMemcpyAsync(rb, dl, sizeof(float) * n_taps, cudaMemcpyDeviceToDevice, e->stream));
+        if (P != e->h_nparts[ir_id]) CK(cudaMemsetAsync(e->rr_pos.as<int>() + ir_id, 0, sizeof(int), e->stream));
+    }
+    if (P != e->h_nparts[ir_id]) e->plan_dirty = true;
     e->h_nparts[ir_id] = P;
     CK(cudaMemcpyAsync(e->nparts.as<int>() + ir_id, &e->h_nparts[ir_id], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// "IRtoConvolve = this buffer" (PluginProcessor.cpp:411-414): nothing is transformed here; every following block step
+// re-transforms ONE partition of the staged taps, round-robin (:455-461), so a new IR replaces the old one partition
+// by partition over nparts blocks.  The first call for an IR fixes its partition count (n_partitions, or
+// ceil(n_taps / block_size) when 0) and starts from cleared spectra, as prepareToPlay does (:225-226).
+int irb_engine_stage_ir(irb_engine* e, int ir_id, const float* left, const float* right, int n_taps, int n_partitions) {
+    if (!e || !left) return fail(IRB_ERR_ARG, "engine or taps null");
+    if (ir_id < 0 || ir_id >= e->n_irs) return fail(IRB_ERR_ARG, "ir_id %d outside [0, %d)", ir_id, e->n_irs);
+    if (n_taps < 1) return fail(IRB_ERR_ARG, "n_taps %d < 1", n_taps);
+    int P = n_partitions > 0 ? n_partitions : (e->h_nparts[ir_id] > 0 ? e->h_nparts[ir_id] : (int) std::ceil((float) n_taps / (float) e->B));
+    if (P > e->ring) return fail(IRB_ERR_ARG, "%d partitions exceed max_partitions %d", P, e->ring);
+    CK(cudaSetDevice(e->device));
+    const size_t cap = (size_t) e->B * e->ring;
+    const bool first = !e->rr_buf[ir_id];
+    if (first) {
+        std::unique_ptr<DevBuf> b(new (std::nothrow) DevBuf);
+        if (!b) return fail(IRB_ERR_ARG, "out of host memory");
+        int rc = b->alloc(sizeof(float) * cap, false);
+        if (rc) return rc;
+        e->rr_buf[ir_id] = std::move(b);
+        e->bytes += sizeof(float) * cap;
+        const float* ptr = e->rr_buf[ir_id]->as<float>();
+        CK(cudaMemcpyAsync(e->rr_ptrs.as<const float*>() + ir_id, &ptr, sizeof(ptr), cudaMemcpyHostToDevice, e->stream));
+        e->h_rr_list.push_back(ir_id);
+        CK(cudaMemcpyAsync(e->rr_list.p, e->h_rr_list.data(), sizeof(int) * e->h_rr_list.size(), cudaMemcpyHostToDevice, e->stream));
+    }
+    const int keep = (int) std::min<size_t>((size_t) n_taps, (size_t) P * e->B);      // taps beyond the partitions are never read
+    float* rb = e->rr_buf[ir_id]->as<float>();
+    CK(cudaMemsetAsync(rb, 0, sizeof(float) * cap, e->stream));
+    if (right) {
+        float* dl = e->taps.as<float>();
+        float* dr = dl + cap;
+        CK(cudaMemcpyAsync(dl, left, sizeof(float) * keep, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(dr, right, sizeof(float) * keep, cudaMemcpyHostToDevice, e->stream));
+        irb::k_fold_mono<<<(keep + 255) / 256, 256, 0, e->stream>>>(dl, dr, rb, keep);
+        g_launches++;
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemcpyAsync(rb, left, sizeof(float) * keep, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (P != e->h_nparts[ir_id]) {
+        if (e->h_nparts[ir_id] == 0 || first)      // never loaded (or loaded whole before): start from cleared spectra only when nothing was loaded
+            if (e->h_nparts[ir_id] == 0) CK(cudaMemsetAsync(e->H.as<float2>() + (size_t) ir_id * e->ring * e->M, 0, sizeof(float2) * (size_t) e->M * e->ring, e->stream));
+        CK(cudaMemsetAsync(e->rr_pos.as<int>() + ir_id, 0, sizeof(int), e->stream));
+        e->h_nparts[ir_id] = P;
+        CK(cudaMemcpyAsync(e->nparts.as<int>() + ir_id, &e->h_nparts[ir_id], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        e->plan_dirty = true;
+    }
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -329,6 +481,23 @@ int irb_engine_bind(irb_engine* e, int chan_begin, int chan_end, int ir_id) {
     return 0;
 }
 int irb_engine_tile_channels(const irb_engine* e) { return e ? tile_rows(e->M) : fail(IRB_ERR_ARG, "engine is null"); }
+int irb_engine_set_mac_split(irb_engine* e, int split_in, int cluster) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    if (split_in < 0 || cluster < 0 || (split_in == 0) != (cluster == 0)) return fail(IRB_ERR_ARG, "split_in and cluster must both be 0 (automatic) or both >= 1");
+    e->force_split_in = split_in; e->force_cluster = cluster;
+    e->plan_dirty = true;
+    return 0;
+}
+int irb_engine_mac_plan(irb_engine* e, int* slots_kernel, int* split_in, int* cluster) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    CK(cudaSetDevice(e->device));
+    int rc = engine_check_binding(e);
+    if (rc) return rc;
+    if (slots_kernel) *slots_kernel = use_slots(e) ? 1 : 0;
+    if (split_in) *split_in = e->split_in;
+    if (cluster) *cluster = e->cluster_dim;
+    return 0;
+}
 
 int irb_engine_process_device(irb_engine* e, const float* in_dev, float* out_dev, int n_blocks) {
     if (!e || !in_dev || !out_dev) return fail(IRB_ERR_ARG, "null argument");
@@ -364,6 +533,42 @@ int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int
         CK(cudaEventRecord(e->ev_out[q], e->s_out));
     }
     CK(cudaStreamSynchronize(e->s_out));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// The order of one plug-in callback (PluginProcessor.cpp:421-518): EVERY block completed by the callback is transformed
+// into the FDL first (:421-445), then the blocks are convolved one after the other (:452-518), each preceded by one
+// round-robin IR refresh (:455-461).  With n_blocks > 1 (host block > processBlockSize) the oldest partitions of the
+// earlier blocks therefore meet slots already overwritten by the later blocks of the same callback whenever
+// max_partitions < partitions + n_blocks - 1 -- the reference's behaviour, kept (create the engine with a larger ring
+// to avoid it).  in/out: HOST [n_blocks][n_channels][block_size].
+int irb_engine_process_callback(irb_engine* e, const float* in_host, float* out_host, int n_blocks) {
+    if (!e || !in_host || !out_host) return fail(IRB_ERR_ARG, "null argument");
+    if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
+    if (n_blocks > e->ring) return fail(IRB_ERR_ARG, "%d blocks in one callback exceed the FDL ring of %d slots", n_blocks, e->ring);
+    if (n_blocks == 0) return 0;
+    CK(cudaSetDevice(e->device));
+    int rc = engine_check_binding(e);
+    if (rc) return rc;
+    const size_t blk = (size_t) e->B * e->n_chans;
+    if (e->cb_blocks < n_blocks) {
+        e->cb_in.reset(new (std::nothrow) DevBuf); e->cb_out.reset(new (std::nothrow) DevBuf);
+        if (!e->cb_in || !e->cb_out) return fail(IRB_ERR_ARG, "out of host memory");
+        e->cb_blocks = 0;
+        if ((rc = e->cb_in->alloc(sizeof(float) * blk * n_blocks, false)) || (rc = e->cb_out->alloc(sizeof(float) * blk * n_blocks, false))) return rc;
+        e->cb_blocks = n_blocks;
+    }
+    float* din = e->cb_in->as<float>();
+    float* dout = e->cb_out->as<float>();
+    CK(cudaMemcpyAsync(din, in_host, sizeof(float) * blk * n_blocks, cudaMemcpyHostToDevice, e->stream));
+    for (int b = 0; b < n_blocks; ++b)
+        if ((rc = engine_launch_fwd(e, din + b * blk, true, false))) return rc;
+    for (int b = 0; b < n_blocks; ++b) {
+        if ((rc = engine_launch_fwd(e, nullptr, false, true))) return rc;
+        if ((rc = engine_launch_mac(e, dout + b * blk, n_blocks - 1 - b))) return rc;
+    }
+    CK(cudaMemcpyAsync(out_host, dout, sizeof(float) * blk * n_blocks, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -432,12 +637,9 @@ int irb_engine_mac_only_device(irb_engine* e, float* acc_dev) {
     int rc = engine_check_binding(e);
     if (rc) return rc;
     irb::MacArgs m{};
-    m.fdl = e->fdl.as<float2>(); m.fdl_chan_stride = (long long) e->ring * e->M;
-    m.head = e->head.as<int>(); m.ring = e->ring; m.blocks_per_chan = 1; m.n_rows = e->n_chans;
-    m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
-    m.ir_of_chan = e->ir_of_chan.as<int>(); m.nparts = e->nparts.as<int>(); m.W = e->W;
-    m.Y = (float2*) acc_dev; m.B = e->B;
-    rc = launch_mac(e->M, false, e->per_row_ir, m, e->stream);
+    fill_mac_args(e, m);
+    m.Y = (float2*) acc_dev;
+    rc = launch_mac(e->M, false, use_slots(e), e->cluster_dim, m, e->stream);
     if (rc) return rc;
     e->launches += 1;
     return 0;
@@ -527,7 +729,8 @@ int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, i
     m.fdl = dX.as<float2>(); m.fdl_chan_stride = (long long) bpc * M; m.head = nullptr; m.ring = bpc; m.blocks_per_chan = bpc;
     m.n_rows = bpc * ch_x; m.H = dH.as<float2>(); m.ir_stride = (long long) P * M; m.ir_of_chan = dir.as<int>(); m.nparts = dnp.as<int>();
     m.W = W; m.B = B; m.out = dout.as<float>(); m.out_chan_stride = Lout; m.Lout = (int) Lw; m.ov = nullptr; m.tail = dtail.as<float>();
-    if ((rc = launch_mac(M, true, false, m, st))) return rc;
+    m.split_in = 1;
+    if ((rc = launch_mac(M, true, false, 1, m, st))) return rc;
     {
         const long long n = (long long) bpc * B * ch_x;
         irb::k_ola_tail<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(dout.as<float>(), Lout, (int) Lw, dtail.as<float>(), B, bpc, ch_x);

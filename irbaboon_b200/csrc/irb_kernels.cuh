@@ -104,35 +104,70 @@ struct FwdArgs {
     int* head;                 // per-chan ring head (nullable)
     int ring;                  // ring slots per chan
     const float2* W;           // N = 2M roots of unity
+    // Round-robin IR refresh rows (Source/PluginProcessor.cpp:455-461): after the ceil(n_rows/ROWS) tiles of audio rows
+    // come ceil(n_rr/ROWS) tiles whose row i re-transforms partition rr_pos[ir] of the staged taps of ir = rr_list[i]
+    // into H[ir] and then advances rr_pos[ir] (mod nparts[ir]).  rr_taps[ir] holds nparts[ir]*B zero-extended samples.
+    int n_rr;
+    const int* rr_list;
+    const float* const* rr_taps;
+    int* rr_pos;
+    const int* nparts;
+    float2* H;
+    long long ir_stride;       // float2 units
 };
+
+struct FwdRow {                // what one row of k_fwd reads and writes
+    const float* p; const float* q; int len; float2* d; bool live;
+};
+template <int ROWS, int M>
+__device__ __forceinline__ FwdRow fwd_row(const FwdArgs& a, int main_tiles, int tile, int r) {
+    FwdRow w{nullptr, nullptr, 0, nullptr, false};
+    if (tile < main_tiles) {
+        const int row = tile * ROWS + r;
+        if (row >= a.n_rows) return w;
+        const int chan = row / a.blocks_per_chan, blk = row % a.blocks_per_chan;
+        int len = a.L - blk * a.B;
+        w.len = len < 0 ? 0 : (len > a.B ? a.B : len);
+        const long long off = chan * a.src_chan_stride + (long long) blk * a.B;
+        w.p = a.src + off;
+        w.q = a.src2 ? a.src2 + off : nullptr;
+        int slot = blk;
+        if (a.head) { slot = a.head[chan] + 1; if (slot >= a.ring) slot = 0; }
+        w.d = a.dst + chan * a.dst_chan_stride + (long long) slot * M;
+    } else {
+        const int i = (tile - main_tiles) * ROWS + r;
+        if (i >= a.n_rr) return w;
+        const int ir = a.rr_list[i], p = a.rr_pos[ir];
+        w.len = a.B;
+        w.p = a.rr_taps[ir] + (long long) p * a.B;
+        w.d = a.H + ir * a.ir_stride + (long long) p * M;
+    }
+    w.live = true;
+    return w;
+}
 
 template <int M>
 __global__ void __launch_bounds__(kThreads) k_fwd(const FwdArgs a) {
     using T = Tile<M>;
     __shared__ __align__(16) float2 s_spec[kTile];
     const int tid = threadIdx.x;
+    const int main_tiles = (a.n_rows + T::ROWS - 1) / T::ROWS;
     {   // FFT layout
         const int rf = tid / T::TPF, t = tid % T::TPF;
-        const int row = blockIdx.x * T::ROWS + rf;
+        const FwdRow w = fwd_row<T::ROWS, M>(a, main_tiles, blockIdx.x, rf);
         float2 v[kPts];
 #pragma unroll
         for (int j = 0; j < kPts; ++j) v[j] = make_float2(0.f, 0.f);
-        if (row < a.n_rows) {
-            const int chan = row / a.blocks_per_chan, blk = row % a.blocks_per_chan;
-            int len = a.L - blk * a.B;
-            len = len < 0 ? 0 : (len > a.B ? a.B : len);
-            const long long off = chan * a.src_chan_stride + (long long) blk * a.B;
-            const float* p = a.src + off;
-            const float* q = a.src2 ? a.src2 + off : nullptr;
+        if (w.live) {
 #pragma unroll
             for (int j = 0; j < kPts; ++j) {
                 const int m = 2 * (t + j * T::TPF);
                 float x0 = 0.f, x1 = 0.f;
-                if (m < len) x0 = p[m];
-                if (m + 1 < len) x1 = p[m + 1];
-                if (q) {
-                    if (m < len) { x0 += q[m]; x0 /= 2.0f; }
-                    if (m + 1 < len) { x1 += q[m + 1]; x1 /= 2.0f; }
+                if (m < w.len) x0 = w.p[m];
+                if (m + 1 < w.len) x1 = w.p[m + 1];
+                if (w.q) {
+                    if (m < w.len) { x0 += w.q[m]; x0 /= 2.0f; }
+                    if (m + 1 < w.len) { x1 += w.q[m + 1]; x1 /= 2.0f; }
                 }
                 v[j] = make_float2(x0, x1);
             }
@@ -149,27 +184,32 @@ __global__ void __launch_bounds__(kThreads) k_fwd(const FwdArgs a) {
 #pragma unroll
         for (int s = 0; s < T::K; ++s) {
             const int rl = s * T::G + g;
-            const int row = blockIdx.x * T::ROWS + rl;
-            if (row >= a.n_rows) continue;
-            const int chan = row / a.blocks_per_chan, blk = row % a.blocks_per_chan;
-            int slot = blk;
-            if (a.head) { slot = a.head[chan] + 1; if (slot >= a.ring) slot = 0; }
+            const FwdRow w = fwd_row<T::ROWS, M>(a, main_tiles, blockIdx.x, rl);
+            if (!w.live) continue;
             const float2* z = s_spec + rl * M;
-            float2* d = a.dst + chan * a.dst_chan_stride + (long long) slot * M;
 #pragma unroll
             for (int vv = 0; vv < T::V; ++vv) {
                 const int k = 2 * (c0 + vv * T::TPR);
                 const float2 x0 = real_split(z[k], z[(M - k) & (M - 1)], root<false>(a.W, k), k);
                 const float2 x1 = real_split(z[k + 1], z[M - k - 1], root<false>(a.W, k + 1), k + 1);
-                *reinterpret_cast<float4*>(d + k) = make_float4(x0.x, x0.y, x1.x, x1.y);
+                *reinterpret_cast<float4*>(w.d + k) = make_float4(x0.x, x0.y, x1.x, x1.y);
             }
         }
     }
-    if (a.head) {   // advance the ring heads once every read of the old value is done
+    // advance the ring heads / round-robin positions once every read of the old value is done
+    if ((int) blockIdx.x < main_tiles) {
+        if (a.head) {
+            bar_compute();
+            if (tid < T::ROWS) {
+                const int row = blockIdx.x * T::ROWS + tid;
+                if (row < a.n_rows) { int h = a.head[row] + 1; a.head[row] = h >= a.ring ? 0 : h; }
+            }
+        }
+    } else {
         bar_compute();
         if (tid < T::ROWS) {
-            const int row = blockIdx.x * T::ROWS + tid;
-            if (row < a.n_rows) { int h = a.head[row] + 1; a.head[row] = h >= a.ring ? 0 : h; }
+            const int i = (blockIdx.x - main_tiles) * T::ROWS + tid;
+            if (i < a.n_rr) { const int ir = a.rr_list[i]; int p = a.rr_pos[ir] + 1; a.rr_pos[ir] = p >= a.nparts[ir] ? 0 : p; }
         }
     }
 }
@@ -198,23 +238,73 @@ struct MacArgs {
     int Lout;
     float* ov;                 // streaming: overlap state [chan][B] (read, then replaced); offline: nullptr
     float* tail;               // offline: second halves [row][B]
+    int split_in;              // k_mac_slots: tile slots that share one row (power of two, >= 1)
+    int head_back;             // streaming: the newest spectrum of this step sits head_back slots behind head (callback order)
 };
 
-// PRI = per-row IR: every row of the tile stages its OWN partition spectrum (per-stream IRs, BASELINE config 4);
-// otherwise the whole tile shares one IR and a ring stage holds U consecutive partitions of it.
-template <int M, int U, bool PRI>
+// Time-domain epilogue of a tile whose accumulated packed spectra sit in shared memory, row r at tile + r*M
+// (r < rows_in_tile): packed merge -> inverse M-point FFT -> x 1/N -> overlap-add -> output block
+// (fp/convolution.cpp:206-230).  Called by all kThreads compute threads.
+template <int M>
+__device__ __forceinline__ void inv_epilogue(const MacArgs& a, float2* tile, int tid, int row0, int rows_in_tile) {
+    using T = Tile<M>;
+    const int rf = tid / T::TPF, t = tid % T::TPF;
+    float2* srow = tile + rf * M;
+    float2 v[kPts];
+#pragma unroll
+    for (int j = 0; j < kPts; ++j) {
+        const int k = t + j * T::TPF;
+        v[j] = real_merge(srow[k], srow[(M - k) & (M - 1)], root<false>(a.W, k), k);
+    }
+    fft_run<M, true>(v, t, srow, a.W);
+    const float scale = 1.0f / (float) (2 * M);      // the 1/N of performRealOnlyInverseTransform
+    const int row = row0 + rf;
+    const bool live = rf < rows_in_tile && row < a.n_rows;
+    const int chan = live ? row / a.blocks_per_chan : 0, blk = live ? row % a.blocks_per_chan : 0;
+    int olen = a.Lout - blk * a.B;
+    olen = olen < 0 ? 0 : (olen > a.B ? a.B : olen);
+    float* outp = a.out + chan * a.out_chan_stride + (long long) blk * a.B;
+    float* ovp = a.ov ? a.ov + (long long) chan * a.B : nullptr;
+    float* tailp = a.tail ? a.tail + (long long) row * a.B : nullptr;
+    // fp/convolution.cpp:210-213: y[i] += overlap[i]; overlap[i] = y[B + i]
+#pragma unroll
+    for (int j = 0; j < kPts; ++j) {
+        v[j].x *= scale; v[j].y *= scale;
+        const int m = 2 * (t + j * T::TPF);
+        if (live && ovp) {
+            if (m < a.B) v[j].x += ovp[m];
+            if (m + 1 < a.B) v[j].y += ovp[m + 1];
+        }
+    }
+    if (a.ov) bar_compute();                           // all overlap reads precede the overlap writes
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < kPts; ++j) {
+            const int m = 2 * (t + j * T::TPF);
+            const float val[2] = {v[j].x, v[j].y};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int mm = m + e;
+                if (mm < a.B) { if (mm < olen) outp[mm] = val[e]; }
+                else if (mm < 2 * a.B) { if (ovp) ovp[mm - a.B] = val[e]; else tailp[mm - a.B] = val[e]; }
+            }
+        }
+    }
+}
+
+// Shared-IR kernel: the whole tile is bound to one IR and a ring stage holds U consecutive partitions of it.
+template <int M, int U>
 struct MacSmem {
     float2 spec[kTile];                                  // tile in both layouts (inverse path)
-    float2 h[kStages][PRI ? kTile / M : U][M];           // IR ring
+    float2 h[kStages][U][M];                             // IR ring
     uint64_t full[kStages], empty[kStages];
 };
 
-template <int M, int U, bool INV, bool PRI>
-__global__ void __launch_bounds__(kThreads + 32, (U == 1 && !PRI) ? 3 : 2) k_mac(const MacArgs a) {
-    static_assert(!PRI || U == 1, "per-row IR stages one partition per row");
+template <int M, int U, bool INV>
+__global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const MacArgs a) {
     using T = Tile<M>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    MacSmem<M, U, PRI>& sm = *reinterpret_cast<MacSmem<M, U, PRI>*>(smem_raw);
+    MacSmem<M, U>& sm = *reinterpret_cast<MacSmem<M, U>*>(smem_raw);
     const int tid = threadIdx.x;
     const int row0 = blockIdx.x * T::ROWS;
 
@@ -224,14 +314,6 @@ __global__ void __launch_bounds__(kThreads + 32, (U == 1 && !PRI) ? 3 : 2) k_mac
     const int np = a.nparts[ir];
     // number of partitions any row of this tile needs
     int pmax = np;
-    if (PRI) {
-        pmax = 0;
-        for (int r = 0; r < T::ROWS && row0 + r < a.n_rows; ++r) {
-            const int chan = (row0 + r) / a.blocks_per_chan;
-            const int n = a.nparts[a.ir_of_chan ? a.ir_of_chan[chan] : 0];
-            pmax = n > pmax ? n : pmax;
-        }
-    }
     if (!a.head) {          // offline: row = chan*blocks_per_chan + blk, blocks_per_chan % ROWS == 0 (host pads)
         int last = row0 + T::ROWS - 1;
         if (last >= a.n_rows) last = a.n_rows - 1;
@@ -248,29 +330,7 @@ __global__ void __launch_bounds__(kThreads + 32, (U == 1 && !PRI) ? 3 : 2) k_mac
 
     if (tid >= kThreads) {
         // ===== TMA producer warp: stream the IR partition spectra through the ring =====
-        if (PRI) {
-            // one bulk copy per (row, partition); lanes split the rows of the tile
-            const int lane = tid - kThreads;
-            for (int g = 0; g < ngroups; ++g) {
-                const int st = g % kStages;
-                if (g >= kStages) mbar_wait(&sm.empty[st], ((g / kStages) - 1) & 1);
-                uint32_t mine = 0;
-                for (int r = lane; r < T::ROWS && row0 + r < a.n_rows; r += 32) {
-                    const int chan = (row0 + r) / a.blocks_per_chan;
-                    if (g < a.nparts[a.ir_of_chan ? a.ir_of_chan[chan] : 0]) mine += M * sizeof(float2);
-                }
-                uint32_t total = mine;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-                if (lane == 0) mbar_expect_tx(&sm.full[st], total);
-                __syncwarp();
-                for (int r = lane; r < T::ROWS && row0 + r < a.n_rows; r += 32) {
-                    const int chan = (row0 + r) / a.blocks_per_chan;
-                    const int irr = a.ir_of_chan ? a.ir_of_chan[chan] : 0;
-                    if (g < a.nparts[irr]) tma_bulk_g2s(&sm.h[st][r][0], a.H + irr * a.ir_stride + (long long) g * M, M * sizeof(float2), &sm.full[st]);
-                }
-            }
-        } else if (tid == kThreads) {
+        if (tid == kThreads) {
             const float2* hsrc = a.H + ir * a.ir_stride;
             for (int g = 0; g < ngroups; ++g) {
                 const int st = g % kStages;
@@ -295,9 +355,9 @@ __global__ void __launch_bounds__(kThreads + 32, (U == 1 && !PRI) ? 3 : 2) k_mac
         nvalid[s] = 0; slot[s] = 0; xptr[s] = nullptr;
         if (row < a.n_rows) {
             const int chan = row / a.blocks_per_chan, blk = row % a.blocks_per_chan;
-            const int hd = a.head ? a.head[chan] : blk;
-            const int npr = PRI ? a.nparts[a.ir_of_chan ? a.ir_of_chan[chan] : 0] : np;
-            nvalid[s] = a.head ? npr : (blk + 1 < npr ? blk + 1 : npr);
+            int hd = blk;
+            if (a.head) { hd = a.head[chan] - a.head_back; if (hd < 0) hd += a.ring; }
+            nvalid[s] = a.head ? np : (blk + 1 < np ? blk + 1 : np);
             slot[s] = hd;
             xptr[s] = reinterpret_cast<const float4*>(a.fdl + chan * a.fdl_chan_stride + (long long) hd * M) + c0;
         }
@@ -336,20 +396,11 @@ __global__ void __launch_bounds__(kThreads + 32, (U == 1 && !PRI) ? 3 : 2) k_mac
 #pragma unroll
                 for (int vv = 0; vv < T::V; ++vv) {
                     const int c = c0 + vv * T::TPR;
-                    float4 h;
-                    float h0i, h0q;
-                    if (!PRI) {
-                        h = *reinterpret_cast<const float4*>(&sm.h[st][u][2 * c]);
-                        // bin 0 is the packed {DC, Nyquist} pair: two real products instead of a complex one
-                        h0i = c == 0 ? 0.f : h.y; h0q = c == 0 ? h.y : h.x;
-                    }
+                    const float4 h = *reinterpret_cast<const float4*>(&sm.h[st][u][2 * c]);
+                    // bin 0 is the packed {DC, Nyquist} pair: two real products instead of a complex one
+                    const float h0i = c == 0 ? 0.f : h.y, h0q = c == 0 ? h.y : h.x;
 #pragma unroll
                     for (int s = 0; s < T::K; ++s) {
-                        if (PRI) {
-                            if (g >= nvalid[s]) continue;      // this row's IR is shorter: its stage slot was not filled
-                            h = *reinterpret_cast<const float4*>(&sm.h[st][s * T::G + g_][2 * c]);
-                            h0i = c == 0 ? 0.f : h.y; h0q = c == 0 ? h.y : h.x;
-                        }
                         const float4 xv = x[u][s][vv];
                         float4& ac = acc[s][vv];
                         ac.x = fmaf(xv.x, h.x, fmaf(-xv.y, h0i, ac.x));
@@ -391,49 +442,235 @@ __global__ void __launch_bounds__(kThreads + 32, (U == 1 && !PRI) ? 3 : 2) k_mac
             for (int vv = 0; vv < T::V; ++vv)
                 reinterpret_cast<float4*>(sm.spec + (s * T::G + g_) * M)[c0 + vv * T::TPR] = acc[s][vv];
         bar_compute();
-        const int rf = tid / T::TPF, t = tid % T::TPF;
-        float2* srow = sm.spec + rf * M;
-        float2 v[kPts];
-#pragma unroll
-        for (int j = 0; j < kPts; ++j) {
-            const int k = t + j * T::TPF;
-            v[j] = real_merge(srow[k], srow[(M - k) & (M - 1)], root<false>(a.W, k), k);
+        inv_epilogue<M>(a, sm.spec, tid, row0, T::ROWS);
+    }
+}
+
+// ===================================================================================================
+// k_mac_slots: the MAC for (a) rows that do NOT share an IR inside a tile (per-stream IRs, BASELINE config 4) and
+// (b) FEW rows (the single-stream latency path, BASELINE config 2), where one CTA per tile would leave the GPU idle
+// and the load chain of a single row is latency-bound.
+//
+// A tile has ROWS = 2048/M SLOTS.  Slot r works for row  row0 + r / split_in  on the partition range number
+// q = cluster_rank * split_in + r % split_in  of nsplit = cluster_size * split_in equal ranges of that row's IR, and
+// stages its OWN IR partition per ring step (one bulk TMA copy per slot).  With nsplit == 1 a slot is a row.
+// Otherwise the partial sums of a row are added in ascending q (i.e. ascending partition order between ranges)
+// through distributed shared memory: every CTA of the cluster reduces 1/cluster_size of the tile and writes it
+// into rank 0, which runs the inverse-FFT epilogue.  Streaming only (head != nullptr).
+template <int M>
+struct SlotSmem {
+    float2 spec[kTile];                                  // partial sums, slot-major
+    float2 h[kStages][kTile / M][M];                     // IR ring: one partition per slot and stage; reused as the reduced tile
+    uint64_t full[kStages], empty[kStages];
+    int pbeg[kTile / M], pcnt[kTile / M], ngroups;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int M, bool INV>
+__global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a) {
+    using T = Tile<M>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SlotSmem<M>& sm = *reinterpret_cast<SlotSmem<M>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int CL = (int) cluster_size(), crank = (int) cluster_rank();
+    const int split_in = a.split_in, nsplit = split_in * CL;
+    const int rpt = T::ROWS / split_in;                   // rows per tile
+    const int row0 = (blockIdx.x / CL) * rpt;
+
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], kThreads / 32); }
+        mbar_fence_init();
+        sm.ngroups = 0;
+    }
+    __syncthreads();
+    // partition range of every slot: row r's nv partitions are cut into nsplit ranges of ceil(nv / nsplit)
+    if (tid < T::ROWS) {
+        const int row = row0 + tid / split_in;
+        int pb = 0, pc = 0;
+        if (row < a.n_rows) {
+            const int chan = row / a.blocks_per_chan;
+            const int nv = a.nparts[a.ir_of_chan ? a.ir_of_chan[chan] : 0];
+            const int per = (nv + nsplit - 1) / nsplit;
+            pb = (crank * split_in + tid % split_in) * per;
+            pc = nv - pb;
+            pc = pc < 0 ? 0 : (pc > per ? per : pc);
         }
-        fft_run<M, true>(v, t, srow, a.W);
-        const float scale = 1.0f / (float) (2 * M);      // the 1/N of performRealOnlyInverseTransform
-        const int row = row0 + rf;
-        const bool live = row < a.n_rows;
-        const int chan = live ? row / a.blocks_per_chan : 0, blk = live ? row % a.blocks_per_chan : 0;
-        int olen = a.Lout - blk * a.B;
-        olen = olen < 0 ? 0 : (olen > a.B ? a.B : olen);
-        float* outp = a.out + chan * a.out_chan_stride + (long long) blk * a.B;
-        float* ovp = a.ov ? a.ov + (long long) chan * a.B : nullptr;
-        float* tailp = a.tail ? a.tail + (long long) row * a.B : nullptr;
-        // fp/convolution.cpp:210-213: y[i] += overlap[i]; overlap[i] = y[B + i]
+        sm.pbeg[tid] = pb; sm.pcnt[tid] = pc;
+        if (pc > 0) atomicMax(&sm.ngroups, pc);
+    }
+    __syncthreads();
+    const int ngroups = sm.ngroups;
+
+    if (tid >= kThreads) {
+        // ===== TMA producer warp: one bulk copy per (slot, step); lanes split the slots of the tile =====
+        const int lane = tid - kThreads;
+        for (int g = 0; g < ngroups; ++g) {
+            const int st = g % kStages;
+            if (g >= kStages) mbar_wait(&sm.empty[st], ((g / kStages) - 1) & 1);
+            uint32_t total = 0;
+            for (int r = lane; r < T::ROWS; r += 32) if (g < sm.pcnt[r]) total += M * sizeof(float2);
 #pragma unroll
-        for (int j = 0; j < kPts; ++j) {
-            v[j].x *= scale; v[j].y *= scale;
-            const int m = 2 * (t + j * T::TPF);
-            if (live && ovp) {
-                if (m < a.B) v[j].x += ovp[m];
-                if (m + 1 < a.B) v[j].y += ovp[m + 1];
-            }
-        }
-        if (a.ov) bar_compute();                           // all overlap reads precede the overlap writes
-        if (live) {
-#pragma unroll
-            for (int j = 0; j < kPts; ++j) {
-                const int m = 2 * (t + j * T::TPF);
-                const float val[2] = {v[j].x, v[j].y};
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int mm = m + e;
-                    if (mm < a.B) { if (mm < olen) outp[mm] = val[e]; }
-                    else if (mm < 2 * a.B) { if (ovp) ovp[mm - a.B] = val[e]; else tailp[mm - a.B] = val[e]; }
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            if (lane == 0) mbar_expect_tx(&sm.full[st], total);
+            __syncwarp();
+            for (int r = lane; r < T::ROWS; r += 32) {
+                if (g < sm.pcnt[r]) {
+                    const int chan = (row0 + r / split_in) / a.blocks_per_chan;
+                    const int irr = a.ir_of_chan ? a.ir_of_chan[chan] : 0;
+                    tma_bulk_g2s(&sm.h[st][r][0], a.H + irr * a.ir_stride + (long long) (sm.pbeg[r] + g) * M, M * sizeof(float2), &sm.full[st]);
                 }
             }
         }
+    } else {
+        // ===== compute threads, MAC layout: thread owns V float4 of the K slots s*G + g_ =====
+        const int g_ = tid / T::TPR, c0 = tid % T::TPR;
+        const float4* xptr[T::K];
+        int slot[T::K], nvalid[T::K];
+#pragma unroll
+        for (int s = 0; s < T::K; ++s) {
+            const int sl = s * T::G + g_;
+            const int row = row0 + sl / split_in;
+            nvalid[s] = sm.pcnt[sl]; slot[s] = 0; xptr[s] = nullptr;
+            if (nvalid[s] > 0) {
+                const int chan = row / a.blocks_per_chan;
+                int hd = a.head[chan] - a.head_back - sm.pbeg[sl];      // partition p meets slot (head - p) mod ring
+                while (hd < 0) hd += a.ring;
+                slot[s] = hd;
+                xptr[s] = reinterpret_cast<const float4*>(a.fdl + chan * a.fdl_chan_stride + (long long) hd * M) + c0;
+            }
+        }
+        float4 acc[T::K][T::V];
+#pragma unroll
+        for (int s = 0; s < T::K; ++s)
+#pragma unroll
+            for (int vv = 0; vv < T::V; ++vv) acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        float4 xa[T::K][T::V], xb[T::K][T::V];
+        auto load_group = [&](float4 (&x)[T::K][T::V], int g) {
+#pragma unroll
+            for (int s = 0; s < T::K; ++s) {
+                const bool ok = g < nvalid[s];
+#pragma unroll
+                for (int vv = 0; vv < T::V; ++vv) x[s][vv] = ok ? ldg_stream(xptr[s] + vv * T::TPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) {
+                    if (slot[s] == 0) { slot[s] = a.ring - 1; xptr[s] += (long long) (a.ring - 1) * (M / 2); }
+                    else { --slot[s]; xptr[s] -= M / 2; }
+                }
+            }
+        };
+        auto consume_group = [&](float4 (&x)[T::K][T::V], int g) {
+            const int st = g % kStages;
+            mbar_wait(&sm.full[st], (g / kStages) & 1);
+#pragma unroll
+            for (int vv = 0; vv < T::V; ++vv) {
+                const int c = c0 + vv * T::TPR;
+#pragma unroll
+                for (int s = 0; s < T::K; ++s) {
+                    if (g >= nvalid[s]) continue;          // this slot's range is shorter: its stage entry was not filled
+                    const float4 h = *reinterpret_cast<const float4*>(&sm.h[st][s * T::G + g_][2 * c]);
+                    const float h0i = c == 0 ? 0.f : h.y, h0q = c == 0 ? h.y : h.x;    // bin 0 = packed {DC, Nyquist}
+                    const float4 xv = x[s][vv];
+                    float4& ac = acc[s][vv];
+                    ac.x = fmaf(xv.x, h.x, fmaf(-xv.y, h0i, ac.x));
+                    ac.y = fmaf(xv.y, h0q, fmaf(xv.x, h0i, ac.y));
+                    ac.z = fmaf(xv.z, h.z, fmaf(-xv.w, h.w, ac.z));
+                    ac.w = fmaf(xv.w, h.z, fmaf(xv.z, h.w, ac.w));
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&sm.empty[st]);
+        };
+        if (ngroups > 0) load_group(xa, 0);
+        for (int g = 0; g < ngroups; g += 2) {
+            if (g + 1 < ngroups) load_group(xb, g + 1);
+            consume_group(xa, g);
+            if (g + 1 < ngroups) {
+                if (g + 2 < ngroups) load_group(xa, g + 2);
+                consume_group(xb, g + 1);
+            }
+        }
+        if (!INV && nsplit == 1) {
+#pragma unroll
+            for (int s = 0; s < T::K; ++s) {
+                const int row = row0 + s * T::G + g_;
+                if (row >= a.n_rows) continue;
+#pragma unroll
+                for (int vv = 0; vv < T::V; ++vv) reinterpret_cast<float4*>(a.Y + (long long) row * M)[c0 + vv * T::TPR] = acc[s][vv];
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < T::K; ++s)
+#pragma unroll
+                for (int vv = 0; vv < T::V; ++vv)
+                    reinterpret_cast<float4*>(sm.spec + (s * T::G + g_) * M)[c0 + vv * T::TPR] = acc[s][vv];
+        }
     }
+    if (!INV && nsplit == 1) return;
+
+    float2* fin = sm.spec;                                // tile the epilogue reads: rows at fin + r*M
+    if (nsplit > 1) {
+        // ---- sum the nsplit partial spectra of every row, ascending q, into rank 0's `red` tile ----
+        float2* red = &sm.h[0][0][0];
+        cluster_sync_all();                               // every CTA's partial sums are in its sm.spec (and its IR ring is idle)
+        if (tid < kThreads) {
+            const int n4 = rpt * (M / 2);                 // float4 of the reduced tile; n4 % CL == 0 (host guarantees)
+            const int per = n4 / CL;
+            const uint32_t red0 = dsmem_addr(red, 0);
+            for (int o = crank * per + tid; o < (crank + 1) * per; o += kThreads) {
+                const int fr = o / (M / 2), c = o % (M / 2);
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int rk = 0; rk < CL; ++rk) {
+                    const uint32_t base = dsmem_addr(sm.spec, (uint32_t) rk);
+                    for (int sub = 0; sub < split_in; ++sub) {
+                        const float4 v = dsmem_ld4(base + (uint32_t) (((fr * split_in + sub) * (M / 2) + c) * sizeof(float4)));
+                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                    }
+                }
+                dsmem_st4(red0 + (uint32_t) (o * sizeof(float4)), sum);
+            }
+        }
+        cluster_sync_all();                               // rank 0 holds the reduced tile; nobody reads remote memory any more
+        if (crank != 0) return;
+        fin = red;
+    }
+    if (tid >= kThreads) return;
+    if (nsplit == 1) bar_compute();                       // the tile is complete in shared memory
+    if constexpr (INV) {
+        inv_epilogue<M>(a, fin, tid, row0, rpt);
+    } else {
+        for (int o = tid; o < rpt * (M / 2); o += kThreads) {
+            const int row = row0 + o / (M / 2);
+            if (row < a.n_rows) reinterpret_cast<float4*>(a.Y + (long long) row * M)[o % (M / 2)] = reinterpret_cast<const float4*>(fin)[o];
+        }
+    }
+}
+
+// (a + b) / 2 : tools::sumToMono (fp/tools.cpp:25-29)
+static __global__ void k_fold_mono(const float* l, const float* r, float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = l[i];
+    v += r[i];
+    v /= 2.0f;
+    out[i] = v;
 }
 
 // offline: out[chan][blk*B + m] += tail[chan][blk-1][m]   (the overlap of the previous block)

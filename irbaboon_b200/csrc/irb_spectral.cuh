@@ -277,16 +277,6 @@ static __global__ void k_avg_apply(float2* S, long long s_stride, const float* r
     s[k] = make_float2(ampl * cosf(phase), ampl * sinf(phase));
 }
 
-// (a + b) / 2 : tools::sumToMono (fp/tools.cpp:25-29)
-static __global__ void k_fold_mono(const float* l, const float* r, float* out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float v = l[i];
-    v += r[i];
-    v /= 2.0f;
-    out[i] = v;
-}
-
 // out[i] = in[(i + h1) mod n] : ir::shifteroo (fp/ir.cpp:85-103), h1 = ceil(n/2)
 static __global__ void k_shifteroo(const float* in, float* out, int n, long long stride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

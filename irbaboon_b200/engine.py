@@ -38,10 +38,14 @@ _SIGS = {
     "irb_engine_destroy": (ctypes.c_int, [_vp]),
     "irb_engine_set_stream": (ctypes.c_int, [_vp, _vp]),
     "irb_engine_set_ir": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int]),
+    "irb_engine_stage_ir": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int]),
+    "irb_engine_mac_plan": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "irb_engine_set_mac_split": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     "irb_engine_bind": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "irb_engine_tile_channels": (ctypes.c_int, [_vp]),
     "irb_engine_reset": (ctypes.c_int, [_vp]),
     "irb_engine_process": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
+    "irb_engine_process_callback": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "irb_engine_process_device": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "irb_engine_synchronize": (ctypes.c_int, [_vp]),
     "irb_engine_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -275,6 +279,27 @@ class Engine:
         else:
             raise ValueError("IR must be mono or stereo")
 
+    def stage_ir(self, ir_id, taps, n_partitions=0):
+        """Round-robin IR switch (PluginProcessor.cpp:411-414,455-461): one partition re-transformed per block step."""
+        t = _planar(taps)
+        if t.shape[0] == 1:
+            _ck(lib().irb_engine_stage_ir(self._h, int(ir_id), _ptr(t), None, t.shape[1], int(n_partitions)))
+        elif t.shape[0] == 2:
+            l, r = np.ascontiguousarray(t[0]), np.ascontiguousarray(t[1])
+            _ck(lib().irb_engine_stage_ir(self._h, int(ir_id), _ptr(l), _ptr(r), t.shape[1], int(n_partitions)))
+        else:
+            raise ValueError("IR must be mono or stereo")
+
+    def mac_plan(self):
+        """(slots_kernel, split_in, cluster) of the next block step's MAC launch."""
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _ck(lib().irb_engine_mac_plan(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return bool(a.value), b.value, c.value
+
+    def set_mac_split(self, split_in=0, cluster=0):
+        """Force how few-row launches split a row's partitions (0, 0 = automatic)."""
+        _ck(lib().irb_engine_set_mac_split(self._h, int(split_in), int(cluster)))
+
     def bind(self, chan_begin, chan_end, ir_id):
         _ck(lib().irb_engine_bind(self._h, int(chan_begin), int(chan_end), int(ir_id)))
 
@@ -294,6 +319,14 @@ class Engine:
         if out is None:
             out = np.empty(shp, np.float32)
         _ck(lib().irb_engine_process(self._h, _ptr(x), _ptr(out), nb))
+        return out
+
+    def process_callback(self, x):
+        """Blocks of one plug-in callback, reference order (all forward FFTs first): host [n_blocks][n_channels][B]."""
+        x = np.ascontiguousarray(x, np.float32)
+        assert x.ndim == 3 and x.shape[1:] == (self.n_channels, self.block_size), x.shape
+        out = np.empty(x.shape, np.float32)
+        _ck(lib().irb_engine_process_callback(self._h, _ptr(x), _ptr(out), x.shape[0]))
         return out
 
     def process_device(self, in_ptr, out_ptr, n_blocks=1):

@@ -8,8 +8,10 @@
 
 #include "../../include/irb_b200.h"
 #include "CircularBufferArray.hpp"
+#include "PluginConvolver.hpp"
 #include "StreamingConvolver.hpp"
 #include "convolution.hpp"
+#include "tools.hpp"
 
 namespace {
 
@@ -157,6 +159,89 @@ void StreamingConvolver::processBlock(AudioBuffer<float>& buffer) {
 }
 void StreamingConvolver::process(const float* in, float* out, int nBlocks) {
     if (irb_engine_process(engine, in, out, nBlocks) != IRB_OK) raise("irb_engine_process");
+}
+
+// ---- PluginConvolver ------------------------------------------------------------------------------------
+PluginConvolver::PluginConvolver(int processBlockSize, int channels_, int device_) : B(processBlockSize), channels(channels_), device(device_) {
+    latency = B;                                                                      // PluginProcessor.cpp:59
+}
+PluginConvolver::~PluginConvolver() { destroyEngine(); }
+void PluginConvolver::destroyEngine() {
+    if (engine) irb_engine_destroy(engine);
+    engine = nullptr;
+}
+void PluginConvolver::prepareToPlay(double, int samplesPerBlock, const AudioBuffer<float>& ir) {
+    if (samplesPerBlock < 1 || ir.getNumSamples() < 1 || ir.getNumChannels() < 1) throw std::invalid_argument("PluginConvolver::prepareToPlay: empty host block or IR");
+    hostBlock = samplesPerBlock;
+    latency = hostBlock > B ? hostBlock : B;                                          // :166-171
+    inArray = (int) std::ceil((float) hostBlock / (float) B);                         // :203
+    outArray = tools::nextPowerOfTwo((int) (std::ceil((float) B / (float) hostBlock) + 1));   // :205
+    partitions = (int) std::ceil((float) ir.getNumSamples() / (float) B);             // :225
+    // FDL ring: the reference's max(partitions, inArray) slots (:229-230), or room for every spectrum a callback needs
+    const int ring = exactOrder ? std::max(partitions, inArray) : partitions + inArray - 1;
+    destroyEngine();
+    if (irb_set_device(device) != IRB_OK) raise("irb_set_device");
+    if (irb_engine_create(&engine, device, B, ring, channels, 1) != IRB_OK) raise("irb_engine_create");
+    if (irb_engine_stage_ir(engine, 0, ir.getReadPointer(0), nullptr, ir.getNumSamples(), partitions) != IRB_OK) raise("irb_engine_stage_ir");
+    inBlocks.assign((size_t) (inArray + 1) * channels * B, 0.0f);        // + the block still being collected
+    outBlocks.assign((size_t) (inArray + 1) * channels * B, 0.0f);
+    outRing.assign((size_t) outArray * channels * hostBlock, 0.0f);
+    bypassRing.assign((size_t) outArray * channels * hostBlock, 0.0f);
+    inSample = 0; blocksToProcess = 0;
+    outWrite = 0; outRead = 1; outWriteSample = 0; outReadSample = 0;                 // :218
+    bypassWrite = 0; bypassRead = 0;
+}
+void PluginConvolver::setIR(const AudioBuffer<float>& ir) {
+    if (!engine) throw std::logic_error("PluginConvolver::setIR before prepareToPlay");
+    if (irb_engine_stage_ir(engine, 0, ir.getReadPointer(0), nullptr, ir.getNumSamples(), 0) != IRB_OK) raise("irb_engine_stage_ir");
+}
+void PluginConvolver::processBlock(AudioBuffer<float>& buffer) {
+    if (!engine) throw std::logic_error("PluginConvolver::processBlock before prepareToPlay");
+    const int n = buffer.getNumSamples();
+    if (n == 0) return;                                                               // :279-281
+    if (buffer.getNumChannels() < channels || n > hostBlock) throw std::invalid_argument("PluginConvolver::processBlock: buffer smaller than the channel count or longer than samplesPerBlock");
+    // collect samples into processBlockSize blocks (:421-445); a callback completes at most inArray of them
+    for (int s = 0; s < n; ++s) {
+        for (int c = 0; c < channels; ++c) inBlocks[((size_t) blocksToProcess * channels + c) * B + inSample] = buffer.getSample(c, s);
+        if (++inSample >= B) { inSample = 0; ++blocksToProcess; }
+    }
+    if (blocksToProcess > 0) {
+        // forward FFTs of all completed blocks, then per block: IR refresh, MAC, inverse FFT, overlap-add (:452-518) -- on the GPU
+        if (irb_engine_process_callback(engine, inBlocks.data(), outBlocks.data(), blocksToProcess) != IRB_OK) raise("irb_engine_process_callback");
+        // the samples of a block still being collected sit at the front of the next callback's first block
+        if (inSample > 0)
+            for (int c = 0; c < channels; ++c)
+                std::copy_n(&inBlocks[((size_t) blocksToProcess * channels + c) * B], inSample, &inBlocks[(size_t) c * B]);
+        // completed blocks -> host-sized output buffers (:525-545); a buffer is cleared when its first sample is written
+        for (int b = 0; b < blocksToProcess; ++b) {
+            for (int s = 0; s < B; ++s) {
+                float* ob = &outRing[(size_t) outWrite * channels * hostBlock];
+                if (outWriteSample == 0) std::fill_n(ob, (size_t) channels * hostBlock, 0.0f);
+                for (int c = 0; c < channels; ++c) ob[(size_t) c * hostBlock + outWriteSample] = outBlocks[((size_t) b * channels + c) * B + s];
+                if (++outWriteSample >= hostBlock) { outWriteSample = 0; if (++outWrite >= outArray) outWrite = 0; }
+            }
+        }
+        blocksToProcess = 0;
+    }
+    // output buffers -> the host's buffer (:552-560)
+    for (int s = 0; s < n; ++s) {
+        const float* ob = &outRing[(size_t) outRead * channels * hostBlock];
+        for (int c = 0; c < channels; ++c) buffer.setSample(c, s, ob[(size_t) c * hostBlock + outReadSample]);
+        if (++outReadSample >= hostBlock) { outReadSample = 0; if (++outRead >= outArray) outRead = 0; }
+    }
+    // standard attenuation, then the limiter: normalise to 0 dB when channel 0 peaks above it (:567-574)
+    buffer.applyGain(tools::dBToLin(outputVolumedB));
+    if (tools::linTodB(buffer.getMagnitude(0, 0, std::min(hostBlock, n))) > 0.0) tools::normalize(&buffer, 0.0f, false);
+}
+void PluginConvolver::processBlockBypassed(AudioBuffer<float>& buffer) {
+    if (!engine) throw std::logic_error("PluginConvolver::processBlockBypassed before prepareToPlay");
+    const int n = std::min(buffer.getNumSamples(), hostBlock);
+    float* wb = &bypassRing[(size_t) bypassWrite * channels * hostBlock];
+    for (int c = 0; c < channels; ++c) { std::fill_n(wb + (size_t) c * hostBlock, hostBlock, 0.0f); std::copy_n(buffer.getReadPointer(c), n, wb + (size_t) c * hostBlock); }
+    if (++bypassWrite >= outArray) bypassWrite = 0;
+    if (++bypassRead >= outArray) bypassRead = 0;
+    const float* rb = &bypassRing[(size_t) bypassRead * channels * hostBlock];
+    for (int c = 0; c < channels; ++c) buffer.copyFrom(c, 0, rb + (size_t) c * hostBlock, n);
 }
 
 }  // namespace b200

@@ -7,6 +7,7 @@
 #include "CircularBufferArray.hpp"
 #include "ExpSineSweep.hpp"
 #include "StreamingConvolver.hpp"
+#include "PluginConvolver.hpp"
 
 using namespace fp;
 #ifndef NOT

@@ -126,3 +126,37 @@ int fac_ess(double dur, double sr, double f1, double f2, double dB, int mode, in
 int fac_ess_index_at_freq(double freq, double dur, double sr, double f1, double f2) { fp::ExpSineSweep s; return s.getSampleIndexAtFreq(freq, dur, sr, f1, f2); }
 double fac_ess_freq_at_index(int idx, double dur, double sr, double f1, double f2) { fp::ExpSineSweep s; return s.getFreqAtSampleIndex(idx, dur, sr, f1, f2); }
 }
+
+// ---- fp::b200::PluginConvolver: processBlock semantics over the engine ----------------------------------------
+#include "../../irbaboon_b200/fp/PluginConvolver.hpp"
+extern "C" {
+void* fac_plugin_create(int B, int channels, int hostBlock, const float* ir, int irLen, int exactOrder, float volumedB) {
+    try {
+        auto* p = new fp::b200::PluginConvolver(B, channels, 0);
+        AudioBuffer<float> h(1, irLen);
+        fill(h, ir);
+        p->setExactReferenceOrder(exactOrder != 0);
+        p->setOutputVolumedB(volumedB);
+        p->prepareToPlay(48000.0, hostBlock, h);
+        return p;
+    } catch (const std::exception& e) { std::fprintf(stderr, "fac_plugin_create: %s\n", e.what()); return nullptr; }
+}
+void fac_plugin_destroy(void* h) { delete (fp::b200::PluginConvolver*) h; }
+int fac_plugin_latency(void* h) { return ((fp::b200::PluginConvolver*) h)->getLatencySamples(); }
+int fac_plugin_set_ir(void* h, const float* ir, int irLen) {
+    AudioBuffer<float> b(1, irLen);
+    fill(b, ir);
+    try { ((fp::b200::PluginConvolver*) h)->setIR(b); return 0; } catch (const std::exception&) { return -1; }
+}
+// buffer: [channels][n] planar, in place
+int fac_plugin_process(void* h, float* buffer, int channels, int n, int bypassed) {
+    AudioBuffer<float> b(channels, n);
+    fill(b, buffer);
+    try {
+        if (bypassed) ((fp::b200::PluginConvolver*) h)->processBlockBypassed(b);
+        else ((fp::b200::PluginConvolver*) h)->processBlock(b);
+        dump(b, buffer);
+        return 0;
+    } catch (const std::exception& e) { std::fprintf(stderr, "fac_plugin_process: %s\n", e.what()); return -1; }
+}
+}

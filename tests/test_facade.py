@@ -290,3 +290,116 @@ def test_facade_ir_to_real_fft_raw_and_sweep_on_gpu(fac, ref):
             got = np.zeros(len(want), np.float64)
             assert fac.fac_ess(0.25, 48000.0, 20.0, 20000.0, -3.0, mode, kind, ff, got.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == len(want)
             assert np.abs(got - want).max() <= 1e-9
+
+
+# ---- fp::b200::PluginConvolver: processBlock semantics (re-blocking, latency, round-robin IR switch, limiter, bypass) ----
+class _Plugin:
+    def __init__(self, fac, B, C, H, ir, exact=True, volume_db=0.0):
+        fac.fac_plugin_create.restype = ctypes.c_void_p
+        fac.fac_plugin_create.argtypes = [ctypes.c_int] * 3 + [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_float]
+        fac.fac_plugin_process.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        fac.fac_plugin_set_ir.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int]
+        fac.fac_plugin_latency.argtypes = [ctypes.c_void_p]
+        fac.fac_plugin_destroy.argtypes = [ctypes.c_void_p]
+        ir = np.ascontiguousarray(ir, np.float32)
+        self.fac, self.C = fac, C
+        self.h = fac.fac_plugin_create(B, C, H, _fp(ir), len(ir), int(exact), volume_db)
+        assert self.h
+
+    def process(self, buf, bypassed=False):
+        b = np.ascontiguousarray(buf, np.float32).copy()
+        assert self.fac.fac_plugin_process(self.h, _fp(b), b.shape[0], b.shape[1], int(bypassed)) == 0
+        return b
+
+    def set_ir(self, ir):
+        ir = np.ascontiguousarray(ir, np.float32)
+        assert self.fac.fac_plugin_set_ir(self.h, _fp(ir), len(ir)) == 0
+
+    @property
+    def latency(self):
+        return self.fac.fac_plugin_latency(self.h)
+
+    def close(self):
+        self.fac.fac_plugin_destroy(self.h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H", [(256, 256), (256, 64), (256, 100), (256, 512), (256, 1024), (256, 300), (64, 480), (128, 127)])
+def test_plugin_convolver_matches_oracle_processblock(fac, orc, B, H):
+    """Every host block size class (== B, divisor of B, unrelated, multiple of B) against the oracle's restatement of
+    PluginProcessor.cpp:403-562, with an IR switch in the middle of the run."""
+    C, P = 2, 8
+    ncb = 60
+    n = ncb * H
+    x = np.stack([synth.white_noise(1007, c, n) for c in range(C)])
+    h0 = synth.decaying_ir(2000, P * B)
+    h1 = synth.decaying_ir(2001, P * B - 100, 1)
+    o = orc.rt_engine(B, H, C, h0)
+    p = _Plugin(fac, B, C, H, h0)
+    assert p.latency == max(B, H)
+    got, want = [], []
+    for k in range(ncb):
+        if k == 31:
+            o.set_ir(h1)
+            p.set_ir(h1)
+        blk = x[:, k * H:(k + 1) * H]
+        want.append(o.process(blk))
+        got.append(p.process(blk))
+    o.close()
+    p.close()
+    e, l2 = parity(np.concatenate(got, axis=1), np.concatenate(want, axis=1))
+    assert e <= TOL and l2 <= TOL, (e, l2)
+
+
+@pytest.mark.gpu
+def test_plugin_convolver_causal_mode_fixes_the_large_host_block_case(fac, orc):
+    B, H, C, P = 256, 1024, 2, 8
+    n = 20 * H
+    x = np.stack([synth.white_noise(1007, c, n) for c in range(C)])
+    h = synth.decaying_ir(2000, P * B)
+    p = _Plugin(fac, B, C, H, h, exact=False)
+    y = np.concatenate([p.process(x[:, k * H:(k + 1) * H]) for k in range(20)], axis=1)
+    p.close()
+    want = orc.convolve_periodic(x, np.stack([h, h]), B)[:, :n - H]
+    assert not y[:, :H].any()
+    e, l2 = parity(y[:, H:], want)
+    assert e <= TOL and l2 <= TOL, (e, l2)
+
+
+@pytest.mark.gpu
+def test_plugin_convolver_gain_limiter_bypass_and_short_buffers(fac, orc):
+    B, H, C = 256, 256, 2
+    h = np.zeros(2048, np.float32)
+    h[100] = 1.0                                                  # the plug-in's default IR: generatePulse(2048, 100)
+    x = np.stack([synth.white_noise(1008, c, 10 * H) for c in range(C)]) * 4.0
+    # -30 dB default gain; the limiter engages when channel 0 still peaks above 0 dB (it does not here)
+    p = _Plugin(fac, B, C, H, h, volume_db=-30.0)
+    o = orc.rt_engine(B, H, C, h)
+    for k in range(10):
+        blk = x[:, k * H:(k + 1) * H]
+        want = orc.rt_post(o.process(blk), -30.0)
+        assert np.abs(p.process(blk) - want).max() <= 1e-6
+    p.close(); o.close()
+    # +12 dB: limiter path (normalise the whole buffer to 0 dB)
+    p = _Plugin(fac, B, C, H, h, volume_db=12.0)
+    o = orc.rt_engine(B, H, C, h)
+    for k in range(10):
+        blk = x[:, k * H:(k + 1) * H]
+        want = orc.rt_post(o.process(blk), 12.0)
+        got = p.process(blk)
+        assert np.abs(got - want).max() <= 2e-6
+        if k > 1:
+            assert abs(np.abs(got).max() - 1.0) <= 1e-6
+    # bypass keeps the latency: outArray = 2 buffers -> one buffer of delay (PluginProcessor.cpp:584-590)
+    a = p.process(x[:, :H], bypassed=True)
+    b = p.process(x[:, H:2 * H], bypassed=True)
+    assert not a.any() and np.array_equal(b, x[:, :H])
+    # a shorter-than-prepared callback (hosts do that at loop ends) just advances the rings by fewer samples
+    o2 = orc.rt_engine(B, H, C, h)
+    p2 = _Plugin(fac, B, C, H, h)
+    pos = 0
+    for nn in (256, 100, 256, 56, 256, 256):
+        blk = x[:, pos:pos + nn]
+        assert np.abs(p2.process(blk) - o2.process(blk)).max() <= 1e-6
+        pos += nn
+    p.close(); o.close(); p2.close(); o2.close()

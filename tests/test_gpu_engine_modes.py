@@ -1,0 +1,177 @@
+"""GPU parity of the streaming engine's launch modes against the CPU oracle:
+
+* the few-row MAC (k_mac_slots: a row's partitions split over tile slots and the CTAs of a cluster, partial sums
+  reduced through distributed shared memory) -- BASELINE config 2, the single-stream latency path;
+* the round-robin IR switch (irb_engine_stage_ir; Source/PluginProcessor.cpp:411-414,455-461) and the block order of a
+  plug-in callback (irb_engine_process_callback; :421-518) against the oracle's restatement of processBlock.
+"""
+import numpy as np
+import pytest
+
+from conftest import TOL, parity
+from irbaboon_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(got, want, tol=TOL):
+    assert got.shape == want.shape
+    e, l2 = parity(got, want)
+    assert e <= tol and l2 <= tol, (e, l2)
+
+
+# ---- few rows: partitions split inside the tile and across a cluster -------------------------------------------
+@pytest.mark.parametrize("B,Lh,C,split,cluster", [
+    (256, 256 * 37 + 11, 2, 1, 1), (256, 256 * 37 + 11, 2, 8, 1), (256, 256 * 37 + 11, 2, 1, 8), (256, 256 * 37 + 11, 2, 8, 16),
+    (256, 256 * 37 + 11, 2, 2, 4), (512, 512 * 21, 1, 4, 16), (512, 512 * 21, 5, 2, 2), (1024, 1024 * 9 + 1, 3, 2, 8),
+    (2048, 2048 * 6, 2, 1, 16), (64, 64 * 50 + 3, 3, 32, 8), (64, 64 * 50 + 3, 40, 4, 2), (16, 16 * 70, 2, 128, 8),
+    (128, 128 * 3, 2, 16, 16),          # more ranges than partitions: most slots are empty
+])
+def test_split_mac_matches_oracle(eng, orc, B, Lh, C, split, cluster):
+    n = 14 * B
+    x = np.stack([synth.white_noise(1002, c, n) for c in range(C)])
+    h = synth.decaying_ir(2000, Lh)
+    P = -(-Lh // B)
+    with eng.Engine(B, P + 2, C, 1) as e:
+        e.set_ir(0, h)
+        e.set_mac_split(split, cluster)
+        slots, s_in, cl = e.mac_plan()
+        assert slots == (s_in > 1 or cl > 1)
+        y = e.process_stream(x)
+        # one CTA per tile, the bandwidth path, on the same state
+        e.reset()
+        e.set_mac_split(1, 1)
+        assert e.mac_plan() == (False, 1, 1)
+        y1 = e.process_stream(x)
+    for c in range(C):
+        want = orc.convolve_periodic(x[c], h, B)[:, :n]
+        _check(y[c:c + 1], want)
+        _check(y1[c:c + 1], want)
+
+
+def test_split_is_chosen_automatically_for_few_rows_only(eng):
+    with eng.Engine(256, 750, 2, 2) as e:                       # BASELINE config 2: stereo, 4 s IR, one stream
+        h = synth.decaying_ir(2000, 192000)
+        e.set_ir(0, h)
+        e.set_ir(1, h)
+        e.bind(1, 2, 1)
+        slots, s_in, cl = e.mac_plan()
+        assert slots and s_in == 8 and cl == 16
+    with eng.Engine(512, 4, 4096, 1) as e:                      # throughput shape: one CTA per tile, shared-IR kernel
+        e.set_ir(0, synth.decaying_ir(2000, 2000))
+        assert e.mac_plan() == (False, 1, 1)
+
+
+def test_split_mac_per_stream_irs_of_different_lengths(eng, orc):
+    B, C = 256, 3
+    n = 12 * B
+    lens = [B * 20 + 5, B * 3, B * 11 + 100]
+    irs = [synth.decaying_ir(2100 + c, lens[c], c) for c in range(C)]
+    x = np.stack([synth.white_noise(1004, c, n) for c in range(C)])
+    with eng.Engine(B, 21, C, C) as e:
+        for c in range(C):
+            e.set_ir(c, irs[c])
+            e.bind(c, c + 1, c)
+        for split, cluster in [(0, 0), (2, 1), (1, 4), (4, 4)]:
+            e.reset()
+            e.set_mac_split(split, cluster)
+            y = e.process_stream(x)
+            for c in range(C):
+                _check(y[c:c + 1], orc.convolve_periodic(x[c], irs[c], B)[:, :n])
+
+
+def test_config2_shape_against_reference(eng, orc):
+    """BASELINE config 2 at full IR size: stereo, B=256, 4 s stereo IR (channel-wise), one stream, block by block."""
+    B, Lh, nb = 256, 192000, 40
+    n = nb * B
+    x = np.stack([synth.white_noise(1002, c, n) for c in range(2)])
+    h = np.stack([synth.decaying_ir(2000 + c, Lh, c) for c in range(2)])
+    with eng.Engine(B, 750, 2, 2) as e:
+        e.set_ir(0, h[0])
+        e.set_ir(1, h[1])
+        e.bind(1, 2, 1)
+        blocks = np.ascontiguousarray(x.reshape(2, nb, B).transpose(1, 0, 2))
+        y = np.stack([e.process(blocks[b]) for b in range(nb)])           # one call per block: the latency path
+    y = np.ascontiguousarray(y.transpose(1, 0, 2)).reshape(2, n)
+    _check(y, orc.convolve_periodic(x, h, B)[:, :n])
+
+
+# ---- round-robin IR switch and callback order against the oracle's processBlock restatement --------------------
+def _rt_oracle_run(orc, B, H, x, h0, switch_at=None, h1=None):
+    C, n = x.shape
+    e = orc.rt_engine(B, H, C, h0)
+    out = []
+    for k, i in enumerate(range(0, n, H)):
+        if switch_at is not None and k == switch_at:
+            e.set_ir(h1)
+        out.append(e.process(x[:, i:i + H]))
+    e.close()
+    return np.concatenate(out, axis=1)
+
+
+@pytest.mark.parametrize("B,C,P", [(256, 2, 8), (64, 3, 5), (512, 1, 12)])
+def test_staged_ir_round_robin_matches_oracle_processblock(eng, orc, B, C, P):
+    """Host block == B: the engine's block k is the oracle's output delayed by its reported latency (B samples)."""
+    nb = 5 * P
+    n = nb * B
+    x = np.stack([synth.white_noise(1005, c, n) for c in range(C)])
+    h0 = synth.decaying_ir(2000, P * B - 7)
+    h1 = synth.decaying_ir(2001, P * B - 40, 1)
+    sw = 2 * P + 3
+    want = _rt_oracle_run(orc, B, B, x, h0, sw, h1)
+    with eng.Engine(B, P, C, 1) as e:
+        e.stage_ir(0, h0)                                     # nothing transformed yet: partitions arrive one per block
+        assert e.partitions(0) == P
+        blocks = np.ascontiguousarray(x.reshape(C, nb, B).transpose(1, 0, 2))
+        ys = []
+        for k in range(nb):
+            if k == sw:
+                e.stage_ir(0, h1)
+            ys.append(e.process(blocks[k]))
+    y = np.ascontiguousarray(np.stack(ys).transpose(1, 0, 2)).reshape(C, n)
+    assert not want[:, :B].any()
+    _check(y[:, :n - B], want[:, B:])
+    # while the new IR fades in the output is neither the old nor the new convolution: the test above pins the mix
+
+
+def test_staged_ir_equals_preloaded_ir_from_a_cold_start(eng):
+    """Round-robin loading from block 0 is indistinguishable from a preloaded IR (partition p is first needed at block p)."""
+    B, C, P = 128, 2, 6
+    x = np.stack([synth.white_noise(1005, c, 20 * B) for c in range(C)])
+    h = synth.decaying_ir(2000, P * B)
+    with eng.Engine(B, P, C, 1) as e:
+        e.set_ir(0, h)
+        a = e.process_stream(x)
+    with eng.Engine(B, P, C, 1) as e:
+        e.stage_ir(0, h)
+        b = e.process_stream(x)
+        e.reset()                                             # prepareToPlay: spectra cleared, refresh restarts at 0
+        c = e.process_stream(x)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+@pytest.mark.parametrize("B,H,C,P,ring", [(256, 512, 2, 8, 8), (256, 1024, 2, 8, 8), (64, 256, 1, 3, 4), (128, 256, 2, 4, 16)])
+def test_callback_order_matches_oracle_when_host_block_exceeds_B(eng, orc, B, H, C, P, ring):
+    """hostBlock = m*B: the reference transforms the callback's m blocks before convolving any of them, so with its
+    ring of max(P, m) slots the oldest partitions see the callback's later blocks.  irb_engine_process_callback keeps
+    that order; the oracle restates PluginProcessor.cpp:403-562."""
+    m = H // B
+    ncb = 12
+    n = ncb * H
+    x = np.stack([synth.white_noise(1006, c, n) for c in range(C)])
+    h = synth.decaying_ir(2000, P * B - 3)
+    want = _rt_oracle_run(orc, B, H, x, h)
+    with eng.Engine(B, ring, C, 1) as e:
+        e.stage_ir(0, h, P)
+        ys = []
+        for k in range(ncb):
+            blk = x[:, k * H:(k + 1) * H].reshape(C, m, B).transpose(1, 0, 2)
+            ys.append(e.process_callback(blk))
+    y = np.ascontiguousarray(np.concatenate(ys).transpose(1, 0, 2)).reshape(C, n)
+    if ring == max(P, m):
+        assert not want[:, :H].any()
+        _check(y[:, :n - H], want[:, H:])                     # latency = hostBlock (PluginProcessor.cpp:166-171)
+    else:
+        # a ring with room for partitions + m - 1 spectra gives the causal result instead
+        causal = orc.convolve_periodic(x, h[None, :], B)[:, :n]
+        _check(y, causal)

@@ -171,3 +171,65 @@ def test_synth_generators_match_c(orc):
     assert np.array_equal(orc.white_noise(1001, 3, 1000), synth.white_noise(1001, 3, 1000))
     h = synth.decaying_ir(2000, 4800)
     assert abs(float(np.sqrt((h.astype(np.float64) ** 2).sum())) - 1.0) < 1e-6
+
+
+# ---- the processBlock restatement (orc_rt_*) ---------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,delay", [(256, 256, 256), (256, 64, 448), (256, 100, 300), (128, 128, 128), (64, 32, 96)])
+def test_rt_restatement_is_the_offline_convolution_delayed(orc, B, H, delay):
+    """Host blocks <= processBlockSize: the streaming engine of PluginProcessor.cpp:403-562 is convolvePeriodic delayed
+    by (outputArraySize - 1) host buffers (>= the latency the plug-in reports, max(B, H))."""
+    n = H * 40
+    x = np.stack([synth.white_noise(1, c, n) for c in range(2)])
+    h = synth.decaying_ir(2000, 3 * B + 5)
+    e = orc.rt_engine(B, H, 2, h)
+    y = np.concatenate([e.process(x[:, i:i + H]) for i in range(0, n, H)], axis=1)
+    e.close()
+    want = orc.convolve_periodic(x, np.stack([h, h]), B)[:, :n - delay]
+    assert not y[:, :delay].any()
+    assert np.abs(y[:, delay:] - want).max() <= 1e-6 * max(1.0, np.abs(want).max())
+
+
+def test_rt_restatement_large_host_blocks_read_future_blocks(orc):
+    """hostBlock > processBlockSize with the reference's ring of max(P, hostBlock/B) spectra: all blocks of a callback
+    are transformed before any is convolved (PluginProcessor.cpp:421-445 then :452-518), so the oldest partitions of
+    the callback's first blocks multiply spectra of its LATER blocks -- the output is not a delayed convolution."""
+    B, H, P = 256, 512, 8
+    n = H * 30
+    x = synth.white_noise(1, 0, n)[None, :]
+    h = synth.decaying_ir(2000, P * B)
+    e = orc.rt_engine(B, H, 1, h)
+    y = np.concatenate([e.process(x[:, i:i + H]) for i in range(0, n, H)], axis=1)
+    e.close()
+    want = orc.convolve_periodic(x, h, B)[:, :n - H]
+    assert np.abs(y[:, H:] - want).max() > 1e-3
+    # with an IR one partition shorter every partition still meets the right slot
+    h2 = h[:(P - 1) * B]
+    e = orc.rt_engine(B, H, 1, np.concatenate([h2, np.zeros(B, np.float32)]))
+    y = np.concatenate([e.process(x[:, i:i + H]) for i in range(0, n, H)], axis=1)
+    e.close()
+    # partition P-1 is all zeros, so its acausal product vanishes
+    assert np.abs(y[:, H:] - orc.convolve_periodic(x, h2, B)[:, :n - H]).max() <= 1e-6 * 10
+
+
+def test_rt_restatement_round_robin_ir_switch(orc):
+    """After orc_rt_set_ir the partitions are replaced one per processed block: P blocks later the output is the new
+    IR's convolution of the recent input; before that it is a partition-wise mix of both."""
+    B, P = 128, 6
+    n = B * 40
+    x = synth.white_noise(1, 0, n)[None, :]
+    h0, h1 = synth.decaying_ir(2000, P * B), synth.decaying_ir(2001, P * B, 1)
+    e = orc.rt_engine(B, B, 1, h0)
+    out = []
+    for k in range(40):
+        if k == 15:
+            e.set_ir(h1)
+        out.append(e.process(x[:, k * B:(k + 1) * B]))
+    e.close()
+    y = np.concatenate(out, axis=1)[:, B:]
+    y0 = orc.convolve_periodic(x, h0, B)[:, :n - B]
+    y1 = orc.convolve_periodic(x, h1, B)[:, :n - B]
+    assert np.abs(y[:, :15 * B] - y0[:, :15 * B]).max() <= 1e-5
+    assert np.abs(y[:, 15 * B:16 * B] - y0[:, 15 * B:16 * B]).max() > 1e-3          # the first partition is already new
+    # the write position was 15 % 6 = 3 at the switch: all six partitions are new after 6 more blocks, and the FDL
+    # only holds blocks convolved with ... the new spectra from then on
+    assert np.abs(y[:, 21 * B:] - y1[:, 21 * B:]).max() <= 1e-5
