@@ -11,6 +11,8 @@ namespace irbh {
 int fail(int code, const char* fmt, ...);                      // records the thread's last error, returns code
 int current_device();                                          // device chosen by irb_set_device on this thread
 int twiddles(int dev, int M, const float2** out);              // table of the 2M roots exp(-2 pi i k / 2M), cached per (device, M)
+// two-level table of the M-th roots: exp(-2 pi i idx / M) = hi[idx >> 10] * lo[idx & 1023], cached per (device, M)
+int twiddles2(int dev, int M, const float2** hi, const float2** lo);
 extern std::atomic<long long> g_launches;
 
 #define CK(call)                                                                                         \
@@ -27,7 +29,12 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFree(p); }
     int alloc(size_t bytes, bool zero) {
         CK(cudaMalloc(&p, bytes ? bytes : 16));
-        if (zero) CK(cudaMemset(p, 0, bytes ? bytes : 16));
+        if (zero) {
+            // cudaMemset runs on the legacy stream, asynchronously to the host, and the library's own streams are
+            // non-blocking: wait for it here or a later copy on another stream could be overwritten by the zeros
+            CK(cudaMemset(p, 0, bytes ? bytes : 16));
+            CK(cudaStreamSynchronize(cudaStreamLegacy));
+        }
         return 0;
     }
     template <typename T> T* as() const { return (T*) p; }

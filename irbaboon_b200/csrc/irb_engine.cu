@@ -55,6 +55,30 @@ int twiddles(int dev, int M, const float2** out) {
     return 0;
 }
 
+int twiddles2(int dev, int M, const float2** hi, const float2** lo) {
+    struct Entry { int dev, M; float2 *hi, *lo; };
+    static std::mutex mu;
+    static std::vector<Entry> tab;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : tab) if (e.dev == dev && e.M == M) { *hi = e.hi; *lo = e.lo; return 0; }
+    const int nlo = 1024, nhi = (M + nlo - 1) / nlo;
+    std::vector<float2> h(nhi + nlo);
+    for (int a = 0; a < nhi; ++a) {
+        const double ang = -2.0 * M_PI * ((double) a * nlo) / (double) M;
+        h[a].x = (float) cos(ang); h[a].y = (float) sin(ang);
+    }
+    for (int b = 0; b < nlo; ++b) {
+        const double ang = -2.0 * M_PI * (double) b / (double) M;
+        h[nhi + b].x = (float) cos(ang); h[nhi + b].y = (float) sin(ang);
+    }
+    float2* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(float2) * h.size()));
+    CK(cudaMemcpy(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
+    tab.push_back({dev, M, d, d + nhi});
+    *hi = d; *lo = d + nhi;
+    return 0;
+}
+
 }  // namespace irbh
 
 namespace {

@@ -4,6 +4,7 @@
 // irb_spectral.cuh; the host only sizes buffers, copies and launches.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -45,10 +46,38 @@ int launch_line(int L, bool inv, const irb::LineArgs& a, int batch, cudaStream_t
 #undef IRB_LINE_CASE
 }
 
+template <int L, bool DIV>
+int launch_pair_t(const irb::PairArgs& a, int batch, cudaStream_t st) {
+    using T = irb::PairTile<L>;
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CK(cudaFuncSetAttribute(irb::k_rowpair<L, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T::SMEM));
+        configured_dev = dev;
+    }
+    dim3 grid((a.M1 / 2 + 1 + T::NP - 1) / T::NP, batch);
+    irb::k_rowpair<L, DIV><<<grid, irb::kThreads, T::SMEM, st>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int launch_pair(int L, bool div, const irb::PairArgs& a, int batch, cudaStream_t st) {
+#define IRB_PAIR_CASE(LL) case LL: return div ? launch_pair_t<LL, true>(a, batch, st) : launch_pair_t<LL, false>(a, batch, st);
+    switch (L) {
+        IRB_PAIR_CASE(64) IRB_PAIR_CASE(128) IRB_PAIR_CASE(256) IRB_PAIR_CASE(512) IRB_PAIR_CASE(1024)
+        default: return fail(IRB_ERR_ARG, "unsupported row length %d", L);
+    }
+#undef IRB_PAIR_CASE
+}
+
 // M-point complex FFT plan: one pass for M <= 2048, else M = M1 * M2 (both in [64, 1024])
 struct Plan {
     int M = 0, M1 = 1, M2 = 0;
     const float2 *W1 = nullptr, *W2 = nullptr, *WN = nullptr;   // WN: table of the N = 2M roots when M <= 2048, else null (computed in double)
+    const float2 *Thi = nullptr, *Tlo = nullptr;                // two-level table of the M-th roots (inter-pass twiddles)
+    const float2 *Nhi = nullptr, *Nlo = nullptr;                // two-level table of the 2M-th roots (split / merge of the big transforms)
+    bool big() const { return M1 > 1; }
     int init(int dev, int M_) {
         M = M_;
         if (M < kMinM || M > kMaxBigM || (M & (M - 1))) return fail(IRB_ERR_ARG, "FFT half size %d outside [%d, %d] or not a power of two", M, kMinM, kMaxBigM);
@@ -62,7 +91,9 @@ struct Plan {
             while ((1 << lg) < M) ++lg;
             M1 = 1 << (lg / 2);
             M2 = M / M1;
-            if ((rc = irbh::twiddles(dev, M1, &W1)) || (rc = irbh::twiddles(dev, M2, &W2))) return rc;
+            if ((rc = irbh::twiddles(dev, M1, &W1)) || (rc = irbh::twiddles(dev, M2, &W2)) || (rc = irbh::twiddles2(dev, M, &Thi, &Tlo)) ||
+                (rc = irbh::twiddles2(dev, 2 * M, &Nhi, &Nlo)))
+                return rc;
         }
         return 0;
     }
@@ -85,7 +116,7 @@ struct Plan {
         // pass 1: M2 column transforms of length M1 (element n1 of line n2 at n1*M2 + n2), twiddle exp(-+2 pi i n2 k1 / M)
         a.in = in; a.out = tmp; a.in_elem_stride = M2; a.in_line_stride = 1; a.in_batch_stride = in_stride;
         a.out_elem_stride = M2; a.out_line_stride = 1; a.out_batch_stride = M;
-        a.n_lines = M2; a.in_real_len = real_len; a.tw_M = M; a.scale = 1.0f; a.W = W1;
+        a.n_lines = M2; a.in_real_len = real_len; a.tw_M = M; a.tw_hi = Thi; a.tw_lo = Tlo; a.scale = 1.0f; a.W = W1;
         int rc = launch_line(M1, inv, a, batch, st);
         if (rc) return rc;
         // pass 2: M1 row transforms of length M2 (line k1 at k1*M2), bin k1 + M1*k2 written in natural order
@@ -94,36 +125,95 @@ struct Plan {
         a.n_lines = M1; a.in_real_len = -1; a.tw_M = 0; a.scale = scale; a.W = W2;
         return launch_line(M2, inv, a, batch, st);
     }
+    // ---- the fused pipeline of the big transforms (M1 > 1); rows = [batch][M1][M2] ------------------------------
+    // column pass of the forward transform: signal (real when real_len >= 0) -> rows, inter-pass twiddle applied
+    int cols_fwd(const void* in, long long in_stride, int real_len, float2* rows, int batch, cudaStream_t st) const {
+        irb::LineArgs a{};
+        a.in = in; a.out = rows; a.in_elem_stride = M2; a.in_line_stride = 1; a.in_batch_stride = in_stride;
+        a.out_elem_stride = M2; a.out_line_stride = 1; a.out_batch_stride = M;
+        a.n_lines = M2; a.in_real_len = real_len; a.tw_M = M; a.tw_hi = Thi; a.tw_lo = Tlo; a.scale = 1.0f; a.W = W1;
+        return launch_line(M1, false, a, batch, st);
+    }
+    // row transforms in place (row k1 then holds the bins k1 + M1*k2), then the split spectrum of a real signal in row layout
+    int rows_to_split_spectrum(float2* rows, float2* brows, int batch, cudaStream_t st) const {
+        irb::LineArgs a{};
+        a.in = rows; a.out = rows; a.in_elem_stride = 1; a.in_line_stride = M2; a.in_batch_stride = M;
+        a.out_elem_stride = 1; a.out_line_stride = M2; a.out_batch_stride = M;
+        a.n_lines = M1; a.in_real_len = -1; a.tw_M = 0; a.scale = 1.0f; a.W = W2;
+        int rc = launch_line(M2, false, a, batch, st);
+        if (rc) return rc;
+        irb::k_split_rows<<<dim3((unsigned) ((M + 255) / 256), (unsigned) batch), 256, 0, st>>>(rows, brows, M1, M2, Nhi, Nlo);
+        g_launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    // rows of `batch` signals: forward row FFT, per-bin multiply / divide by brows, inverse row FFT + twiddle, in place
+    int rows_binop(float2* rows, const float2* brows, long long b_stride, bool div, int batch, cudaStream_t st) const {
+        irb::PairArgs a{};
+        a.Z = rows; a.z_batch_stride = M; a.Brows = brows; a.b_batch_stride = b_stride; a.M1 = M1; a.W = W2;
+        a.Nhi = Nhi; a.Nlo = Nlo; a.Mhi = Thi; a.Mlo = Tlo;
+        return launch_pair(M2, div, a, batch, st);
+    }
+    // column pass of the inverse transform: rows -> out (natural order), scaled
+    int cols_inv(const float2* rows, float2* out, long long out_stride, int batch, float scale, cudaStream_t st) const {
+        irb::LineArgs a{};
+        a.in = rows; a.out = out; a.in_elem_stride = M2; a.in_line_stride = 1; a.in_batch_stride = M;
+        a.out_elem_stride = M2; a.out_line_stride = 1; a.out_batch_stride = out_stride;
+        a.n_lines = M2; a.in_real_len = -1; a.tw_M = 0; a.scale = scale; a.W = W1;
+        return launch_line(M1, true, a, batch, st);
+    }
 };
 
 inline dim3 grid1(long long n, int batch) { return dim3((unsigned) ((n + 255) / 256), (unsigned) batch); }
 #define LAUNCHED() do { g_launches++; CK(cudaGetLastError()); } while (0)
 
-// three smoothing passes on interleaved spectra S[batch][>= M+1] (fp/convolution.cpp:389-394 calls this 3x with 1/13 octave)
-int averaging_pass(float2* S, long long s_stride, int batch, int M, double octave_fraction, double sample_rate, int log_avg, int include_phase,
-                   int include_ampl, float* la, float* rs, int* lo, int* hi, cudaStream_t st) {
-    const double fract_per_side = octave_fraction / 2.0;
-    const double nyquist = sample_rate / 2;
-    const double freq_per_bin = nyquist / (double) M;                  // fp/convolution.cpp:425 (N/2 complex bins up to Nyquist)
-    const double c_side = pow(2.0, fract_per_side);
-    const long long stride = M + 1;
-    irb::k_avg_prepare<<<grid1(M + 1, batch), 256, 0, st>>>(S, s_stride, la, stride, lo, hi, M, log_avg, freq_per_bin, c_side);
-    LAUNCHED();
-    if (log_avg) irb::k_avg_scan<<<batch, 32, 0, st>>>(la, stride, lo, hi, rs, stride, M);
-    else irb::k_avg_linear_sum<<<grid1(M + 1, batch), 256, 0, st>>>(la, stride, lo, hi, rs, stride, M);
-    LAUNCHED();
-    irb::k_avg_apply<<<grid1(M + 1, batch), 256, 0, st>>>(S, s_stride, rs, stride, lo, hi, M, log_avg, include_phase, include_ampl);
-    LAUNCHED();
-    return 0;
-}
-
-struct SmoothBufs {
-    DevBuf la, rs, lo, hi;
-    int alloc(int M, int batch) {
+// fp::convolution::averagingFilter state shared by every spectrum and pass of a call: windows, the operation list of
+// the running sum and its chunking (irb_spectral.cuh), plus per-spectrum scratch
+struct Smoother {
+    DevBuf la, rs, lo, hi, ops, endq, kstart;
+    int M = 0, n_ops = 0, nchunks = 0;
+    int init(int M_, int batch, double octave_fraction, double sample_rate, int log_avg, cudaStream_t st) {
+        M = M_;
+        const double fract_per_side = octave_fraction / 2.0;
+        const double nyquist = sample_rate / 2;
+        const double freq_per_bin = nyquist / (double) M;                  // fp/convolution.cpp:425 (N/2 complex bins up to Nyquist)
+        const double c_side = pow(2.0, fract_per_side);
+        if (!(octave_fraction >= 0.0) || !(freq_per_bin > 0.0) || c_side * (double) M > 1.0e9) return fail(IRB_ERR_ARG, "averagingFilter: octave fraction %g / sample rate %g out of range", octave_fraction, sample_rate);
         int rc;
         if ((rc = la.alloc(sizeof(float) * (size_t) (M + 1) * batch, false)) || (rc = rs.alloc(sizeof(float) * (size_t) (M + 1) * batch, false)) ||
             (rc = lo.alloc(sizeof(int) * (size_t) (M + 1), false)) || (rc = hi.alloc(sizeof(int) * (size_t) (M + 1), false)))
             return rc;
+        irb::k_avg_windows<<<grid1(M + 1, 1), 256, 0, st>>>(lo.as<int>(), hi.as<int>(), M, freq_per_bin, c_side);
+        LAUNCHED();
+        if (log_avg) {
+            // the same double operations as k_avg_windows for k = M give the length of the operation list
+            const double f = (double) M * freq_per_bin;
+            const long long T = (long long) round((f / c_side) / freq_per_bin) + (long long) round((f * c_side) / freq_per_bin) + 1;
+            n_ops = (int) T;
+            nchunks = (n_ops + irb::kAvgChunk - 1) / irb::kAvgChunk;
+            if ((rc = ops.alloc(sizeof(int) * (size_t) n_ops, false)) || (rc = endq.alloc(sizeof(int) * (size_t) (M + 1), false)) ||
+                (rc = kstart.alloc(sizeof(int) * (size_t) (nchunks + 1), false)))
+                return rc;
+            irb::k_avg_oplist<<<grid1(M + 1, 1), 256, 0, st>>>(lo.as<int>(), hi.as<int>(), ops.as<int>(), endq.as<int>(), M);
+            LAUNCHED();
+            irb::k_avg_chunk_starts<<<grid1(M + 1, 1), 256, 0, st>>>(endq.as<int>(), kstart.as<int>(), M, nchunks);
+            LAUNCHED();
+        }
+        return 0;
+    }
+    // `passes` smoothing passes on interleaved spectra S[batch][>= M+1] (fp/convolution.cpp:389-394 runs three)
+    int run(float2* S, long long s_stride, int batch, int passes, int log_avg, int include_phase, int include_ampl, cudaStream_t st) {
+        const long long stride = M + 1;
+        irb::k_avg_prepare<<<grid1(M + 1, batch), 256, 0, st>>>(S, s_stride, la.as<float>(), stride, M, log_avg);
+        LAUNCHED();
+        for (int i = 0; i < passes; ++i) {
+            if (log_avg) irb::k_avg_scan<<<batch, 128, 0, st>>>(la.as<float>(), stride, ops.as<int>(), endq.as<int>(), kstart.as<int>(), nchunks, n_ops, rs.as<float>(), stride, M);
+            else irb::k_avg_linear_sum<<<grid1(M + 1, batch), 256, 0, st>>>(la.as<float>(), stride, lo.as<int>(), hi.as<int>(), rs.as<float>(), stride, M);
+            LAUNCHED();
+            irb::k_avg_apply<<<grid1(M + 1, batch), 256, 0, st>>>(S, s_stride, rs.as<float>(), stride, lo.as<int>(), hi.as<int>(), M, log_avg, include_phase, include_ampl,
+                                                                  i + 1 < passes ? la.as<float>() : nullptr, stride);
+            LAUNCHED();
+        }
         return 0;
     }
 };
@@ -176,12 +266,21 @@ int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h
         LAUNCHED();
         hsrc = dhf.as<float>();
     }
-    if ((rc = plan.run(dx.p, lxe / 2, len_x, Zx.as<float2>(), M, tmp.as<float2>(), ch_x, false, 1.0f, st))) return rc;
-    if ((rc = plan.run(hsrc, lhe / 2, len_h, Zh.as<float2>(), M, tmp.as<float2>(), n_ir, false, 1.0f, st))) return rc;
-    // per channel: bins of the audio times bins of its IR (fp/convolution.cpp:326-335), in place on Zx
-    irb::k_spec_fused<false><<<grid1(M / 2 + 1, ch_x), 256, 0, st>>>(Zx.as<float2>(), M, Zh.as<float2>(), n_ir == 2 ? M : 0, Zx.as<float2>(), M, M, plan.WN);
-    LAUNCHED();
-    if ((rc = plan.run(Zx.p, M, -1, dy.as<float2>(), M, tmp.as<float2>(), ch_x, true, 1.0f / (float) N, st))) return rc;
+    if (plan.big()) {
+        // column passes, then one fused kernel per row pair: row FFT, bins of the audio times bins of its IR, inverse row FFT
+        if ((rc = plan.cols_fwd(dx.p, lxe / 2, len_x, Zx.as<float2>(), ch_x, st)) || (rc = plan.cols_fwd(hsrc, lhe / 2, len_h, Zh.as<float2>(), n_ir, st)) ||
+            (rc = plan.rows_to_split_spectrum(Zh.as<float2>(), tmp.as<float2>(), n_ir, st)) ||
+            (rc = plan.rows_binop(Zx.as<float2>(), tmp.as<float2>(), n_ir == 2 ? M : 0, false, ch_x, st)) ||
+            (rc = plan.cols_inv(Zx.as<float2>(), dy.as<float2>(), M, ch_x, 1.0f / (float) N, st)))
+            return rc;
+    } else {
+        if ((rc = plan.run(dx.p, lxe / 2, len_x, Zx.as<float2>(), M, tmp.as<float2>(), ch_x, false, 1.0f, st))) return rc;
+        if ((rc = plan.run(hsrc, lhe / 2, len_h, Zh.as<float2>(), M, tmp.as<float2>(), n_ir, false, 1.0f, st))) return rc;
+        // per channel: bins of the audio times bins of its IR (fp/convolution.cpp:326-335), in place on Zx
+        irb::k_spec_fused<false><<<grid1(M / 2 + 1, ch_x), 256, 0, st>>>(Zx.as<float2>(), M, Zh.as<float2>(), n_ir == 2 ? M : 0, Zx.as<float2>(), M, M, plan.WN);
+        LAUNCHED();
+        if ((rc = plan.run(Zx.p, M, -1, dy.as<float2>(), M, tmp.as<float2>(), ch_x, true, 1.0f / (float) N, st))) return rc;
+    }
     if ((rc = tm.end())) return rc;
     for (int c = 0; c < ch_x; ++c)
         CK(cudaMemcpyAsync(out + (size_t) c * Lout, dy.as<float>() + (size_t) c * N, sizeof(float) * Lout, cudaMemcpyDeviceToHost, st));
@@ -192,6 +291,8 @@ int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h
 // fp::convolution::deconvolve (fp/convolution.cpp:351-403) for `batch` numerators against one denominator.
 // nums: [batch][len_num] (channel 0 of each capture, as tools::fftTransform reads only channel 0, fp/tools.cpp:328)
 // out: [batch][N], N = nextPowerOfTwo(max(len_num, len_den))
+// The batch runs in sub-batches through a three-stage pipeline (upload i+1 | kernels i | download i-1) over
+// double-buffered device memory; a sub-batch is small enough for its intermediate spectra to stay in the L2.
 int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase,
                          int include_amplitude, float* out) {
     if (!nums || !den || !out) return fail(IRB_ERR_ARG, "null argument");
@@ -202,63 +303,106 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
     CK(cudaSetDevice(dev));
     Plan plan;
     if ((rc = plan.init(dev, M))) return rc;
-    irbh::StreamGuard sg;
-    if ((rc = sg.create())) return rc;
+    irbh::StreamGuard sg, sg_in, sg_out;
+    if ((rc = sg.create()) || (rc = sg_in.create()) || (rc = sg_out.create())) return rc;
     cudaStream_t st = sg.s;
     const long long lne = (len_num + 1) & ~1LL, lde = (len_den + 1) & ~1LL;
-    // work on chunks of the batch so that device memory stays bounded (about 6 N floats per item)
-    const int chunk = (int) std::max<long long>(1, std::min<long long>(batch, (8LL << 30) / (sizeof(float) * 8LL * N)));
-    DevBuf dn, dd, Zn, Zd, tmp, S, Sd, dy, dy2;
-    SmoothBufs sm;
-    if ((rc = dn.alloc(sizeof(float) * lne * chunk, true)) || (rc = dd.alloc(sizeof(float) * lde, true)) || (rc = Zn.alloc(sizeof(float2) * (size_t) M * chunk, false)) ||
-        (rc = Zd.alloc(sizeof(float2) * (size_t) M, false)) || (rc = tmp.alloc(sizeof(float2) * (size_t) M * chunk, false)) ||
-        (rc = dy.alloc(sizeof(float2) * (size_t) M * chunk, false)))
-        return rc;
-    if (smoothing && ((rc = S.alloc(sizeof(float2) * (size_t) (M + 1) * chunk, false)) || (rc = Sd.alloc(sizeof(float2) * (size_t) (M + 1), false)) || (rc = sm.alloc(M, chunk))))
-        return rc;
-    if (!include_phase && (rc = dy2.alloc(sizeof(float) * (size_t) N * chunk, false))) return rc;
-    irbh::ComputeTimer tm;
-    if ((rc = tm.init(st))) return rc;
+    // captures per sub-batch: about 48 MB of spectra (IRB_DECONV_SUB overrides), never more than the batch
+    static const int sub_env = [] { const char* v = getenv("IRB_DECONV_SUB"); return v ? atoi(v) : 0; }();
+    int sub = sub_env > 0 ? sub_env : (int) std::max<long long>(1, (48LL << 20) / ((long long) sizeof(float2) * M));
+    // smoothing: the running sum is one sequential chain per capture, so the whole batch (up to ~6 GB of state) goes at once
+    if (smoothing) sub = (int) std::max<long long>(1, (6LL << 30) / (28LL * N));
+    sub = std::min(sub, batch);
+    const bool fused = plan.big() && !smoothing;
+    struct Slot { DevBuf dn, Zn, dy, dy2, tmp, S; cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr, t0 = nullptr, t1 = nullptr;
+                  ~Slot() { for (cudaEvent_t e : {ev_in, ev_done, ev_out, t0, t1}) if (e) cudaEventDestroy(e); } } slot[2];
+    DevBuf dd, Zd, Bd, Sd, dtmp;
+    Smoother sm;
+    const float smooth_per_avg = 1.0 / 13.0;                                          // fp/convolution.cpp:390 (a float there)
+    const int nslots = batch > sub ? 2 : 1;
+    for (int i = 0; i < nslots; ++i) {
+        Slot& q = slot[i];
+        if ((rc = q.dn.alloc(sizeof(float) * lne * sub, true)) || (rc = q.Zn.alloc(sizeof(float2) * (size_t) M * sub, false)) ||
+            (rc = q.dy.alloc(sizeof(float2) * (size_t) M * sub, false)))
+            return rc;
+        if (!fused && (rc = q.tmp.alloc(sizeof(float2) * (size_t) M * sub, false))) return rc;
+        if (smoothing && (rc = q.S.alloc(sizeof(float2) * (size_t) (M + 1) * sub, false))) return rc;
+        if (!include_phase && (rc = q.dy2.alloc(sizeof(float) * (size_t) N * sub, false))) return rc;
+        CK(cudaEventCreateWithFlags(&q.ev_in, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&q.ev_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&q.ev_out, cudaEventDisableTiming)); CK(cudaEventCreate(&q.t0)); CK(cudaEventCreate(&q.t1));
+    }
+    if ((rc = dd.alloc(sizeof(float) * lde, true)) || (rc = Zd.alloc(sizeof(float2) * (size_t) M, false)) || (rc = dtmp.alloc(sizeof(float2) * (size_t) M, false))) return rc;
+    if (fused && (rc = Bd.alloc(sizeof(float2) * (size_t) M, false))) return rc;
+    if (smoothing && ((rc = Sd.alloc(sizeof(float2) * (size_t) (M + 1), false)) || (rc = sm.init(M, sub, (double) smooth_per_avg, sample_rate, 1, st)))) return rc;
     irbh::set_last_compute_ms(0.0);
+    // the denominator's spectrum, once
     CK(cudaMemcpyAsync(dd.p, den, sizeof(float) * len_den, cudaMemcpyHostToDevice, st));
-    if ((rc = plan.run(dd.p, lde / 2, len_den, Zd.as<float2>(), M, tmp.as<float2>(), 1, false, 1.0f, st))) return rc;
-    if (smoothing) {
-        irb::k_spec_split<<<grid1(M + 1, 1), 256, 0, st>>>(Zd.as<float2>(), M, Sd.as<float2>(), M + 1, M, 0, plan.WN);
-        LAUNCHED();
-    }
-    for (int b0 = 0; b0 < batch; b0 += chunk) {
-        const int nb = std::min(chunk, batch - b0);
-        CK(cudaMemcpy2DAsync(dn.p, sizeof(float) * lne, nums + (size_t) b0 * len_num, sizeof(float) * len_num, sizeof(float) * len_num, nb, cudaMemcpyHostToDevice, st));
-        if ((rc = tm.begin())) return rc;
-        if ((rc = plan.run(dn.p, lne / 2, len_num, Zn.as<float2>(), M, tmp.as<float2>(), nb, false, 1.0f, st))) return rc;
-        if (!smoothing) {
-            irb::k_spec_fused<true><<<grid1(M / 2 + 1, nb), 256, 0, st>>>(Zn.as<float2>(), M, Zd.as<float2>(), 0, Zn.as<float2>(), M, M, plan.WN);
+    if (fused) {
+        if ((rc = plan.cols_fwd(dd.p, lde / 2, len_den, Zd.as<float2>(), 1, st)) || (rc = plan.rows_to_split_spectrum(Zd.as<float2>(), Bd.as<float2>(), 1, st))) return rc;
+    } else {
+        if ((rc = plan.run(dd.p, lde / 2, len_den, Zd.as<float2>(), M, dtmp.as<float2>(), 1, false, 1.0f, st))) return rc;
+        if (smoothing) {
+            irb::k_spec_split<<<grid1(M + 1, 1), 256, 0, st>>>(Zd.as<float2>(), M, Sd.as<float2>(), M + 1, M, 0, plan.WN);
             LAUNCHED();
+        }
+    }
+    double total_ms = 0.0;
+    int it = 0;
+    auto collect = [&](Slot& q) -> int {          // kernel time of the sub-batch that last used this slot
+        CK(cudaEventSynchronize(q.t1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, q.t0, q.t1));
+        total_ms += ms;
+        return 0;
+    };
+    for (int b0 = 0; b0 < batch; b0 += sub, ++it) {
+        Slot& q = slot[it & 1];
+        const int nb = std::min(sub, batch - b0);
+        if (it >= 2) {
+            CK(cudaStreamWaitEvent(sg_in.s, q.ev_done, 0));                          // kernels of it-2 have consumed q.dn
+            if ((rc = collect(q))) return rc;
+        }
+        CK(cudaMemcpy2DAsync(q.dn.p, sizeof(float) * lne, nums + (size_t) b0 * len_num, sizeof(float) * len_num, sizeof(float) * len_num, nb, cudaMemcpyHostToDevice, sg_in.s));
+        CK(cudaEventRecord(q.ev_in, sg_in.s));
+        CK(cudaStreamWaitEvent(st, q.ev_in, 0));
+        if (it >= 2) CK(cudaStreamWaitEvent(st, q.ev_out, 0));                       // download of it-2 has drained q.dy
+        CK(cudaEventRecord(q.t0, st));
+        if (fused) {
+            if ((rc = plan.cols_fwd(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), nb, st)) || (rc = plan.rows_binop(q.Zn.as<float2>(), Bd.as<float2>(), 0, true, nb, st)) ||
+                (rc = plan.cols_inv(q.Zn.as<float2>(), q.dy.as<float2>(), M, nb, 1.0f / (float) N, st)))
+                return rc;
         } else {
-            irb::k_spec_split<<<grid1(M + 1, nb), 256, 0, st>>>(Zn.as<float2>(), M, S.as<float2>(), M + 1, M, 0, plan.WN);
-            LAUNCHED();
-            irb::k_spec_binop<true><<<grid1(M + 1, nb), 256, 0, st>>>(S.as<float2>(), M + 1, Sd.as<float2>(), 0, M);
-            LAUNCHED();
-            const float smooth_per_avg = 1.0 / 13.0;                                  // fp/convolution.cpp:390 (a float there)
-            for (int i = 0; i < 3; ++i)
-                if ((rc = averaging_pass(S.as<float2>(), M + 1, nb, M, (double) smooth_per_avg, sample_rate, 1, include_phase, include_amplitude, sm.la.as<float>(),
-                                         sm.rs.as<float>(), sm.lo.as<int>(), sm.hi.as<int>(), st)))
-                    return rc;
-            irb::k_spec_merge<<<grid1(M, nb), 256, 0, st>>>(S.as<float2>(), M + 1, Zn.as<float2>(), M, M, plan.WN);
-            LAUNCHED();
+            if ((rc = plan.run(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), M, q.tmp.as<float2>(), nb, false, 1.0f, st))) return rc;
+            if (!smoothing) {
+                irb::k_spec_fused<true><<<grid1(M / 2 + 1, nb), 256, 0, st>>>(q.Zn.as<float2>(), M, Zd.as<float2>(), 0, q.Zn.as<float2>(), M, M, plan.WN);
+                LAUNCHED();
+            } else {
+                irb::k_spec_split<<<grid1(M + 1, nb), 256, 0, st>>>(q.Zn.as<float2>(), M, q.S.as<float2>(), M + 1, M, 0, plan.WN);
+                LAUNCHED();
+                irb::k_spec_binop<true><<<grid1(M + 1, nb), 256, 0, st>>>(q.S.as<float2>(), M + 1, Sd.as<float2>(), 0, M);
+                LAUNCHED();
+                if ((rc = sm.run(q.S.as<float2>(), M + 1, nb, 3, 1, include_phase, include_amplitude, st))) return rc;
+                irb::k_spec_merge<<<grid1(M, nb), 256, 0, st>>>(q.S.as<float2>(), M + 1, q.Zn.as<float2>(), M, M, plan.WN);
+                LAUNCHED();
+            }
+            if ((rc = plan.run(q.Zn.p, M, -1, q.dy.as<float2>(), M, q.tmp.as<float2>(), nb, true, 1.0f / (float) N, st))) return rc;
         }
-        if ((rc = plan.run(Zn.p, M, -1, dy.as<float2>(), M, tmp.as<float2>(), nb, true, 1.0f / (float) N, st))) return rc;
-        const float* res = dy.as<float>();
+        const float* res = q.dy.as<float>();
         if (!include_phase) {                                                        // ir::shifteroo, fp/convolution.cpp:400
-            irb::k_shifteroo<<<grid1(N, nb), 256, 0, st>>>(dy.as<float>(), dy2.as<float>(), N, N);
+            irb::k_shifteroo<<<grid1(N, nb), 256, 0, st>>>(q.dy.as<float>(), q.dy2.as<float>(), N, N);
             LAUNCHED();
-            res = dy2.as<float>();
+            res = q.dy2.as<float>();
         }
-        if ((rc = tm.end())) return rc;
-        CK(cudaMemcpyAsync(out + (size_t) b0 * N, res, sizeof(float) * (size_t) N * nb, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if ((rc = tm.collect())) return rc;
+        CK(cudaEventRecord(q.t1, st));
+        CK(cudaEventRecord(q.ev_done, st));
+        CK(cudaStreamWaitEvent(sg_out.s, q.ev_done, 0));
+        CK(cudaMemcpyAsync(out + (size_t) b0 * N, res, sizeof(float) * (size_t) N * nb, cudaMemcpyDeviceToHost, sg_out.s));
+        CK(cudaEventRecord(q.ev_out, sg_out.s));
     }
+    CK(cudaStreamSynchronize(sg_out.s));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < std::min(it, 2); ++i) if ((rc = collect(slot[i]))) return rc;
+    irbh::set_last_compute_ms(total_ms);
     return 0;
 }
 
@@ -338,12 +482,10 @@ int irb_averaging_filter(float* spec, int ch, int fft_size, double octave_fracti
     if ((rc = sg.create())) return rc;
     cudaStream_t st = sg.s;
     DevBuf S;
-    SmoothBufs sm;
-    if ((rc = S.alloc(sizeof(float) * (size_t) fft_size * ch, false)) || (rc = sm.alloc(M, ch))) return rc;
+    Smoother sm;
+    if ((rc = S.alloc(sizeof(float) * (size_t) fft_size * ch, false)) || (rc = sm.init(M, ch, octave_fraction, sample_rate, log_avg, st))) return rc;
     CK(cudaMemcpyAsync(S.p, spec, sizeof(float) * (size_t) fft_size * ch, cudaMemcpyHostToDevice, st));
-    if ((rc = averaging_pass(S.as<float2>(), N, ch, M, octave_fraction, sample_rate, log_avg, include_phase, include_amplitude, sm.la.as<float>(), sm.rs.as<float>(),
-                             sm.lo.as<int>(), sm.hi.as<int>(), st)))
-        return rc;
+    if ((rc = sm.run(S.as<float2>(), N, ch, 1, log_avg, include_phase, include_amplitude, st))) return rc;
     CK(cudaMemcpyAsync(spec, S.p, sizeof(float) * (size_t) fft_size * ch, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return 0;

@@ -29,9 +29,16 @@ struct LineArgs {
     int n_lines;                  // lines per batch item (grid.y = batch)
     int in_real_len;              // >= 0: input is real, this many valid floats per batch item, zero beyond
     int tw_M;                     // > 0: multiply output element k of line l by exp(-+2 pi i l k / tw_M)
+    const float2 *tw_hi, *tw_lo;  // that root as tw_hi[idx >> 10] * tw_lo[idx & 1023], idx = l k mod tw_M (tables built in double)
     float scale;                  // applied on store
     const float2* W;              // the 2L roots of unity of the line length
 };
+
+constexpr int kTwLoBits = 10;
+// exp(-2 pi i idx / M) from the two-level table: one complex product of two correctly rounded factors
+__device__ __forceinline__ float2 root_big(const float2* __restrict__ hi, const float2* __restrict__ lo, long long idx) {
+    return cmul(__ldg(hi + (idx >> kTwLoBits)), __ldg(lo + (idx & ((1 << kTwLoBits) - 1))));
+}
 
 template <int L, bool INV>
 static __global__ void __launch_bounds__(kThreads) k_line_fft(const LineArgs a) {
@@ -42,22 +49,36 @@ static __global__ void __launch_bounds__(kThreads) k_line_fft(const LineArgs a) 
     const long long ib = (long long) blockIdx.y * a.in_batch_stride, ob = (long long) blockIdx.y * a.out_batch_stride;
     const bool in_contig = a.in_elem_stride == 1, out_contig = a.out_elem_stride == 1;
 
-    for (int idx = tid; idx < T::C * L; idx += kThreads) {
-        const int c = in_contig ? idx / L : idx % T::C;
-        const int j = in_contig ? idx % L : idx / T::C;
-        const int line = line0 + c;
-        float2 v = make_float2(0.f, 0.f);
-        if (line < a.n_lines) {
-            const long long off = (long long) line * a.in_line_stride + (long long) j * a.in_elem_stride;
-            if (a.in_real_len < 0) v = reinterpret_cast<const float2*>(a.in)[ib + off];
-            else {
-                const float* r = reinterpret_cast<const float*>(a.in) + 2 * ib;
-                const long long e = 2 * off;
-                if (e + 1 < a.in_real_len) v = *reinterpret_cast<const float2*>(r + e);
-                else if (e < a.in_real_len) v.x = r[e];
+    // all of a thread's loads are issued before the first shared-memory store: PER x 8 bytes in flight per thread
+    constexpr int PER = T::C * L / kThreads;
+    {
+        float2 r[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int idx = tid + i * kThreads;
+            const int c = in_contig ? idx / L : idx % T::C;
+            const int j = in_contig ? idx % L : idx / T::C;
+            const int line = line0 + c;
+            float2 v = make_float2(0.f, 0.f);
+            if (line < a.n_lines) {
+                const long long off = (long long) line * a.in_line_stride + (long long) j * a.in_elem_stride;
+                if (a.in_real_len < 0) v = reinterpret_cast<const float2*>(a.in)[ib + off];
+                else {
+                    const float* rp = reinterpret_cast<const float*>(a.in) + 2 * ib;
+                    const long long e = 2 * off;
+                    if (e + 1 < a.in_real_len) v = *reinterpret_cast<const float2*>(rp + e);
+                    else if (e < a.in_real_len) v.x = rp[e];
+                }
             }
+            r[i] = v;
         }
-        s_lines[c * T::PITCH + j] = v;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int idx = tid + i * kThreads;
+            const int c = in_contig ? idx / L : idx % T::C;
+            const int j = in_contig ? idx % L : idx / T::C;
+            s_lines[c * T::PITCH + j] = r[i];
+        }
     }
     bar_compute();
     {
@@ -72,17 +93,17 @@ static __global__ void __launch_bounds__(kThreads) k_line_fft(const LineArgs a) 
             for (int j = 0; j < kPts; ++j) {
                 const int k = t + j * T::TPF;
                 if (a.tw_M > 0) {
-                    double sn, cs;
-                    sincospi(2.0 * (double) ((long long) line * k % a.tw_M) / (double) a.tw_M, &sn, &cs);
-                    const float2 w = make_float2((float) cs, INV ? (float) sn : (float) -sn);
-                    v[j] = cmul(v[j], w);
+                    const float2 w = root_big(a.tw_hi, a.tw_lo, (long long) line * k & (a.tw_M - 1));
+                    v[j] = cmul(v[j], INV ? cconj(w) : w);
                 }
                 srow[k] = v[j];              // each thread rewrites exactly the elements it gathered last
             }
         }
     }
     bar_compute();
-    for (int idx = tid; idx < T::C * L; idx += kThreads) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int idx = tid + i * kThreads;
         const int c = out_contig ? idx / L : idx % T::C;
         const int j = out_contig ? idx % L : idx / T::C;
         const int line = line0 + c;
@@ -170,6 +191,135 @@ static __global__ void k_spec_fused(const float2* Za, long long a_stride, const 
     if (2 * k != M) zo[M - k] = real_merge(Qm, Q, wm, M - k);
 }
 
+// ---- fused middle of the large transform pair (M = M1*M2 > 2048) ----------------------------------------------
+// After the column pass the M-point spectrum of one signal lies as M1 rows of M2 values; row k1 becomes the bins
+// k = k1 + M1*k2 once its M2-point row FFT is done.  The per-bin stage needs the bin pair (k, M-k), which lives in rows
+// k1 and M1-k1, so ONE CTA takes that pair of rows through: forward row FFT -> split into the real signal's spectrum
+// -> multiply / divide by the other operand's spectrum B -> merge back -> inverse row FFT -> inter-pass twiddle of
+// the inverse transform, all in shared memory.  The inverse column pass then finishes.  Per signal this replaces
+// forward row pass + bin kernel + inverse column pass with twiddle (3 x 8M bytes) by 1 x 8M bytes.
+// B is given in the same row layout, already split: Brows[k1*M2 + k2] = B[k1 + M1*k2], Brows[0] = {B[0], B[M]} (both real).
+template <int L> struct PairTile {
+    static constexpr int TPF = L / kPts;                                   // threads per row
+    static constexpr int G = kThreads / TPF;                               // rows transformed concurrently
+    static constexpr int NP = G >= 2 ? G / 2 : 1;                          // row pairs per CTA
+    static constexpr int PITCH = L + 2;
+    static constexpr size_t SMEM = sizeof(float2) * (size_t) (2 * NP) * PITCH;
+};
+struct PairArgs {
+    float2* Z;                   // [batch][M1][M2] rows, in place
+    long long z_batch_stride;
+    const float2* Brows;         // [nb][M1*M2]
+    long long b_batch_stride;    // 0: one B for the whole batch
+    int M1;                      // rows (M2 = L is the template parameter)
+    const float2 *W;             // the 2L roots (row transforms)
+    const float2 *Nhi, *Nlo;     // two-level table of the 2M-th roots (split / merge)
+    const float2 *Mhi, *Mlo;     // two-level table of the M-th roots (inverse inter-pass twiddle)
+};
+// the bin pair (k, M-k) of one signal against B: writes Z'[k] and Z'[M-k] (what the inverse complex FFT takes)
+template <bool DIV>
+__device__ __forceinline__ void pair_op(float2& zk, float2& zm, float2 bk, float2 bm, float2 w, bool self) {
+    const float2 wm = make_float2(-w.x, w.y);                              // root of M-k = -conj(root of k)
+    const float2 A = real_split(zk, zm, w, 1), Am = real_split(zm, zk, wm, 1);
+    const float2 Q = DIV ? bin_div(A, bk) : bin_mul(A, bk), Qm = DIV ? bin_div(Am, bm) : bin_mul(Am, bm);
+    zk = real_merge(Q, Qm, w, 1);
+    if (!self) zm = real_merge(Qm, Q, wm, 1);
+}
+template <int L, bool DIV>
+static __global__ void __launch_bounds__(kThreads) k_rowpair(const PairArgs a) {
+    using T = PairTile<L>;
+    extern __shared__ __align__(16) float2 s_lines[];
+    const int tid = threadIdx.x, M1 = a.M1;
+    const long long M = (long long) M1 * L;
+    float2* Z = a.Z + blockIdx.y * a.z_batch_stride;
+    const float2* Bq = a.Brows + blockIdx.y * a.b_batch_stride;
+    const int p0 = blockIdx.x * T::NP;                                    // pairs p0 .. p0+NP-1 of 0 .. M1/2
+    // line 2i = row p, line 2i+1 = row M1-p (unused when the row pairs with itself: p == 0 or p == M1/2)
+    auto row_of = [&](int line) { const int p = p0 + line / 2; return (line & 1) ? M1 - p : p; };
+    auto line_live = [&](int line) { const int p = p0 + line / 2; return p <= M1 / 2 && !((line & 1) && (p == 0 || 2 * p == M1)); };
+    constexpr int PER = 2 * T::NP * L / kThreads;                          // = 8 for every L
+    {
+        float2 r[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int idx = tid + i * kThreads, line = idx / L, j = idx % L;
+            r[i] = line_live(line) ? Z[(long long) row_of(line) * L + j] : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int idx = tid + i * kThreads, line = idx / L, j = idx % L;
+            s_lines[line * T::PITCH + j] = r[i];
+        }
+    }
+    bar_compute();
+    const int t = tid % T::TPF;
+    for (int line = tid / T::TPF; line < 2 * T::NP; line += T::G) {       // forward row transforms
+        float2* srow = s_lines + line * T::PITCH;
+        float2 v[kPts];
+        fft_gather<L>(v, t, srow);
+        fft_run<L, false>(v, t, srow, a.W);
+#pragma unroll
+        for (int j = 0; j < kPts; ++j) srow[t + j * T::TPF] = v[j];
+    }
+    bar_compute();
+    for (int idx = tid; idx < T::NP * L; idx += kThreads) {               // the bin pairs
+        const int i = idx / L, k2 = idx % L, p = p0 + i;
+        if (p > M1 / 2) continue;
+        float2* la = s_lines + (2 * i) * T::PITCH;
+        const bool selfrow = p == 0 || 2 * p == M1;
+        float2* lb = selfrow ? la : la + T::PITCH;
+        const int rb = selfrow ? p : M1 - p;
+        const int pk2 = p == 0 ? (L - k2) & (L - 1) : L - 1 - k2;        // element of M-k in its row
+        if (selfrow && pk2 < k2) continue;                                // each pair once
+        const long long k = p + (long long) M1 * k2;
+        if (k == 0) {
+            const float2 z0 = la[0], b0 = Bq[0];
+            const float2 a0 = make_float2(z0.x + z0.y, 0.f), aM = make_float2(z0.x - z0.y, 0.f);
+            const float2 bb0 = make_float2(b0.x, 0.f), bbM = make_float2(b0.y, 0.f);
+            const float2 q0 = DIV ? bin_div(a0, bb0) : bin_mul(a0, bb0), qM = DIV ? bin_div(aM, bbM) : bin_mul(aM, bbM);
+            la[0] = make_float2(q0.x + qM.x, q0.x - qM.x);
+            continue;
+        }
+        const float2 w = root_big(a.Nhi, a.Nlo, k);
+        const bool self = selfrow && pk2 == k2;                            // 2k == M
+        float2 zk = la[k2], zm = lb[pk2];
+        pair_op<DIV>(zk, zm, __ldg(Bq + (long long) p * L + k2), __ldg(Bq + (long long) rb * L + pk2), w, self);
+        la[k2] = zk;
+        if (!self) lb[pk2] = zm;
+    }
+    bar_compute();
+    for (int line = tid / T::TPF; line < 2 * T::NP; line += T::G) {       // inverse row transforms + twiddle
+        float2* srow = s_lines + line * T::PITCH;
+        float2 v[kPts];
+        fft_gather<L>(v, t, srow);
+        fft_run<L, true>(v, t, srow, a.W);
+        const int row = line_live(line) ? row_of(line) : 0;
+#pragma unroll
+        for (int j = 0; j < kPts; ++j) {
+            const int n2 = t + j * T::TPF;
+            srow[n2] = cmul(v[j], cconj(root_big(a.Mhi, a.Mlo, ((long long) row * n2) & (M - 1))));
+        }
+    }
+    bar_compute();
+    for (int idx = tid; idx < 2 * T::NP * L; idx += kThreads) {
+        const int line = idx / L, j = idx % L;
+        if (line_live(line)) Z[(long long) row_of(line) * L + j] = s_lines[line * T::PITCH + j];
+    }
+}
+// the other operand: Zrows (row layout after its own row FFTs, same place) -> Brows, the split spectrum in row layout
+static __global__ void k_split_rows(const float2* Zrows, float2* Brows, int M1, int L, const float2* Nhi, const float2* Nlo) {
+    const long long M = (long long) M1 * L;
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const float2* z = Zrows + blockIdx.y * M;
+    float2* b = Brows + blockIdx.y * M;
+    const int k1 = (int) (i / L), k2 = (int) (i % L);
+    const long long k = k1 + (long long) M1 * k2;
+    if (k == 0) { b[0] = make_float2(z[0].x + z[0].y, z[0].x - z[0].y); return; }
+    const int r = k1 == 0 ? 0 : M1 - k1, e = k1 == 0 ? (L - k2) & (L - 1) : L - 1 - k2;
+    b[i] = real_split(z[i], z[(long long) r * L + e], root_big(Nhi, Nlo, k), 1);
+}
+
 // tools::fftTransform(formatAmplPhase = true): bins 0..M -> {amplitude, phase} (fp/tools.cpp:337-342,222-231)
 static __global__ void k_spec_ampl_phase(float2* S, long long s_stride, int M) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,66 +340,114 @@ __device__ __forceinline__ float round_to_zero(float x, float thr) {   // tools:
     if (signbit(x) && x > -thr) x = 0.0f;
     return x;
 }
-// (1) per bin k <= M: la[k] = log(clamp(|S[k]|)) (or the plain amplitude for the linear average) and the window
-// [lo, hi] of the bin, with the reference's double-precision operation order (fp/convolution.cpp:451-458):
-// binFreq = k*freqPerBin; lo = round((binFreq / c) / freqPerBin); hi = round((binFreq * c) / freqPerBin)
-static __global__ void k_avg_prepare(const float2* S, long long s_stride, float* la, long long la_stride, int* lo, int* hi, int M, int log_avg,
-                              double freq_per_bin, double c_side) {
+// (0) once per call: the window [lo, hi] of every bin k <= M with the reference's double-precision operation order
+// (fp/convolution.cpp:451-458): binFreq = k*freqPerBin; lo = round((binFreq / c) / freqPerBin); hi = round((binFreq * c) / freqPerBin)
+static __global__ void k_avg_windows(int* lo, int* hi, int M, double freq_per_bin, double c_side) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > M) return;
-    const float2 v = S[blockIdx.y * s_stride + k];
-    const float ampl = (float) sqrt((double) v.x * (double) v.x + (double) v.y * (double) v.y);     // tools::binAmpl
-    la[blockIdx.y * la_stride + k] = log_avg ? logf(round_1e16(ampl)) : ampl;
-    if (blockIdx.y == 0) {
-        const double f = (double) k * freq_per_bin;
-        lo[k] = (int) round((f / c_side) / freq_per_bin);
-        hi[k] = (int) round((f * c_side) / freq_per_bin);
-    }
+    const double f = (double) k * freq_per_bin;
+    lo[k] = (int) round((f / c_side) / freq_per_bin);
+    hi[k] = (int) round((f * c_side) / freq_per_bin);
 }
-// (2) the running window sum in the reference's exact sequential float order (fp/convolution.cpp:482-505): one warp
-// per spectrum; lane 0 carries the dependent add chain while all lanes stage la[] and the window edges through
-// shared memory in coalesced chunks.  Bins past Nyquist (k > M) hold amplitude 0 -> clamp -> log(1e-16) and
-// count up to bin 2M-1 (the "addBin < fftSize" test).  rs[k] receives the raw running sum.
-static __global__ void __launch_bounds__(32) k_avg_scan(const float* la, long long la_stride, const int* lo, const int* hi, float* rs, long long rs_stride,
-                                                 int M) {
-    constexpr int CH = 1024;
-    __shared__ float s_sub[CH], s_add[CH], s_out[CH];
-    __shared__ int s_lo[CH], s_hi[CH];
+// (1) per bin k <= M: la[k] = log(clamp(|S[k]|)) (or the plain amplitude for the linear average)
+__device__ __forceinline__ float avg_log_ampl(float2 v, int log_avg) {
+    const float ampl = (float) sqrt((double) v.x * (double) v.x + (double) v.y * (double) v.y);     // tools::binAmpl
+    return log_avg ? logf(round_1e16(ampl)) : ampl;
+}
+static __global__ void k_avg_prepare(const float2* S, long long s_stride, float* la, long long la_stride, int M, int log_avg) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > M) return;
+    la[blockIdx.y * la_stride + k] = avg_log_ampl(S[blockIdx.y * s_stride + k], log_avg);
+}
+// (2) The running window sum of the log average is a FIXED sequence of float additions (fp/convolution.cpp:482-505): for
+// bin k = 0, 1, ...: subtract la[b] for b in [lo[k-1], lo[k]), then add la[b] for b in (hi[k-1], hi[k]] (bins past
+// Nyquist, M < b < 2M, hold amplitude 0 -> clamp -> log(1e-16); b >= 2M is skipped, "addBin < fftSize"), then record.
+// The sequence depends on the windows only, so it is laid out ONCE per call as a list of signed bin codes:
+//   ops[j] = b (add la[b]) or ~b (subtract la[b]);  endq[k] = index of the last operation before bin k is recorded.
+static __global__ void k_avg_oplist(const int* lo, const int* hi, int* ops, int* endq, int M) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > M) return;
+    const int l0 = k ? lo[k - 1] : 0, l1 = lo[k], h0 = k ? hi[k - 1] : -1, h1 = hi[k];
+    int j = l0 + h0 + 1;
+    for (int b = l0; b < l1; ++b) ops[j++] = ~b;
+    for (int b = h0 + 1; b <= h1; ++b) ops[j++] = b;
+    endq[k] = l1 + h1;
+}
+// first bin recorded in each chunk of kAvgChunk operations (kstart[nchunks] = M + 1)
+constexpr int kAvgChunk = 2048;
+static __global__ void k_avg_chunk_starts(const int* endq, int* kstart, int M, int nchunks) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > M) return;
+    const int c1 = endq[k] / kAvgChunk, c0 = k ? endq[k - 1] / kAvgChunk : -1;
+    for (int c = c0 + 1; c <= c1; ++c) kstart[c] = k;
+    if (k == M) for (int c = c1 + 1; c <= nchunks; ++c) kstart[c] = M + 1;
+}
+// One CTA per spectrum: lane 0 of warp 0 carries the dependent add chain, nothing else (4 cycles per operation);
+// warps 1..3 gather the operands of the next chunk into shared memory and write the previous chunk's sums back.
+static __global__ void __launch_bounds__(128) k_avg_scan(const float* la, long long la_stride, const int* __restrict__ ops, const int* __restrict__ endq,
+                                                  const int* __restrict__ kstart, int nchunks, int n_ops, float* rs, long long rs_stride, int M) {
+    __shared__ __align__(16) float s_val[2][kAvgChunk], s_sum[2][kAvgChunk];
     const float* a = la + blockIdx.x * la_stride;
     float* out = rs + blockIdx.x * rs_stride;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, ptid = tid - 32;
     const float log_floor = logf(1e-16f);
-    float running = 0.0f;
-    int prevLo = 0, prevHi = -1;
-    int sub_base = 0, add_base = 0;
-    auto stage = [&](float* dst, int base) {
-        __syncwarp();
-        for (int i = lane; i < CH; i += 32) { const int k = base + i; dst[i] = k <= M ? a[k] : log_floor; }
-        __syncwarp();
-    };
-    stage(s_sub, 0);
-    stage(s_add, 0);
-    for (int k0 = 0; k0 <= M; k0 += CH) {
-        __syncwarp();
-        for (int i = lane; i < CH; i += 32) { const int k = k0 + i; s_lo[i] = k <= M ? lo[k] : 0; s_hi[i] = k <= M ? hi[k] : 0; }
-        __syncwarp();
-        const int kend = min(CH, M + 1 - k0);
-        for (int i = 0; i < kend; ++i) {
-            const int l = s_lo[i], h = s_hi[i];
-            for (int b = prevLo; b < l; ++b) {
-                if (b - sub_base >= CH) { sub_base = b; stage(s_sub, sub_base); }
-                if (lane == 0) running -= s_sub[b - sub_base];
+    auto fill = [&](int c) {
+        float* dst = s_val[c & 1];
+        const int j0 = c * kAvgChunk;
+#pragma unroll 8
+        for (int j = ptid; j < kAvgChunk; j += 96) {
+            float v = 0.0f;
+            if (j0 + j < n_ops) {
+                const int code = __ldg(ops + j0 + j);
+                const int b = code < 0 ? ~code : code;
+                v = b <= M ? a[b] : (b < 2 * M ? log_floor : 0.0f);
+                if (code < 0) v = -v;
             }
-            for (int b = prevHi + 1; b <= h; ++b) {
-                if (b - add_base >= CH) { add_base = b; stage(s_add, add_base); }
-                if (b < 2 * M && lane == 0) running += s_add[b - add_base];
-            }
-            if (lane == 0) s_out[i] = running;
-            prevLo = l; prevHi = h;
+            dst[j] = v;
         }
-        __syncwarp();
-        for (int i = lane; i < kend; i += 32) out[k0 + i] = s_out[i];
+    };
+    auto write_back = [&](int c) {
+        const float* src = s_sum[c & 1];
+        const int j0 = c * kAvgChunk;
+        for (int k = kstart[c] + ptid; k < kstart[c + 1]; k += 96) out[k] = src[__ldg(endq + k) - j0];
+    };
+    if (tid >= 32) fill(0);
+    __syncthreads();
+    float running = 0.0f;
+    for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0) {
+            // operands are fetched 32 operations ahead so that the chain never waits for shared memory
+            const float4* v4 = reinterpret_cast<const float4*>(s_val[c & 1]);
+            float4* p4 = reinterpret_cast<float4*>(s_sum[c & 1]);
+            constexpr int D = 8;
+            float4 cur[D], nxt[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) cur[i] = v4[i];
+#pragma unroll 1
+            for (int j = 0; j < kAvgChunk / 4; j += D) {
+                if (j + D < kAvgChunk / 4) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) nxt[i] = v4[j + D + i];
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    float4 p;
+                    running += cur[i].x; p.x = running;
+                    running += cur[i].y; p.y = running;
+                    running += cur[i].z; p.z = running;
+                    running += cur[i].w; p.w = running;
+                    p4[j + i] = p;
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) cur[i] = nxt[i];
+            }
+        } else if (tid >= 32) {
+            if (c + 1 < nchunks) fill(c + 1);
+            if (c >= 1) write_back(c - 1);
+        }
+        __syncthreads();
     }
+    if (tid >= 32) write_back(nchunks - 1);
 }
 // linear average: a fresh ascending sum per bin (fp/convolution.cpp:508-514) -- no sequential dependence
 static __global__ void k_avg_linear_sum(const float* la, long long la_stride, const int* lo, const int* hi, float* rs, long long rs_stride, int M) {
@@ -261,8 +459,9 @@ static __global__ void k_avg_linear_sum(const float* la, long long la_stride, co
     rs[blockIdx.y * rs_stride + k] = sum;
 }
 // (3) new amplitude = exp(sum / window length), bins rebuilt from it and the original phase (fp/convolution.cpp:518-543)
+// next_la != nullptr: also the log amplitudes of the rebuilt bins, i.e. the next pass's step (1)
 static __global__ void k_avg_apply(float2* S, long long s_stride, const float* rs, long long rs_stride, const int* lo, const int* hi, int M, int log_avg,
-                            int include_phase, int include_ampl) {
+                            int include_phase, int include_ampl, float* next_la, long long la_stride) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > M) return;
     float2* s = S + blockIdx.y * s_stride;
@@ -274,7 +473,9 @@ static __global__ void k_avg_apply(float2* S, long long s_stride, const float* r
     float phase = atan2f(im, re);
     if (!include_ampl) ampl = 1.0f;
     if (!include_phase) phase = 0.0f;
-    s[k] = make_float2(ampl * cosf(phase), ampl * sinf(phase));
+    const float2 nv = make_float2(ampl * cosf(phase), ampl * sinf(phase));
+    s[k] = nv;
+    if (next_la) next_la[blockIdx.y * la_stride + k] = avg_log_ampl(nv, log_avg);
 }
 
 // out[i] = in[(i + h1) mod n] : ir::shifteroo (fp/ir.cpp:85-103), h1 = ceil(n/2)
