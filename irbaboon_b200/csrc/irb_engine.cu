@@ -33,23 +33,18 @@ int current_device() { return g_device; }
 thread_local double g_last_compute_ms = 0.0;
 void set_last_compute_ms(double ms) { g_last_compute_ms = ms; }
 
-// twiddle tables, one per (device, M), built in double like the reference FFT's tables
+// FFT tables (irb_fft.cuh: fft_build_table), one per (device, M), built in double like the reference FFT's tables
 int twiddles(int dev, int M, const float2** out) {
     struct Entry { int dev, M; float2* d; };
     static std::mutex mu;
     static std::vector<Entry> tab;
     std::lock_guard<std::mutex> lk(mu);
     for (auto& e : tab) if (e.dev == dev && e.M == M) { *out = e.d; return 0; }
-    const int N = 2 * M;
-    std::vector<float2> h(N);
-    for (int k = 0; k < N; ++k) {
-        const double ang = -2.0 * M_PI * (double) k / (double) N;
-        h[k].x = (float) cos(ang);
-        h[k].y = (float) sin(ang);
-    }
+    std::vector<float2> h((size_t) irb::fft_table_size(M));
+    irb::fft_build_table(M, h.data());          // the N roots, then the per-thread twiddles of every pass (irb_fft.cuh)
     float2* d = nullptr;
-    CK(cudaMalloc(&d, sizeof(float2) * N));
-    CK(cudaMemcpy(d, h.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d, sizeof(float2) * h.size()));
+    CK(cudaMemcpy(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice));
     tab.push_back({dev, M, d});
     *out = d;
     return 0;

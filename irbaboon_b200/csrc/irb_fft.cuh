@@ -75,7 +75,11 @@ template <bool INV, int S> IRB_HD void dft8(float2* a) {
     t = a[3 * S]; a[3 * S] = a[6 * S]; a[6 * S] = t;
 }
 
-// W is the table of N = 2M roots, W[k] = exp(-2 pi i k / N); exp(-2 pi i j / M) = W[2j].
+// The table W of an M-point transform: first the N = 2M roots W[k] = exp(-2 pi i k / N) (split / merge of the real
+// transform), then, for every pass after the first, the twiddles of that pass laid out PER THREAD: entry
+// [slot*TPF + t], slot = b*(R-1) + r-1, is the factor of register b + r*NB of thread t.  Consecutive threads read
+// consecutive entries, so a warp's twiddle load is one contiguous 256-byte line instead of up to 28 scattered ones
+// (the scattered lookups into the root table were what kept the block FFT kernels busy: ncu, profiles/).
 template <bool INV> IRB_HD float2 root(const float2* __restrict__ W, int k) {
 #if defined(__CUDA_ARCH__)
     float2 w = __ldg(W + k);
@@ -84,27 +88,61 @@ template <bool INV> IRB_HD float2 root(const float2* __restrict__ W, int k) {
 #endif
     return INV ? cconj(w) : w;
 }
+IRB_CX int fft_pass_slots() { return kPts - 1; }                 // entries per thread and pass (radix 8: 7; 4: 2*3; 2: 4*1)
+IRB_CX int fft_num_passes(int M) { int n = 0; for (int rem = M; rem > 1; rem /= (rem >= 8 ? 8 : rem)) ++n; return n; }
+IRB_CX int fft_table_size(int M) { return 2 * M + (fft_num_passes(M) - 1) * fft_pass_slots() * (M / kPts); }
+// host: fill W[fft_table_size(M)], every value computed in double and rounded once (as the reference FFT's tables are)
+inline void fft_build_table(int M, float2* W) {
+    const double two_pi = 6.283185307179586476925286766559;
+    const int N = 2 * M, TPF = M / kPts;
+    for (int k = 0; k < N; ++k) {
+        const double a = -two_pi * (double) k / (double) N;
+        W[k].x = (float) cos(a); W[k].y = (float) sin(a);
+    }
+    int PS = 1;
+    for (int pass = 0; PS < M; ++pass) {
+        const int R = pass_radix(M, pass), NB = kPts / R;
+        if (pass > 0) {
+            float2* T = W + N + (pass - 1) * fft_pass_slots() * TPF;
+            for (int b = 0; b < NB; ++b)
+                for (int r = 1; r < R; ++r)
+                    for (int t = 0; t < TPF; ++t) {
+                        const int k = (t + b * TPF) & (PS - 1);
+                        const double a = -two_pi * (double) r * (double) k / (double) (PS * R);
+                        float2& w = T[(b * (R - 1) + r - 1) * TPF + t];
+                        w.x = (float) cos(a); w.y = (float) sin(a);
+                    }
+        }
+        PS *= R;
+    }
+}
 
 // One Stockham pass on the 8 registers of thread t (of M/8 per row).  The thread holds v[j] = x[t + j*M/8].
 // With NB = 8/R butterflies per thread, butterfly b works on v[b + r*NB], r < R; its index is i = t + b*M/8,
 // k = i mod PS, and after the pass its r-th output is element (i-k)*R + k + r*PS of the next array.
-template <int M, int R, int PS, bool INV>
+template <int M, int R, int PS, bool INV, int PASS>
 IRB_HD void fft_pass(float2* v, int t, const float2* __restrict__ W) {
     constexpr int NB = kPts / R;
     constexpr int TPF = M / kPts;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         if (PS > 1) {
-            const int k = (t + b * TPF) & (PS - 1);
-            const int step = 2 * k * (M / (PS * R));          // index into the N-root table
+            const float2* T = W + 2 * M + (PASS - 1) * fft_pass_slots() * TPF + t;
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[b + r * NB] = cmul(v[b + r * NB], root<INV>(W, r * step));
+            for (int r = 1; r < R; ++r) v[b + r * NB] = cmul(v[b + r * NB], root<INV>(T, (b * (R - 1) + r - 1) * TPF));
         }
         if (R == 8) dft8<INV, NB>(v + b);
         else if (R == 4) dft4<INV, NB>(v + b);
         else dft2<INV, NB>(v + b);
     }
 }
+// Bank swizzle of the exchange buffer.  A pass scatters with stride R (pass 0: element 8t + r), which on 8-byte elements
+// puts the 16 threads of a half-warp on 2 (pass 0) or 8 (pass 1) of the 16 bank pairs.  XOR-ing the low four index bits
+// with bits 4..6 and bit 6 of the index keeps aligned groups of 16 together (so the gather of 16 consecutive elements
+// stays conflict-free) and spreads every scatter of every pass over all 16 bank pairs (checked exhaustively for
+// M = 128 .. 2048 by tests/test_emu_fft.py::test_exchange_is_bank_conflict_free).
+IRB_HD int fft_sw(int e) { return e ^ (((e >> 4) & 7) | (((e >> 6) & 1) << 3)); }
+
 template <int M, int R, int PS>
 IRB_HD void fft_scatter(const float2* v, int t, float2* srow) {
     constexpr int NB = kPts / R;
@@ -115,13 +153,19 @@ IRB_HD void fft_scatter(const float2* v, int t, float2* srow) {
         const int k = i & (PS - 1);
         const int base = (i - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) srow[base + r * PS] = v[b + r * NB];
+        for (int r = 0; r < R; ++r) srow[fft_sw(base + r * PS)] = v[b + r * NB];
     }
 }
+// natural-order row -> registers (the layout a caller stages), and the same from the swizzled exchange buffer
 template <int M>
 IRB_HD void fft_gather(float2* v, int t, const float2* srow) {
 #pragma unroll
     for (int j = 0; j < kPts; ++j) v[j] = srow[t + j * (M / kPts)];
+}
+template <int M>
+IRB_HD void fft_gather_sw(float2* v, int t, const float2* srow) {
+#pragma unroll
+    for (int j = 0; j < kPts; ++j) v[j] = srow[fft_sw(t + j * (M / kPts))];
 }
 
 // ---- real <-> packed-half-complex split / merge ---------------------------------------------------

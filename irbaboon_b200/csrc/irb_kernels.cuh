@@ -76,12 +76,12 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
 template <int M, bool INV, int PASS = 0, int PS = 1>
 __device__ __forceinline__ void fft_run(float2 (&v)[kPts], int t, float2* srow, const float2* __restrict__ W) {
     constexpr int R = pass_radix(M, PASS);
-    fft_pass<M, R, PS, INV>(v, t, W);
+    fft_pass<M, R, PS, INV, PASS>(v, t, W);
     if constexpr (PS * R < M) {
         bar_compute();                       // every earlier read of the tile has completed
         fft_scatter<M, R, PS>(v, t, srow);
         bar_compute();
-        fft_gather<M>(v, t, srow);
+        fft_gather_sw<M>(v, t, srow);
         fft_run<M, INV, PASS + 1, PS * R>(v, t, srow, W);
     }
 }

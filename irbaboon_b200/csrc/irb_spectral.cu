@@ -46,24 +46,24 @@ int launch_line(int L, bool inv, const irb::LineArgs& a, int batch, cudaStream_t
 #undef IRB_LINE_CASE
 }
 
-template <int L, bool DIV>
+template <int L>
 int launch_pair_t(const irb::PairArgs& a, int batch, cudaStream_t st) {
     using T = irb::PairTile<L>;
     static thread_local int configured_dev = -1;
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        CK(cudaFuncSetAttribute(irb::k_rowpair<L, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T::SMEM));
+        CK(cudaFuncSetAttribute(irb::k_rowpair<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) T::SMEM));
         configured_dev = dev;
     }
     dim3 grid((a.M1 / 2 + 1 + T::NP - 1) / T::NP, batch);
-    irb::k_rowpair<L, DIV><<<grid, irb::kThreads, T::SMEM, st>>>(a);
+    irb::k_rowpair<L><<<grid, irb::kThreads, T::SMEM, st>>>(a);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
 }
-int launch_pair(int L, bool div, const irb::PairArgs& a, int batch, cudaStream_t st) {
-#define IRB_PAIR_CASE(LL) case LL: return div ? launch_pair_t<LL, true>(a, batch, st) : launch_pair_t<LL, false>(a, batch, st);
+int launch_pair(int L, const irb::PairArgs& a, int batch, cudaStream_t st) {
+#define IRB_PAIR_CASE(LL) case LL: return launch_pair_t<LL>(a, batch, st);
     switch (L) {
         IRB_PAIR_CASE(64) IRB_PAIR_CASE(128) IRB_PAIR_CASE(256) IRB_PAIR_CASE(512) IRB_PAIR_CASE(1024)
         default: return fail(IRB_ERR_ARG, "unsupported row length %d", L);
@@ -135,24 +135,25 @@ struct Plan {
         return launch_line(M1, false, a, batch, st);
     }
     // row transforms in place (row k1 then holds the bins k1 + M1*k2), then the split spectrum of a real signal in row layout
-    int rows_to_split_spectrum(float2* rows, float2* brows, int batch, cudaStream_t st) const {
+    // (reciprocal: 1/B, for a division carried out as a multiplication)
+    int rows_to_split_spectrum(float2* rows, float2* brows, int batch, bool reciprocal, cudaStream_t st) const {
         irb::LineArgs a{};
         a.in = rows; a.out = rows; a.in_elem_stride = 1; a.in_line_stride = M2; a.in_batch_stride = M;
         a.out_elem_stride = 1; a.out_line_stride = M2; a.out_batch_stride = M;
         a.n_lines = M1; a.in_real_len = -1; a.tw_M = 0; a.scale = 1.0f; a.W = W2;
         int rc = launch_line(M2, false, a, batch, st);
         if (rc) return rc;
-        irb::k_split_rows<<<dim3((unsigned) ((M + 255) / 256), (unsigned) batch), 256, 0, st>>>(rows, brows, M1, M2, Nhi, Nlo);
+        irb::k_split_rows<<<dim3((unsigned) ((M + 255) / 256), (unsigned) batch), 256, 0, st>>>(rows, brows, M1, M2, Nhi, Nlo, reciprocal ? 1 : 0);
         g_launches++;
         CK(cudaGetLastError());
         return 0;
     }
-    // rows of `batch` signals: forward row FFT, per-bin multiply / divide by brows, inverse row FFT + twiddle, in place
-    int rows_binop(float2* rows, const float2* brows, long long b_stride, bool div, int batch, cudaStream_t st) const {
+    // rows of `batch` signals: forward row FFT, per-bin multiply by brows, inverse row FFT + twiddle, in place
+    int rows_binop(float2* rows, const float2* brows, long long b_stride, int batch, cudaStream_t st) const {
         irb::PairArgs a{};
         a.Z = rows; a.z_batch_stride = M; a.Brows = brows; a.b_batch_stride = b_stride; a.M1 = M1; a.W = W2;
         a.Nhi = Nhi; a.Nlo = Nlo; a.Mhi = Thi; a.Mlo = Tlo;
-        return launch_pair(M2, div, a, batch, st);
+        return launch_pair(M2, a, batch, st);
     }
     // column pass of the inverse transform: rows -> out (natural order), scaled
     int cols_inv(const float2* rows, float2* out, long long out_stride, int batch, float scale, cudaStream_t st) const {
@@ -269,8 +270,8 @@ int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h
     if (plan.big()) {
         // column passes, then one fused kernel per row pair: row FFT, bins of the audio times bins of its IR, inverse row FFT
         if ((rc = plan.cols_fwd(dx.p, lxe / 2, len_x, Zx.as<float2>(), ch_x, st)) || (rc = plan.cols_fwd(hsrc, lhe / 2, len_h, Zh.as<float2>(), n_ir, st)) ||
-            (rc = plan.rows_to_split_spectrum(Zh.as<float2>(), tmp.as<float2>(), n_ir, st)) ||
-            (rc = plan.rows_binop(Zx.as<float2>(), tmp.as<float2>(), n_ir == 2 ? M : 0, false, ch_x, st)) ||
+            (rc = plan.rows_to_split_spectrum(Zh.as<float2>(), tmp.as<float2>(), n_ir, false, st)) ||
+            (rc = plan.rows_binop(Zx.as<float2>(), tmp.as<float2>(), n_ir == 2 ? M : 0, ch_x, st)) ||
             (rc = plan.cols_inv(Zx.as<float2>(), dy.as<float2>(), M, ch_x, 1.0f / (float) N, st)))
             return rc;
     } else {
@@ -338,7 +339,7 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
     // the denominator's spectrum, once
     CK(cudaMemcpyAsync(dd.p, den, sizeof(float) * len_den, cudaMemcpyHostToDevice, st));
     if (fused) {
-        if ((rc = plan.cols_fwd(dd.p, lde / 2, len_den, Zd.as<float2>(), 1, st)) || (rc = plan.rows_to_split_spectrum(Zd.as<float2>(), Bd.as<float2>(), 1, st))) return rc;
+        if ((rc = plan.cols_fwd(dd.p, lde / 2, len_den, Zd.as<float2>(), 1, st)) || (rc = plan.rows_to_split_spectrum(Zd.as<float2>(), Bd.as<float2>(), 1, true, st))) return rc;
     } else {
         if ((rc = plan.run(dd.p, lde / 2, len_den, Zd.as<float2>(), M, dtmp.as<float2>(), 1, false, 1.0f, st))) return rc;
         if (smoothing) {
@@ -368,7 +369,7 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
         if (it >= 2) CK(cudaStreamWaitEvent(st, q.ev_out, 0));                       // download of it-2 has drained q.dy
         CK(cudaEventRecord(q.t0, st));
         if (fused) {
-            if ((rc = plan.cols_fwd(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), nb, st)) || (rc = plan.rows_binop(q.Zn.as<float2>(), Bd.as<float2>(), 0, true, nb, st)) ||
+            if ((rc = plan.cols_fwd(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), nb, st)) || (rc = plan.rows_binop(q.Zn.as<float2>(), Bd.as<float2>(), 0, nb, st)) ||
                 (rc = plan.cols_inv(q.Zn.as<float2>(), q.dy.as<float2>(), M, nb, 1.0f / (float) N, st)))
                 return rc;
         } else {

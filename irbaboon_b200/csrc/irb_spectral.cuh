@@ -41,7 +41,7 @@ __device__ __forceinline__ float2 root_big(const float2* __restrict__ hi, const 
 }
 
 template <int L, bool INV>
-static __global__ void __launch_bounds__(kThreads) k_line_fft(const LineArgs a) {
+static __global__ void __launch_bounds__(kThreads, L >= 1024 ? 2 : 3) k_line_fft(const LineArgs a) {
     using T = LineTile<L>;
     extern __shared__ __align__(16) float2 s_lines[];
     const int tid = threadIdx.x;
@@ -89,11 +89,15 @@ static __global__ void __launch_bounds__(kThreads) k_line_fft(const LineArgs a) 
             fft_gather<L>(v, t, srow);
             fft_run<L, INV>(v, t, srow, a.W);
             const int line = line0 + c;
+            float2 tw_base = make_float2(1.f, 0.f);
+            if (a.tw_M > 0) tw_base = root_big(a.tw_hi, a.tw_lo, ((long long) line * t) & (a.tw_M - 1));
 #pragma unroll
             for (int j = 0; j < kPts; ++j) {
                 const int k = t + j * T::TPF;
                 if (a.tw_M > 0) {
-                    const float2 w = root_big(a.tw_hi, a.tw_lo, (long long) line * k & (a.tw_M - 1));
+                    // root(line*k), k = t + j*TPF, as root(line*t) * root(line*TPF*j): the second factor is the same for
+                    // the whole line, so a warp reads one table line instead of 32 scattered ones
+                    const float2 w = cmul(tw_base, root_big(a.tw_hi, a.tw_lo, ((long long) line * T::TPF * j) & (a.tw_M - 1)));
                     v[j] = cmul(v[j], INV ? cconj(w) : w);
                 }
                 srow[k] = v[j];              // each thread rewrites exactly the elements it gathered last
@@ -216,98 +220,80 @@ struct PairArgs {
     const float2 *Nhi, *Nlo;     // two-level table of the 2M-th roots (split / merge)
     const float2 *Mhi, *Mlo;     // two-level table of the M-th roots (inverse inter-pass twiddle)
 };
-// the bin pair (k, M-k) of one signal against B: writes Z'[k] and Z'[M-k] (what the inverse complex FFT takes)
-template <bool DIV>
-__device__ __forceinline__ void pair_op(float2& zk, float2& zm, float2 bk, float2 bm, float2 w, bool self) {
+// Z'[k] of the bin pair (k, M-k): split both bins of the real signal's spectrum, multiply by B, merge back.
+// Division is multiplication by the reciprocal spectrum that k_split_rows prepares once for the whole batch.
+__device__ __forceinline__ float2 pair_op(float2 zk, float2 zm, float2 bk, float2 bm, float2 w) {
     const float2 wm = make_float2(-w.x, w.y);                              // root of M-k = -conj(root of k)
     const float2 A = real_split(zk, zm, w, 1), Am = real_split(zm, zk, wm, 1);
-    const float2 Q = DIV ? bin_div(A, bk) : bin_mul(A, bk), Qm = DIV ? bin_div(Am, bm) : bin_mul(Am, bm);
-    zk = real_merge(Q, Qm, w, 1);
-    if (!self) zm = real_merge(Qm, Q, wm, 1);
+    return real_merge(bin_mul(A, bk), bin_mul(Am, bm), w, 1);
 }
-template <int L, bool DIV>
-static __global__ void __launch_bounds__(kThreads) k_rowpair(const PairArgs a) {
+// Every thread owns 8 values of ONE row from the global load to the global store (FFT layout: k2 = t + j*L/8).  The only
+// traffic through shared memory besides the exchanges of the two transforms is one natural-order copy of the
+// forward result, from which a thread reads the partners Z[M-k] of its own 8 bins; both owners of a pair evaluate
+// the pair, each keeping its own half, which costs arithmetic but no second exchange.
+template <int L>
+static __global__ void __launch_bounds__(kThreads, 3) k_rowpair(const PairArgs a) {
     using T = PairTile<L>;
     extern __shared__ __align__(16) float2 s_lines[];
     const int tid = threadIdx.x, M1 = a.M1;
     const long long M = (long long) M1 * L;
     float2* Z = a.Z + blockIdx.y * a.z_batch_stride;
     const float2* Bq = a.Brows + blockIdx.y * a.b_batch_stride;
-    const int p0 = blockIdx.x * T::NP;                                    // pairs p0 .. p0+NP-1 of 0 .. M1/2
-    // line 2i = row p, line 2i+1 = row M1-p (unused when the row pairs with itself: p == 0 or p == M1/2)
-    auto row_of = [&](int line) { const int p = p0 + line / 2; return (line & 1) ? M1 - p : p; };
-    auto line_live = [&](int line) { const int p = p0 + line / 2; return p <= M1 / 2 && !((line & 1) && (p == 0 || 2 * p == M1)); };
-    constexpr int PER = 2 * T::NP * L / kThreads;                          // = 8 for every L
-    {
-        float2 r[PER];
+    // line 2i = row p, line 2i+1 = row M1-p, p = blockIdx.x*NP + i in 0 .. M1/2; rows 0 and M1/2 pair with themselves
+    const int line = tid / T::TPF, t = tid % T::TPF;
+    const int p = blockIdx.x * T::NP + line / 2;
+    const bool selfrow = p == 0 || 2 * p == M1;
+    const bool live = line < 2 * T::NP && p <= M1 / 2 && !((line & 1) && selfrow);
+    const int row = live ? ((line & 1) ? M1 - p : p) : 0;
+    const int prow = selfrow ? row : M1 - row;                            // the row holding the partners
+    float2* srow = s_lines + line * T::PITCH;
+    const float2* spart = selfrow ? srow : s_lines + (line ^ 1) * T::PITCH;
+    float2* zrow = Z + (long long) row * L;
+    float2 v[kPts];
 #pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int idx = tid + i * kThreads, line = idx / L, j = idx % L;
-            r[i] = line_live(line) ? Z[(long long) row_of(line) * L + j] : make_float2(0.f, 0.f);
-        }
+    for (int j = 0; j < kPts; ++j) v[j] = live ? zrow[t + j * T::TPF] : make_float2(0.f, 0.f);
+    fft_run<L, false>(v, t, srow, a.W);                                   // forward row transform: v[j] = Z[row + M1*(t + j*TPF)]
+    bar_compute();
 #pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int idx = tid + i * kThreads, line = idx / L, j = idx % L;
-            s_lines[line * T::PITCH + j] = r[i];
-        }
-    }
+    for (int j = 0; j < kPts; ++j) srow[t + j * T::TPF] = v[j];
     bar_compute();
-    const int t = tid % T::TPF;
-    for (int line = tid / T::TPF; line < 2 * T::NP; line += T::G) {       // forward row transforms
-        float2* srow = s_lines + line * T::PITCH;
-        float2 v[kPts];
-        fft_gather<L>(v, t, srow);
-        fft_run<L, false>(v, t, srow, a.W);
-#pragma unroll
-        for (int j = 0; j < kPts; ++j) srow[t + j * T::TPF] = v[j];
-    }
-    bar_compute();
-    for (int idx = tid; idx < T::NP * L; idx += kThreads) {               // the bin pairs
-        const int i = idx / L, k2 = idx % L, p = p0 + i;
-        if (p > M1 / 2) continue;
-        float2* la = s_lines + (2 * i) * T::PITCH;
-        const bool selfrow = p == 0 || 2 * p == M1;
-        float2* lb = selfrow ? la : la + T::PITCH;
-        const int rb = selfrow ? p : M1 - p;
-        const int pk2 = p == 0 ? (L - k2) & (L - 1) : L - 1 - k2;        // element of M-k in its row
-        if (selfrow && pk2 < k2) continue;                                // each pair once
-        const long long k = p + (long long) M1 * k2;
-        if (k == 0) {
-            const float2 z0 = la[0], b0 = Bq[0];
-            const float2 a0 = make_float2(z0.x + z0.y, 0.f), aM = make_float2(z0.x - z0.y, 0.f);
-            const float2 bb0 = make_float2(b0.x, 0.f), bbM = make_float2(b0.y, 0.f);
-            const float2 q0 = DIV ? bin_div(a0, bb0) : bin_mul(a0, bb0), qM = DIV ? bin_div(aM, bbM) : bin_mul(aM, bbM);
-            la[0] = make_float2(q0.x + qM.x, q0.x - qM.x);
-            continue;
-        }
-        const float2 w = root_big(a.Nhi, a.Nlo, k);
-        const bool self = selfrow && pk2 == k2;                            // 2k == M
-        float2 zk = la[k2], zm = lb[pk2];
-        pair_op<DIV>(zk, zm, __ldg(Bq + (long long) p * L + k2), __ldg(Bq + (long long) rb * L + pk2), w, self);
-        la[k2] = zk;
-        if (!self) lb[pk2] = zm;
-    }
-    bar_compute();
-    for (int line = tid / T::TPF; line < 2 * T::NP; line += T::G) {       // inverse row transforms + twiddle
-        float2* srow = s_lines + line * T::PITCH;
-        float2 v[kPts];
-        fft_gather<L>(v, t, srow);
-        fft_run<L, true>(v, t, srow, a.W);
-        const int row = line_live(line) ? row_of(line) : 0;
+    if (live) {
 #pragma unroll
         for (int j = 0; j < kPts; ++j) {
-            const int n2 = t + j * T::TPF;
-            srow[n2] = cmul(v[j], cconj(root_big(a.Mhi, a.Mlo, ((long long) row * n2) & (M - 1))));
+            const int k2 = t + j * T::TPF;
+            const int pk2 = row == 0 ? (L - k2) & (L - 1) : L - 1 - k2;      // element of M-k in its row
+            const long long k = row + (long long) M1 * k2;
+            if (k == 0) {
+                const float2 z0 = v[j], b0 = __ldg(Bq);
+                const float2 a0 = make_float2(z0.x + z0.y, 0.f), aM = make_float2(z0.x - z0.y, 0.f);
+                const float2 bb0 = make_float2(b0.x, 0.f), bbM = make_float2(b0.y, 0.f);
+                const float2 q0 = bin_mul(a0, bb0), qM = bin_mul(aM, bbM);
+                v[j] = make_float2(q0.x + qM.x, q0.x - qM.x);
+            } else {
+                v[j] = pair_op(v[j], spart[pk2], __ldg(Bq + (long long) row * L + k2), __ldg(Bq + (long long) prow * L + pk2), root_big(a.Nhi, a.Nlo, k));
+            }
         }
     }
-    bar_compute();
-    for (int idx = tid; idx < 2 * T::NP * L; idx += kThreads) {
-        const int line = idx / L, j = idx % L;
-        if (line_live(line)) Z[(long long) row_of(line) * L + j] = s_lines[line * T::PITCH + j];
+    fft_run<L, true>(v, t, srow, a.W);                                    // its first barrier orders the partner reads before the scatter
+    if (live) {
+        // inter-pass twiddle conj(root_M(row*n2)), n2 = t + j*TPF, as root(row*t) * root(row*TPF*j) (one table line per warp)
+        const float2 tw_base = root_big(a.Mhi, a.Mlo, ((long long) row * t) & (M - 1));
+#pragma unroll
+        for (int j = 0; j < kPts; ++j) {
+            const float2 w = cmul(tw_base, root_big(a.Mhi, a.Mlo, ((long long) row * T::TPF * j) & (M - 1)));
+            zrow[t + j * T::TPF] = cmul(v[j], cconj(w));
+        }
     }
 }
 // the other operand: Zrows (row layout after its own row FFTs, same place) -> Brows, the split spectrum in row layout
-static __global__ void k_split_rows(const float2* Zrows, float2* Brows, int M1, int L, const float2* Nhi, const float2* Nlo) {
+// reciprocal: Brows holds 1/B instead, with the reference's rule for an all-zero bin (tools::complexDivCartesian,
+// fp/tools.cpp:72-76: the numerator stays as it is) expressed as the factor 1
+__device__ __forceinline__ float2 bin_recip(float2 b) {
+    if (b.x == 0.0f && b.y == 0.0f) return make_float2(1.0f, 0.0f);
+    const float den = b.x * b.x + b.y * b.y;
+    return make_float2(b.x / den, -b.y / den);
+}
+static __global__ void k_split_rows(const float2* Zrows, float2* Brows, int M1, int L, const float2* Nhi, const float2* Nlo, int reciprocal) {
     const long long M = (long long) M1 * L;
     const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
@@ -315,9 +301,15 @@ static __global__ void k_split_rows(const float2* Zrows, float2* Brows, int M1, 
     float2* b = Brows + blockIdx.y * M;
     const int k1 = (int) (i / L), k2 = (int) (i % L);
     const long long k = k1 + (long long) M1 * k2;
-    if (k == 0) { b[0] = make_float2(z[0].x + z[0].y, z[0].x - z[0].y); return; }
+    if (k == 0) {
+        float b0 = z[0].x + z[0].y, bM = z[0].x - z[0].y;
+        if (reciprocal) { b0 = b0 == 0.0f ? 1.0f : 1.0f / b0; bM = bM == 0.0f ? 1.0f : 1.0f / bM; }
+        b[0] = make_float2(b0, bM);
+        return;
+    }
     const int r = k1 == 0 ? 0 : M1 - k1, e = k1 == 0 ? (L - k2) & (L - 1) : L - 1 - k2;
-    b[i] = real_split(z[i], z[(long long) r * L + e], root_big(Nhi, Nlo, k), 1);
+    const float2 v = real_split(z[i], z[(long long) r * L + e], root_big(Nhi, Nlo, k), 1);
+    b[i] = reciprocal ? bin_recip(v) : v;
 }
 
 // tools::fftTransform(formatAmplPhase = true): bins 0..M -> {amplitude, phase} (fp/tools.cpp:337-342,222-231)

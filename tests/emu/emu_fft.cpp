@@ -12,10 +12,10 @@ template <int M, bool INV, int PASS = 0, int PS = 1>
 static void emu_run(std::vector<float2>& regs, float2* srow, const float2* W) {
     constexpr int TPF = M / kPts;
     constexpr int R = pass_radix(M, PASS);
-    for (int t = 0; t < TPF; ++t) fft_pass<M, R, PS, INV>(&regs[t * kPts], t, W);
+    for (int t = 0; t < TPF; ++t) fft_pass<M, R, PS, INV, PASS>(&regs[t * kPts], t, W);
     if constexpr (PS * R < M) {
         for (int t = 0; t < TPF; ++t) fft_scatter<M, R, PS>(&regs[t * kPts], t, srow);
-        for (int t = 0; t < TPF; ++t) fft_gather<M>(&regs[t * kPts], t, srow);
+        for (int t = 0; t < TPF; ++t) fft_gather_sw<M>(&regs[t * kPts], t, srow);
         emu_run<M, INV, PASS + 1, PS * R>(regs, srow, W);
     }
 }
@@ -56,12 +56,8 @@ static void inv(const float2* packed, const float2* W, float* y) {
 }
 
 static void make_w(int M, std::vector<float2>& W) {
-    const int N = 2 * M;
-    W.resize(N);
-    for (int k = 0; k < N; ++k) {
-        const double a = -2.0 * M_PI * (double) k / (double) N;
-        W[k] = make_float2((float) cos(a), (float) sin(a));
-    }
+    W.resize((size_t) fft_table_size(M));
+    fft_build_table(M, W.data());
 }
 
 #define DISPATCH(M_, CALL)                         \
@@ -77,7 +73,47 @@ static void make_w(int M, std::vector<float2>& W) {
         default: return -1;                        \
     }
 
+// Shared-memory wavefronts of the exchange of every pass, counted from the addresses the device code itself produces:
+// each "thread" scatters a tag (its id and register number) through fft_scatter / reads through fft_gather_sw, and the
+// 8-byte accesses of each half-warp are grouped by bank pair (16 of them).  out[2*pass] = scatter wavefronts,
+// out[2*pass+1] = gather wavefronts, both divided by the conflict-free count (1.0 = no conflicts).
+template <int M, int PASS = 0, int PS = 1>
+static void emu_conflicts(double* out) {
+    constexpr int TPF = M / kPts;
+    constexpr int R = pass_radix(M, PASS);
+    if constexpr (PS * R < M) {
+        std::vector<float2> s(M);
+        long long wf_s = 0, wf_g = 0, ideal = 0;
+        for (int w0 = 0; w0 < TPF; w0 += 16) {                     // one half-warp at a time
+            const int nt = TPF - w0 < 16 ? TPF - w0 : 16;
+            for (int reg = 0; reg < kPts; ++reg) {
+                int cnt_s[16] = {0}, cnt_g[16] = {0};
+                for (int l = 0; l < nt; ++l) {
+                    const int t = w0 + l;
+                    // scatter: find where register `reg` of thread t lands by scattering a one-hot tag
+                    float2 v[kPts];
+                    for (int j = 0; j < kPts; ++j) v[j] = make_float2(j == reg ? 1.f : 0.f, 0.f);
+                    for (auto& e : s) e = make_float2(0.f, 0.f);
+                    fft_scatter<M, R, PS>(v, t, s.data());
+                    for (int e = 0; e < M; ++e) if (s[e].x == 1.f) cnt_s[e & 15]++;
+                    cnt_g[fft_sw(t + reg * TPF) & 15]++;
+                }
+                int ms = 0, mg = 0;
+                for (int b = 0; b < 16; ++b) { ms = cnt_s[b] > ms ? cnt_s[b] : ms; mg = cnt_g[b] > mg ? cnt_g[b] : mg; }
+                wf_s += ms; wf_g += mg; ideal += 1;
+            }
+        }
+        out[2 * PASS] = (double) wf_s / (double) ideal;
+        out[2 * PASS + 1] = (double) wf_g / (double) ideal;
+        emu_conflicts<M, PASS + 1, PS * R>(out);
+    }
+}
+
 extern "C" {
+int emu_exchange_conflicts(int M, double* out) {
+    DISPATCH(M, emu_conflicts<MM>(out));
+    return 0;
+}
 int emu_real_forward(int M, const float* x, int len, float* packed) {
     std::vector<float2> W;
     make_w(M, W);

@@ -69,3 +69,14 @@ def test_block_convolution_through_the_emulated_path(emu):
     emu.emu_real_inverse(M, _p(acc), _p(y))
     want = np.convolve(x.astype(np.float64), h.astype(np.float64))
     assert np.abs(y[:2 * M - 1] - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("M", [128, 256, 512, 1024, 2048])
+def test_exchange_is_bank_conflict_free(emu, M):
+    """The XOR swizzle of the Stockham exchange buffer (fft_sw): for rows of >= 16 threads every scatter and gather of
+    every pass touches 16 distinct bank pairs per half-warp.  Counted from the addresses the device code itself
+    produces (tests/emu), so the kernel and this check cannot drift apart."""
+    out = np.full(8, -1.0)
+    assert emu.emu_exchange_conflicts(M, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0
+    used = out[out >= 0]
+    assert len(used) >= 4 and np.all(used == 1.0), out
