@@ -46,7 +46,14 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 32))")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the bounded CPU sample")
-    return ap.parse_args()
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4"],
+                    help="c3 (default, the headline line): streams sharing one IR.  c4: BASELINE configs[3], --streams-total streams with PER-STREAM "
+                         "10 s IRs, block 1024, sharded by stream over the ranks (strong scaling; not the headline metric)")
+    ap.add_argument("--streams-total", type=int, default=8192, help="c4: streams of the whole job")
+    a = ap.parse_args()
+    if a.workload == "c4":
+        a.block, a.ir_seconds = 1024, 10.0
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -124,11 +131,14 @@ def cpu_reference_sample(args, target_seconds, threads=None):
         ref = oracle.Reference()
         T = threads or max(1, ref.hardware_threads())
         secs, _ = ref.bench_convolve_periodic(T, T, int(SR // 4), h, B, 1003)              # probe: 0.25 s of audio per stream
-        per_audio_second = max(secs, 1e-3) / 0.25
+        per_audio_second = max(secs, 1e-3) / 0.25                                           # wall seconds per audio second with T streams on T threads
+        # T..8T streams of up to 10 s each: about target_seconds of wall time on all host threads
         audio_s = float(np.clip(target_seconds / per_audio_second, 0.5, 10.0))
+        rounds = int(np.clip(target_seconds / (audio_s * per_audio_second), 1, 8))
         Lx = int(audio_s * SR) // B * B
-        secs, chk = ref.bench_convolve_periodic(T, T, Lx, h, B, 1003)
-        kind, streams = "reference", T
+        streams = T * rounds
+        secs, chk = ref.bench_convolve_periodic(T, streams, Lx, h, B, 1003)
+        kind = "reference"
     else:                                                                                   # scalar C port, 1 thread
         orc = oracle.Oracle()
         T, streams = 1, 1
@@ -189,11 +199,22 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     B, Lh, P = workload(args)
+    per_stream_ir = args.workload == "c4"
     S = args.streams
+    if per_stream_ir:                                  # strong scaling: the job's streams are cut into contiguous ranges
+        lo, hi = sharding.stream_range(rank, world, args.streams_total)
+        S = hi - lo
     bins = B + 1
-    h = synth.decaying_ir(2000, Lh)
-    e = eng.Engine(B, P, S, 1, device=local)
-    e.set_ir(0, h)
+    if per_stream_ir:
+        e = eng.Engine(B, P, S, S, device=local)
+        irs = [synth.decaying_ir(2000 + j, Lh, j) for j in range(8)]          # 8 distinct IRs cycled: every stream still owns its spectra
+        for s_ in range(S):
+            e.set_ir(s_, irs[(lo + s_) % 8])
+            e.bind(s_, s_ + 1, s_)
+    else:
+        h = synth.decaying_ir(2000, Lh)
+        e = eng.Engine(B, P, S, 1, device=local)
+        e.set_ir(0, h)
     stream = torch.cuda.Stream()                       # the kernels and the timing events share this stream
     torch.cuda.set_stream(stream)
     e.set_stream(stream.cuda_stream)
@@ -235,15 +256,19 @@ def run_b200(args):
     ms_per_step = total_ms / args.steps
     # final host-side gather of the last output block in global stream order (outside the timed region; the only
     # cross-rank data movement of the whole job)
-    gathered = sharding.gather_streams(d_out.cpu().numpy(), world * S, device="cuda")
-    value = world * S * B / (ms_per_step * 1e-3) / SR
+    total_streams = args.streams_total if per_stream_ir else world * S
+    gathered = sharding.gather_streams(d_out.cpu().numpy(), total_streams, device="cuda")
+    value = total_streams * B / (ms_per_step * 1e-3) / SR
 
     # roofline of the dominant kernel (FDL MAC, fused with the inverse FFT + overlap-add epilogue)
-    alg_bytes = (S + 1) * P * bins * 8                     # FDL read per stream + the shared IR once
+    # FDL read per stream + the shared IR once per GPU (c3) or every stream's own IR spectra (c4)
+    alg_bytes = 2 * S * P * bins * 8 if per_stream_ir else (S + 1) * P * bins * 8
     mac_avg_ms = float(np.mean(mac_ms)) if len(mac_ms) else float("nan")
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (mac_avg_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_mac<512,INV> (FDL multiply-accumulate + inverse FFT + overlap-add)", "achieved": achieved, "peak": peak,
+    kname = "k_mac_slots<%d,INV> (per-stream-IR FDL multiply-accumulate + inverse FFT + overlap-add)" % (e.fft_size // 2) if per_stream_ir else \
+            "k_mac<%d,INV> (FDL multiply-accumulate + inverse FFT + overlap-add)" % (e.fft_size // 2)
+    roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": mac_avg_ms, "kernel_share_of_step": mac_avg_ms / float(np.mean(step_ms)),
             "traffic": None}
@@ -263,6 +288,8 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         K2 = args.e2e_steps or min(args.steps, 32)
+        if per_stream_ir:
+            K2 = min(K2, 8)
         hin = eng.pinned_empty((K2, S, B))
         hout = eng.pinned_empty((K2, S, B))
         rng = np.random.default_rng(1003 + rank)
@@ -279,7 +306,7 @@ def run_b200(args):
         for i in range(min(K2, 16)):
             e.process(hin[i], hout[i])
         dt1 = (time.perf_counter() - t0) / min(K2, 16)
-        e2e = {"value": world * S * B * K2 / dt / SR, "unit": UNIT, "h2d_bytes_per_step": S * B * 4, "d2h_bytes_per_step": S * B * 4,
+        e2e = {"value": total_streams * B * K2 / dt / SR, "unit": UNIT, "h2d_bytes_per_step": S * B * 4, "d2h_bytes_per_step": S * B * 4,
                "steps": K2, "ms_per_step": 1e3 * dt / K2, "api": "irb_engine_process(host in, host out, n_blocks=%d), pinned buffers, wall clock" % K2,
                "blockwise_roundtrip_ms": 1e3 * dt1, "checksum": float(np.abs(hout[-1]).sum())}
         eng.pinned_free(hin)
@@ -291,12 +318,15 @@ def run_b200(args):
         cpu.pop("seconds", None)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[2] shape: %d independent mono streams per GPU sharing one %.1f s IR (%d taps, %d partitions), block %d"
-                                       % (S, args.ir_seconds, Lh, P, B),
+        wl = ("configs[3]: %d streams with per-stream %.0f s IRs (%d taps, %d partitions), block %d, sharded by stream over %d GPU(s)"
+              % (total_streams, args.ir_seconds, Lh, P, B, world)) if per_stream_ir else \
+             ("configs[2] shape: %d independent mono streams per GPU sharing one %.1f s IR (%d taps, %d partitions), block %d" % (S, args.ir_seconds, Lh, P, B))
+        line = {"metric": METRIC if not per_stream_ir else "48kHz RT channels (block 1024, per-stream 10s IRs)", "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "strong" if per_stream_ir else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl,
                            "streams_per_gpu": S, "block": B, "ir_taps": Lh, "partitions": P, "fft_size": e.fft_size,
-                           "state_bytes_per_gpu": int(e.state_bytes), "l2_policy": "inputs larger than L2 (FDL %.2f GB per GPU)" % (S * P * B * 8 / 1e9),
+                           "state_bytes_per_gpu": int(e.state_bytes), "l2_policy": "inputs larger than L2 (FDL %.2f GB per GPU)" % (S * P * B * 8 / 1e9), "mac_plan": list(e.mac_plan()),
                            "sharding": "contiguous stream ranges by rank, IR replicated, no data-path collective; host gather of outputs",
                            "gathered_output_shape": list(gathered.shape), "channel_samples_per_s": value * SR},
                 "latency": lat, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}

@@ -208,7 +208,7 @@ struct Smoother {
         irb::k_avg_prepare<<<grid1(M + 1, batch), 256, 0, st>>>(S, s_stride, la.as<float>(), stride, M, log_avg);
         LAUNCHED();
         for (int i = 0; i < passes; ++i) {
-            if (log_avg) irb::k_avg_scan<<<batch, 128, 0, st>>>(la.as<float>(), stride, ops.as<int>(), endq.as<int>(), kstart.as<int>(), nchunks, n_ops, rs.as<float>(), stride, M);
+            if (log_avg) irb::k_avg_scan<<<batch, 32 + irb::kAvgProducers, 0, st>>>(la.as<float>(), stride, ops.as<int>(), endq.as<int>(), kstart.as<int>(), nchunks, n_ops, rs.as<float>(), stride, M);
             else irb::k_avg_linear_sum<<<grid1(M + 1, batch), 256, 0, st>>>(la.as<float>(), stride, lo.as<int>(), hi.as<int>(), rs.as<float>(), stride, M);
             LAUNCHED();
             irb::k_avg_apply<<<grid1(M + 1, batch), 256, 0, st>>>(S, s_stride, rs.as<float>(), stride, lo.as<int>(), hi.as<int>(), M, log_avg, include_phase, include_ampl,

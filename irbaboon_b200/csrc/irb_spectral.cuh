@@ -375,33 +375,53 @@ static __global__ void k_avg_chunk_starts(const int* endq, int* kstart, int M, i
     if (k == M) for (int c = c1 + 1; c <= nchunks; ++c) kstart[c] = M + 1;
 }
 // One CTA per spectrum: lane 0 of warp 0 carries the dependent add chain, nothing else (4 cycles per operation);
-// warps 1..3 gather the operands of the next chunk into shared memory and write the previous chunk's sums back.
-static __global__ void __launch_bounds__(128) k_avg_scan(const float* la, long long la_stride, const int* __restrict__ ops, const int* __restrict__ endq,
-                                                  const int* __restrict__ kstart, int nchunks, int n_ops, float* rs, long long rs_stride, int M) {
+// warps 1..4 gather the operands of the next chunk into shared memory and write the previous chunk's sums back.
+// The gather is branch-free and issues all of a thread's loads of one kind back to back (codes, then operands), so a
+// chunk costs the producers two memory latencies, well under the chain's 2048 x 4 cycles.
+constexpr int kAvgProducers = 128;
+static __global__ void __launch_bounds__(32 + kAvgProducers) k_avg_scan(const float* la, long long la_stride, const int* __restrict__ ops,
+                                                                 const int* __restrict__ endq, const int* __restrict__ kstart, int nchunks, int n_ops,
+                                                                 float* rs, long long rs_stride, int M) {
     __shared__ __align__(16) float s_val[2][kAvgChunk], s_sum[2][kAvgChunk];
     const float* a = la + blockIdx.x * la_stride;
     float* out = rs + blockIdx.x * rs_stride;
     const int tid = threadIdx.x, ptid = tid - 32;
     const float log_floor = logf(1e-16f);
+    constexpr int PER = kAvgChunk / kAvgProducers;
     auto fill = [&](int c) {
         float* dst = s_val[c & 1];
         const int j0 = c * kAvgChunk;
-#pragma unroll 8
-        for (int j = ptid; j < kAvgChunk; j += 96) {
-            float v = 0.0f;
-            if (j0 + j < n_ops) {
-                const int code = __ldg(ops + j0 + j);
-                const int b = code < 0 ? ~code : code;
-                v = b <= M ? a[b] : (b < 2 * M ? log_floor : 0.0f);
-                if (code < 0) v = -v;
-            }
-            dst[j] = v;
+        int code[PER];
+        float val[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int g = j0 + ptid + i * kAvgProducers;
+            code[i] = __ldg(ops + (g < n_ops ? g : n_ops - 1));
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int b = code[i] < 0 ? ~code[i] : code[i];
+            val[i] = a[b <= M ? b : 0];
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int g = j0 + ptid + i * kAvgProducers;
+            const int b = code[i] < 0 ? ~code[i] : code[i];
+            float v = b <= M ? val[i] : (b < 2 * M ? log_floor : 0.0f);
+            v = code[i] < 0 ? -v : v;
+            dst[ptid + i * kAvgProducers] = g < n_ops ? v : 0.0f;
         }
     };
     auto write_back = [&](int c) {
         const float* src = s_sum[c & 1];
-        const int j0 = c * kAvgChunk;
-        for (int k = kstart[c] + ptid; k < kstart[c + 1]; k += 96) out[k] = src[__ldg(endq + k) - j0];
+        const int j0 = c * kAvgChunk, k0 = kstart[c], k1 = kstart[c + 1];
+        for (int kb = k0; kb < k1; kb += 4 * kAvgProducers) {
+            int e[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int k = kb + ptid + i * kAvgProducers; e[i] = __ldg(endq + (k < k1 ? k : k0)); }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int k = kb + ptid + i * kAvgProducers; if (k < k1) out[k] = src[e[i] - j0]; }
+        }
     };
     if (tid >= 32) fill(0);
     __syncthreads();
