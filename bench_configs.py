@@ -87,6 +87,43 @@ def c2(eng, synth, args):
             "mac_kernel_ms_mean": float(mac_ms.mean()), "realtime": bool(np.percentile(rt, 99) * 1e3 < period)}
 
 
+def c3cap(eng, synth, args):
+    """Real-time capacity of configs[2]'s shape: the largest stream count S whose p99 block step stays under
+    the 10.667 ms block period with all S streams resident (FDL 0.77 MB per stream)."""
+    import torch
+    B, Lh = 512, 96000
+    P = int(np.ceil(np.float32(Lh) / np.float32(B)))
+    period = 1e3 * B / SR
+    h = synth.decaying_ir(2000, Lh)
+    rows = []
+    for S in [int(v) for v in args.c3cap_streams.split(",")]:
+        e = eng.Engine(B, P, S, 1)
+        e.set_ir(0, h)
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        e.set_stream(stream.cuda_stream)
+        d_in = (torch.rand((2, S, B), device="cuda") * 2 - 1).contiguous()
+        d_out = torch.empty((S, B), device="cuda")
+        for i in range(P + 5):
+            e.process_device(d_in[i % 2].data_ptr(), d_out.data_ptr(), 1)
+        torch.cuda.synchronize()
+        e.set_timing(True)
+        for i in range(args.c3cap_steps):
+            e.process_device(d_in[i % 2].data_ptr(), d_out.data_ptr(), 1)
+        step_ms, mac_ms = e.timings()
+        e.set_timing(False)
+        alg = (S + 1) * P * (B + 1) * 8
+        rows.append({"streams": S, "state_gb": e.state_bytes / 1e9, "step_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)),
+                     "max": float(step_ms.max())}, "mac_gbs": alg / (mac_ms.mean() * 1e-3) / 1e9, "realtime": bool(np.percentile(step_ms, 99) < period),
+                     "headroom": float(period / np.percentile(step_ms, 99))})
+        e.close()
+        del d_in, d_out
+        torch.cuda.empty_cache()
+    ok = [r["streams"] for r in rows if r["realtime"]]
+    return {"config": "c3cap", "what": "streams sharing one 2 s IR, B=512, all resident on one GPU: block-step latency vs the %.3f ms block period, %d timed steps each" % (period, args.c3cap_steps),
+            "block_period_ms": period, "runs": rows, "rt_channels_sustained": max(ok) if ok else 0}
+
+
 def c4(eng, synth, args):
     import torch
     B, Lh = 1024, 480000
@@ -171,6 +208,8 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--c2-blocks", type=int, default=10000)
     ap.add_argument("--c2-split", default="", help="force the few-row MAC split 'split_in,cluster' (default: automatic)")
+    ap.add_argument("--c3cap-streams", default="65536,81920,86016")
+    ap.add_argument("--c3cap-steps", type=int, default=300)
     ap.add_argument("--c4-streams", type=int, default=8192)
     ap.add_argument("--c4-steps", type=int, default=30)
     ap.add_argument("--c5-captures", type=int, default=256)
@@ -180,7 +219,7 @@ def main():
     eng.set_device(0)
     res = []
     for name in args.configs.split(","):
-        r = {"c1": c1, "c2": c2, "c4": c4, "c5": c5}[name](eng, synth, args)
+        r = {"c1": c1, "c2": c2, "c3cap": c3cap, "c4": c4, "c5": c5}[name](eng, synth, args)
         print(json.dumps(r, default=float), flush=True)
         res.append(r)
     if args.out:
