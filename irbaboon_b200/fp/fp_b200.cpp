@@ -511,3 +511,166 @@ void ExpSineSweep::brickwallFadeout(double freq) {
 }
 
 }  // namespace fp
+
+// =====================================================================================================
+// Formats (N4) and the capture -> filter chain (N3): host I/O and composition only
+// =====================================================================================================
+#include <cstdint>
+#include <fstream>
+#include <iomanip>
+
+#include "CaptureChain.hpp"
+#include "Formats.hpp"
+
+namespace fp {
+namespace b200 {
+namespace formats {
+
+namespace {
+void put16(std::vector<unsigned char>& v, uint32_t x) { v.push_back(x & 0xff); v.push_back((x >> 8) & 0xff); }
+void put32(std::vector<unsigned char>& v, uint32_t x) { put16(v, x & 0xffff); put16(v, x >> 16); }
+uint32_t get32(const unsigned char* p) { return (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24); }
+uint32_t get16(const unsigned char* p) { return (uint32_t) p[0] | ((uint32_t) p[1] << 8); }
+}  // namespace
+
+bool writeWav(const std::string& path, const AudioBuffer<float>& buffer, int sampleRate, int bitsPerSample) {
+    if (bitsPerSample != 16 && bitsPerSample != 24) return false;
+    const int ch = buffer.getNumChannels(), n = buffer.getNumSamples(), bytes = bitsPerSample / 8;
+    if (ch < 1) return false;
+    const uint32_t dataBytes = (uint32_t) ((size_t) ch * (size_t) n * (size_t) bytes);
+    std::vector<unsigned char> out;
+    out.reserve(44 + (size_t) dataBytes + 1);
+    out.insert(out.end(), {'R', 'I', 'F', 'F'});
+    put32(out, 36 + dataBytes + (dataBytes & 1));
+    out.insert(out.end(), {'W', 'A', 'V', 'E', 'f', 'm', 't', ' '});
+    put32(out, 16); put16(out, 1); put16(out, (uint32_t) ch); put32(out, (uint32_t) sampleRate);
+    put32(out, (uint32_t) (sampleRate * ch * bytes)); put16(out, (uint32_t) (ch * bytes)); put16(out, (uint32_t) bitsPerSample);
+    out.insert(out.end(), {'d', 'a', 't', 'a'});
+    put32(out, dataBytes);
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < ch; ++c) {
+            double v = (double) buffer.getSample(c, i);
+            v = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);
+            const int32_t q = (int32_t) std::lrint(v * 2147483647.0);           // 32-bit fixed point, then the top `bits` bits
+            const uint32_t u = (uint32_t) (q >> (32 - bitsPerSample));
+            for (int b = 0; b < bytes; ++b) out.push_back((u >> (8 * b)) & 0xff);
+        }
+    if (dataBytes & 1) out.push_back(0);
+    std::ofstream f(path, std::ios::binary | std::ios::trunc);
+    if (!f) return false;
+    f.write((const char*) out.data(), (std::streamsize) out.size());
+    return (bool) f;
+}
+
+AudioBuffer<float> readWav(const std::string& path, int* sampleRate) {
+    AudioBuffer<float> empty;
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return empty;
+    std::vector<unsigned char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (d.size() < 12 || std::memcmp(d.data(), "RIFF", 4) != 0 || std::memcmp(d.data() + 8, "WAVE", 4) != 0) return empty;
+    int fmt = 0, ch = 0, bits = 0, rate = 0;
+    size_t pos = 12;
+    while (pos + 8 <= d.size()) {
+        const uint32_t len = get32(&d[pos + 4]);
+        const unsigned char* body = &d[pos + 8];
+        if (pos + 8 + len > d.size() && std::memcmp(&d[pos], "data", 4) != 0) return empty;
+        if (std::memcmp(&d[pos], "fmt ", 4) == 0 && len >= 16) {
+            fmt = (int) get16(body); ch = (int) get16(body + 2); rate = (int) get32(body + 4); bits = (int) get16(body + 14);
+            if (fmt == 0xfffe && len >= 26) fmt = (int) get16(body + 24);      // WAVE_FORMAT_EXTENSIBLE: the sub-format's first two bytes
+        } else if (std::memcmp(&d[pos], "data", 4) == 0) {
+            if (ch < 1 || !((fmt == 1 && (bits == 16 || bits == 24 || bits == 32)) || (fmt == 3 && bits == 32))) return empty;
+            const size_t avail = std::min<size_t>(len, d.size() - pos - 8), bytes = (size_t) bits / 8;
+            const int n = (int) (avail / (bytes * (size_t) ch));
+            AudioBuffer<float> out(ch, n);
+            for (int i = 0; i < n; ++i)
+                for (int c = 0; c < ch; ++c) {
+                    const unsigned char* p = body + ((size_t) i * ch + c) * bytes;
+                    float v;
+                    if (fmt == 3) { uint32_t u = get32(p); std::memcpy(&v, &u, 4); }
+                    else {
+                        uint32_t u = 0;
+                        for (size_t b = 0; b < bytes; ++b) u |= (uint32_t) p[b] << (8 * b);
+                        const int32_t s = (int32_t) (u << (32 - bits)) >> (32 - bits);      // sign extension
+                        v = (float) ((double) s / (double) (1u << (bits - 1)));
+                    }
+                    out.setSample(c, i, v);
+                }
+            if (sampleRate) *sampleRate = rate;
+            return out;
+        }
+        pos += 8 + (size_t) len + (len & 1);
+    }
+    return empty;
+}
+
+bool writeSweepAndIR(const std::string& path, const AudioBuffer<float>& sweepRecording, const AudioBuffer<float>& ir, int sampleRate, int numSamples) {
+    if (sweepRecording.getNumChannels() < 1 || ir.getNumChannels() < 1 || numSamples < 1) return false;
+    AudioBuffer<float> save(2, numSamples);                                       // PluginProcessor.cpp:664-682
+    save.clear();
+    save.copyFrom(0, 0, sweepRecording, 0, 0, std::min(numSamples, sweepRecording.getNumSamples()));
+    save.copyFrom(1, 0, ir, 0, 0, std::min(numSamples, ir.getNumSamples()));
+    return writeWav(path, save, sampleRate, 24);
+}
+bool readSweepAndIR(const std::string& path, AudioBuffer<float>& sweepRecording, AudioBuffer<float>& ir, int numSamples) {
+    AudioBuffer<float> both = readWav(path);
+    if (both.getNumChannels() < 2) return false;
+    sweepRecording.setSize(1, numSamples); ir.setSize(1, numSamples);             // PluginProcessor.cpp:909-917
+    sweepRecording.clear(); ir.clear();
+    const int n = std::min(numSamples, both.getNumSamples());
+    sweepRecording.copyFrom(0, 0, both, 0, 0, n);
+    ir.copyFrom(0, 0, both, 1, 0, n);
+    return true;
+}
+
+bool writeSpectrumTsv(const std::string& path, const std::string& name, const AudioBuffer<float>& spectrum, int sampleRate) {
+    const int fftSize = spectrum.getNumSamples();
+    if (spectrum.getNumChannels() < 1 || !tools::isPowerOfTwo(fftSize)) return false;          // ParallelBufferPrinter.cpp:289-293
+    const int N = fftSize / 2;
+    const double nyquist = sampleRate / 2;
+    const double freqPerBin = nyquist / (double) (N / 2);
+    std::ofstream fout(path, std::ofstream::out | std::ofstream::trunc);
+    if (!fout.is_open()) return false;
+    std::vector<float> bins(spectrum.getReadPointer(0), spectrum.getReadPointer(0) + fftSize);
+    fout << "freq\t" << name << "[lin]\t" << name << "[dB]\t" << "bin\t" << name << " phase[rad]\n";
+    for (int bin = 0; bin <= N; bin += 2) {                                       // the first column keeps the stream's precision of the
+        fout << freqPerBin * bin / 2 << "\t";                                     // previous row (8 after row 0), as in the reference
+        fout << std::setprecision(8) << tools::binAmpl(&bins[(size_t) bin]) << "\t";
+        fout << std::setprecision(8) << tools::linTodB(std::fabs(tools::binAmpl(&bins[(size_t) bin]))) << "\t";
+        fout << bin / 2 << "\t";
+        fout << std::setprecision(8) << tools::binPhase(&bins[(size_t) bin]) << "\n";
+    }
+    return (bool) fout;
+}
+
+bool writeRawSpectraText(const std::string& path, const AudioBuffer<float>& packed, int irPartSize) {
+    if (packed.getNumChannels() < 1 || irPartSize < 1) return false;
+    const int N = 2 * irPartSize;
+    std::ofstream fout(path, std::ofstream::out | std::ofstream::trunc);
+    if (!fout.is_open()) return false;
+    for (int i = 0; i < packed.getNumSamples(); ++i) {                             // fp/ir.cpp:137-142
+        if (i % 8 == 0) fout << '\n';
+        if (i % N == 0) fout << '\n';
+        fout << packed.getSample(0, i) << ", ";
+    }
+    return (bool) fout;
+}
+
+}  // namespace formats
+
+// ---- capture -> filter chain ---------------------------------------------------------------------------
+AudioBuffer<float> captureToIR(CircularBufferArray& capturedBlocks, AudioBuffer<float>& sweepForDeconv, double sampleRate, AudioBuffer<float>* recordingOut) {
+    AudioBuffer<float> recording = capturedBlocks.consolidate(0);                 // PluginProcessor.cpp:305,311
+    if (recordingOut) recordingOut->makeCopyOf(recording);
+    return convolution::deconvolve(&recording, &sweepForDeconv, sampleRate);      // :306,312 (smoothing, phase, amplitude: defaults)
+}
+AudioBuffer<float> createIRFilt(AudioBuffer<float>& irTarget, AudioBuffer<float>& irBase, double sampleRate, bool includePhase, bool includeAmplitude) {
+    return convolution::deconvolve(&irTarget, &irBase, sampleRate, true, includePhase, includeAmplitude);      // :606-615
+}
+AudioBuffer<float> chopAndNormalize(AudioBuffer<float>& ir, int irLength, float thresholdLeveldB, int consecutiveSamplesBelowThreshold) {
+    AudioBuffer<float> out = ir::IRchop(ir, irLength, thresholdLeveldB, consecutiveSamplesBelowThreshold);
+    tools::normalize(&out, 0.0f, false);
+    return out;
+}
+
+}  // namespace b200
+}  // namespace fp

@@ -8,6 +8,8 @@
 #include "ExpSineSweep.hpp"
 #include "StreamingConvolver.hpp"
 #include "PluginConvolver.hpp"
+#include "Formats.hpp"
+#include "CaptureChain.hpp"
 
 using namespace fp;
 #ifndef NOT

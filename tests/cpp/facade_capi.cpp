@@ -160,3 +160,74 @@ int fac_plugin_process(void* h, float* buffer, int channels, int n, int bypassed
     } catch (const std::exception& e) { std::fprintf(stderr, "fac_plugin_process: %s\n", e.what()); return -1; }
 }
 }
+
+// ---- formats (N4) and the capture -> filter chain (N3) --------------------------------------------------------
+#include "../../irbaboon_b200/fp/CaptureChain.hpp"
+#include "../../irbaboon_b200/fp/Formats.hpp"
+extern "C" {
+int fac_write_wav(const char* path, const float* data, int ch, int n, int sr, int bits) {
+    AudioBuffer<float> b(ch, n);
+    fill(b, data);
+    return fp::b200::formats::writeWav(path, b, sr, bits) ? 0 : -1;
+}
+int fac_read_wav(const char* path, float* out, int capacity, int* ch, int* n, int* sr) {
+    AudioBuffer<float> b = fp::b200::formats::readWav(path, sr);
+    *ch = b.getNumChannels(); *n = b.getNumSamples();
+    if (*ch == 0) return -1;
+    if ((long long) *ch * *n > capacity) return -2;
+    dump(b, out);
+    return 0;
+}
+int fac_write_sweep_and_ir(const char* path, const float* sweep, int ns, const float* ir, int ni, int sr, int num) {
+    AudioBuffer<float> s(1, ns), i(1, ni);
+    fill(s, sweep); fill(i, ir);
+    return fp::b200::formats::writeSweepAndIR(path, s, i, sr, num) ? 0 : -1;
+}
+int fac_read_sweep_and_ir(const char* path, float* sweep, float* ir, int num) {
+    AudioBuffer<float> s, i;
+    if (!fp::b200::formats::readSweepAndIR(path, s, i, num)) return -1;
+    dump(s, sweep); dump(i, ir);
+    return 0;
+}
+int fac_write_spectrum_tsv(const char* path, const char* name, const float* spec, int fftSize, int sr) {
+    AudioBuffer<float> b(1, fftSize);
+    fill(b, spec);
+    return fp::b200::formats::writeSpectrumTsv(path, name, b, sr) ? 0 : -1;
+}
+int fac_write_raw_text(const char* path, const float* packed, int n, int part) {
+    AudioBuffer<float> b(1, n);
+    fill(b, packed);
+    return fp::b200::formats::writeRawSpectraText(path, b, part) ? 0 : -1;
+}
+// blocks: [nb][H] captured host buffers (mono) -> ring -> consolidate -> deconvolve against the sweep; returns N
+int fac_capture_to_ir(const float* blocks, int nb, int H, const float* sweep, int ns, double sr, float* recording, float* ir) {
+    try {
+        fp::CircularBufferArray ring(nb, 1, H);
+        for (int b = 0; b < nb; ++b) {                                    // PluginProcessor.cpp:291-292
+            ring.getWriteBufferPtr()->copyFrom(0, 0, blocks + (size_t) b * H, H);
+            ring.incrWriteIndex();
+        }
+        AudioBuffer<float> sw(1, ns), rec;
+        fill(sw, sweep);
+        AudioBuffer<float> r = fp::b200::captureToIR(ring, sw, sr, &rec);
+        dump(rec, recording); dump(r, ir);
+        return r.getNumSamples();
+    } catch (const std::exception& e) { std::fprintf(stderr, "fac_capture_to_ir: %s\n", e.what()); return -1; }
+}
+int fac_create_ir_filt(const float* targ, int nt, const float* base, int nbse, double sr, int phase, int ampl, float* out) {
+    try {
+        AudioBuffer<float> t(1, nt), b(1, nbse);
+        fill(t, targ); fill(b, base);
+        AudioBuffer<float> r = fp::b200::createIRFilt(t, b, sr, phase != 0, ampl != 0);
+        dump(r, out);
+        return r.getNumSamples();
+    } catch (const std::exception&) { return -1; }
+}
+int fac_chop_and_normalize(const float* x, int n, int len, float thr, int cons, float* out) {
+    AudioBuffer<float> b(1, n);
+    fill(b, x);
+    AudioBuffer<float> r = fp::b200::chopAndNormalize(b, len, thr, cons);
+    dump(r, out);
+    return r.getNumSamples();
+}
+}
