@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 32))")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the bounded CPU sample")
+    ap.add_argument("--two-launch", action="store_true", help="block step as k_fwd + k_mac instead of the fused single launch (A/B measurement)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c4"],
                     help="c3 (default, the headline line): streams sharing one IR.  c4: BASELINE configs[3], --streams-total streams with PER-STREAM "
                          "10 s IRs, block 1024, sharded by stream over the ranks (strong scaling; not the headline metric)")
@@ -215,6 +216,8 @@ def run_b200(args):
         h = synth.decaying_ir(2000, Lh)
         e = eng.Engine(B, P, S, 1, device=local)
         e.set_ir(0, h)
+    if args.two_launch:
+        e.set_fused_step(False)
     stream = torch.cuda.Stream()                       # the kernels and the timing events share this stream
     torch.cuda.set_stream(stream)
     e.set_stream(stream.cuda_stream)
@@ -262,12 +265,18 @@ def run_b200(args):
 
     # roofline of the dominant kernel (FDL MAC, fused with the inverse FFT + overlap-add epilogue)
     # FDL read per stream + the shared IR once per GPU (c3) or every stream's own IR spectra (c4)
+    # With the fused step (default for c3) the kernel is the WHOLE block step: add the new spectrum's write and the audio in/out
+    # (SURVEY 8d bytes_blk = bytes_mac + (B+1)*8 + 2*B*4 per stream).
+    fused = (not per_stream_ir) and (not args.two_launch) and not e.mac_plan()[0]
     alg_bytes = 2 * S * P * bins * 8 if per_stream_ir else (S + 1) * P * bins * 8
+    if fused:
+        alg_bytes += S * (bins * 8 + 2 * B * 4)
     mac_avg_ms = float(np.mean(mac_ms)) if len(mac_ms) else float("nan")
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (mac_avg_ms * 1e-3) / 1e9
     kname = "k_mac_slots<%d,INV> (per-stream-IR FDL multiply-accumulate + inverse FFT + overlap-add)" % (e.fft_size // 2) if per_stream_ir else \
-            "k_mac<%d,INV> (FDL multiply-accumulate + inverse FFT + overlap-add)" % (e.fft_size // 2)
+            ("k_mac<%d,INV,FUSE> (one launch per block step: forward FFT + FDL multiply-accumulate + inverse FFT + overlap-add)" if fused else
+             "k_mac<%d,INV> (FDL multiply-accumulate + inverse FFT + overlap-add)") % (e.fft_size // 2)
     roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": mac_avg_ms, "kernel_share_of_step": mac_avg_ms / float(np.mean(step_ms)),
@@ -276,7 +285,7 @@ def run_b200(args):
     if os.path.exists(prof):
         try:
             tj = json.load(open(prof))
-            if tj.get("streams") == S and tj.get("block") == B and tj.get("partitions") == P:
+            if tj.get("streams") == S and tj.get("block") == B and tj.get("partitions") == P and bool(tj.get("fused", False)) == fused:
                 roof["traffic"] = tj["dram_bytes_per_launch"]
         except Exception:
             pass

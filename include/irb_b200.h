@@ -81,6 +81,9 @@ int irb_engine_tile_channels(const irb_engine* e);
 int irb_engine_mac_plan(irb_engine* e, int* slots_kernel, int* split_in, int* cluster);
 /* Force the split (powers of two; clamped to what the tile allows; 1,1 = one CTA per tile) or return to automatic (0,0). */
 int irb_engine_set_mac_split(irb_engine* e, int split_in, int cluster);
+/* With every tile bound to one IR a block step is ONE launch: the forward transform of the new block runs in the MAC kernel's
+ * prologue (default).  0 restores the two-launch form (k_fwd, then k_mac) -- same results bit for bit; kept for measurement. */
+int irb_engine_set_fused_step(irb_engine* e, int enable);
 /* clear FDL rings, overlap buffers and heads (prepareToPlay, PluginProcessor.cpp:164-234) */
 int irb_engine_reset(irb_engine* e);
 

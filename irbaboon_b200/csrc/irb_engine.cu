@@ -108,7 +108,7 @@ int launch_fwd_t(const irb::FwdArgs& a, cudaStream_t st) {
     CK(cudaGetLastError());
     return 0;
 }
-template <int M, int U, bool INV>
+template <int M, int U, bool INV, bool FUSE = false>
 int launch_mac_u(const irb::MacArgs& a, cudaStream_t st) {
     const int grid = (a.n_rows + irb::Tile<M>::ROWS - 1) / irb::Tile<M>::ROWS;
     if (grid <= 0) return 0;
@@ -117,10 +117,10 @@ int launch_mac_u(const irb::MacArgs& a, cudaStream_t st) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        CK(cudaFuncSetAttribute(irb::k_mac<M, U, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CK(cudaFuncSetAttribute(irb::k_mac<M, U, INV, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         configured_dev = dev;
     }
-    irb::k_mac<M, U, INV><<<grid, irb::kThreads + 32, smem, st>>>(a);
+    irb::k_mac<M, U, INV, FUSE><<<grid, irb::kThreads + 32, smem, st>>>(a);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
@@ -153,6 +153,7 @@ int launch_slots_t(const irb::MacArgs& a, int cl, cudaStream_t st) {
 template <int M, bool INV>
 int launch_mac_t(const irb::MacArgs& a, bool slots, int cl, cudaStream_t st) {
     if (slots) return launch_slots_t<M, INV>(a, cl, st);
+    if constexpr (INV) { if (a.in) return launch_mac_u<M, 1, true, true>(a, st); }      // forward transform fused into the prologue
     if constexpr (M <= 512) { if (mac_u_pref() == 2) return launch_mac_u<M, 2, INV>(a, st); }
     return launch_mac_u<M, 1, INV>(a, st);
 }
@@ -191,6 +192,7 @@ struct irb_engine {
     bool plan_dirty = true;
     int split_in = 1, cluster_dim = 1;
     int force_split_in = 0, force_cluster = 0;      // irb_engine_set_mac_split
+    bool fuse_fwd = true;                           // irb_engine_set_fused_step
     int num_sms = 148;
     // round-robin IR refresh (Source/PluginProcessor.cpp:455-461): staged taps per IR, positions on the device
     std::vector<std::unique_ptr<DevBuf>> rr_buf;
@@ -285,11 +287,13 @@ int engine_launch_fwd(irb_engine* e, const float* in_dev, bool audio, bool refre
     e->launches += 1;
     return 0;
 }
-int engine_launch_mac(irb_engine* e, float* out_dev, int head_back) {
+// in_dev != nullptr: the forward transform of that block runs inside the MAC kernel (shared-IR kernel only)
+int engine_launch_mac(irb_engine* e, float* out_dev, int head_back, const float* in_dev = nullptr) {
     irb::MacArgs m{};
     fill_mac_args(e, m);
     m.Y = nullptr; m.out = out_dev; m.out_chan_stride = e->B; m.Lout = e->B;
     m.ov = e->ov.as<float>(); m.tail = nullptr; m.head_back = head_back;
+    m.in = in_dev; m.in_chan_stride = e->B; m.head_rw = e->head.as<int>();
     int rc = launch_mac(e->M, true, use_slots(e), e->cluster_dim, m, e->stream);
     if (rc) return rc;
     e->launches += 1;
@@ -299,10 +303,13 @@ int engine_launch_mac(irb_engine* e, float* out_dev, int head_back) {
 int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
     const bool rec = e->timing && e->t_rec < kTimingCap;
     if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec], e->stream));
-    int rc = engine_launch_fwd(e, in_dev, true, true);
+    // Shared-IR tiles: ONE launch per block step, the forward transform is the MAC kernel's prologue (staged IRs still
+    // get their refresh rows through a k_fwd launch of their own).  The slot kernel keeps the two-launch form.
+    const bool fused = !use_slots(e) && e->fuse_fwd;
+    int rc = engine_launch_fwd(e, in_dev, !fused, true);
     if (rc) return rc;
     if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec + 1], e->stream));
-    if ((rc = engine_launch_mac(e, out_dev, 0))) return rc;
+    if ((rc = engine_launch_mac(e, out_dev, 0, fused ? in_dev : nullptr))) return rc;
     if (rec) { CK(cudaEventRecord(e->tev[3 * e->t_rec + 2], e->stream)); e->t_rec++; }
     return 0;
 }
@@ -505,6 +512,11 @@ int irb_engine_set_mac_split(irb_engine* e, int split_in, int cluster) {
     if (split_in < 0 || cluster < 0 || (split_in == 0) != (cluster == 0)) return fail(IRB_ERR_ARG, "split_in and cluster must both be 0 (automatic) or both >= 1");
     e->force_split_in = split_in; e->force_cluster = cluster;
     e->plan_dirty = true;
+    return 0;
+}
+int irb_engine_set_fused_step(irb_engine* e, int enable) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    e->fuse_fwd = enable != 0;
     return 0;
 }
 int irb_engine_mac_plan(irb_engine* e, int* slots_kernel, int* split_in, int* cluster) {

@@ -240,6 +240,12 @@ struct MacArgs {
     float* tail;               // offline: second halves [row][B]
     int split_in;              // k_mac_slots: tile slots that share one row (power of two, >= 1)
     int head_back;             // streaming: the newest spectrum of this step sits head_back slots behind head (callback order)
+    // k_mac<FUSE>: the step's forward transform runs in the MAC kernel's prologue (no k_fwd launch): in[chan*in_chan_stride + i],
+    // i < B, is the new block of every row; its spectrum goes to slot head+1, is used from registers as partition 0, and
+    // head[chan] is advanced by this kernel.  `head` must not be const for that.
+    const float* in;
+    long long in_chan_stride;
+    int* head_rw;
 };
 
 // Time-domain epilogue of a tile whose accumulated packed spectra sit in shared memory, row r at tile + r*M
@@ -300,8 +306,9 @@ struct MacSmem {
     uint64_t full[kStages], empty[kStages];
 };
 
-template <int M, int U, bool INV>
+template <int M, int U, bool INV, bool FUSE = false>
 __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const MacArgs a) {
+    static_assert(!FUSE || INV, "the fused forward transform belongs to the streaming block step");
     using T = Tile<M>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     MacSmem<M, U>& sm = *reinterpret_cast<MacSmem<M, U>*>(smem_raw);
@@ -345,13 +352,38 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
         return;
     }
 
+    if constexpr (FUSE) {
+        // ===== the block step's forward transform (k_fwd's work) for the rows of this tile, FFT layout; the IR ring fills meanwhile =====
+        const int rf = tid / T::TPF, t = tid % T::TPF;
+        const int row = row0 + rf;
+        float2 v[kPts];
+#pragma unroll
+        for (int j = 0; j < kPts; ++j) v[j] = make_float2(0.f, 0.f);
+        if (row < a.n_rows) {
+            const float* p = a.in + row * a.in_chan_stride;
+#pragma unroll
+            for (int j = 0; j < kPts; ++j) {
+                const int m = 2 * (t + j * T::TPF);
+                if (m + 1 < a.B) v[j] = *reinterpret_cast<const float2*>(p + m);
+                else if (m < a.B) v[j].x = p[m];
+            }
+        }
+        float2* srow = sm.spec + rf * M;
+        fft_run<M, false>(v, t, srow, a.W);
+        bar_compute();
+#pragma unroll
+        for (int j = 0; j < kPts; ++j) srow[t + j * T::TPF] = v[j];
+        bar_compute();
+    }
+
     // ===== compute threads, MAC layout =====
     const int g_ = tid / T::TPR, c0 = tid % T::TPR;
-    const float4* xptr[T::K];      // points at the float4 of partition 0 (the newest slot)
+    const float4* xptr[T::K];      // points at the float4 of the next partition to load (partition 0 = the newest slot)
     int slot[T::K], nvalid[T::K];
+    float4 xa[U][T::K][T::V], xb[U][T::K][T::V];
 #pragma unroll
     for (int s = 0; s < T::K; ++s) {
-        const int row = row0 + s * T::G + g_;
+        const int rl = s * T::G + g_, row = row0 + rl;
         nvalid[s] = 0; slot[s] = 0; xptr[s] = nullptr;
         if (row < a.n_rows) {
             const int chan = row / a.blocks_per_chan, blk = row % a.blocks_per_chan;
@@ -360,7 +392,29 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
             nvalid[s] = a.head ? np : (blk + 1 < np ? blk + 1 : np);
             slot[s] = hd;
             xptr[s] = reinterpret_cast<const float4*>(a.fdl + chan * a.fdl_chan_stride + (long long) hd * M) + c0;
+            if constexpr (FUSE) {
+                // packed spectrum of the new block: into the slot after the old head, and kept as partition 0's operand;
+                // the loads below then start at partition 1 = the old head
+                const int ns = hd + 1 >= a.ring ? 0 : hd + 1;
+                const float2* z = sm.spec + rl * M;
+                float4* d = reinterpret_cast<float4*>(const_cast<float2*>(a.fdl) + chan * a.fdl_chan_stride + (long long) ns * M);
+#pragma unroll
+                for (int vv = 0; vv < T::V; ++vv) {
+                    const int k = 2 * (c0 + vv * T::TPR);
+                    const float2 x0 = real_split(z[k], z[(M - k) & (M - 1)], root<false>(a.W, k), k);
+                    const float2 x1 = real_split(z[k + 1], z[M - k - 1], root<false>(a.W, k + 1), k + 1);
+                    xa[0][s][vv] = make_float4(x0.x, x0.y, x1.x, x1.y);
+                    d[c0 + vv * T::TPR] = xa[0][s][vv];
+                }
+            }
+        } else if constexpr (FUSE) {
+#pragma unroll
+            for (int vv = 0; vv < T::V; ++vv) xa[0][s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    }
+    if constexpr (FUSE) {
+        bar_compute();                                    // every read of the tile and of the old heads is done
+        if (tid < T::ROWS && row0 + tid < a.n_rows) { const int h = a.head_rw[row0 + tid] + 1; a.head_rw[row0 + tid] = h >= a.ring ? 0 : h; }
     }
     float4 acc[T::K][T::V];
 #pragma unroll
@@ -368,11 +422,11 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
 #pragma unroll
         for (int vv = 0; vv < T::V; ++vv) acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    float4 xa[U][T::K][T::V], xb[U][T::K][T::V];
     auto load_group = [&](float4 (&x)[U][T::K][T::V], int g) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int p = g * U + u;
+            if (FUSE && p == 0) continue;                 // partition 0 already sits in xa[0] (registers)
 #pragma unroll
             for (int s = 0; s < T::K; ++s) {
                 const bool ok = p < nvalid[s];

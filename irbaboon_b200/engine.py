@@ -41,6 +41,7 @@ _SIGS = {
     "irb_engine_stage_ir": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int]),
     "irb_engine_mac_plan": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "irb_engine_set_mac_split": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    "irb_engine_set_fused_step": (ctypes.c_int, [_vp, ctypes.c_int]),
     "irb_engine_bind": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "irb_engine_tile_channels": (ctypes.c_int, [_vp]),
     "irb_engine_reset": (ctypes.c_int, [_vp]),
@@ -299,6 +300,10 @@ class Engine:
     def set_mac_split(self, split_in=0, cluster=0):
         """Force how few-row launches split a row's partitions (0, 0 = automatic)."""
         _ck(lib().irb_engine_set_mac_split(self._h, int(split_in), int(cluster)))
+
+    def set_fused_step(self, enable=True):
+        """One launch per block step (forward transform inside the MAC kernel) or the two-launch form."""
+        _ck(lib().irb_engine_set_fused_step(self._h, int(bool(enable))))
 
     def bind(self, chan_begin, chan_end, ir_id):
         _ck(lib().irb_engine_bind(self._h, int(chan_begin), int(chan_end), int(ir_id)))

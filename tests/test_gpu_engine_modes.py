@@ -175,3 +175,54 @@ def test_callback_order_matches_oracle_when_host_block_exceeds_B(eng, orc, B, H,
         # a ring with room for partitions + m - 1 spectra gives the causal result instead
         causal = orc.convolve_periodic(x, h[None, :], B)[:, :n]
         _check(y, causal)
+
+
+# ---- one launch per block step: forward transform fused into the MAC kernel --------------------------------------
+@pytest.mark.parametrize("B,C,Lh", [(512, 300, 512 * 9 + 5), (256, 1200, 256 * 3), (1024, 150, 1024 * 5), (2048, 160, 2048 * 2 + 1), (64, 5000, 64 * 7), (100, 2000, 900)])
+def test_fused_step_is_bit_identical_to_two_launches_and_matches_oracle(eng, orc, B, C, Lh):
+    n = 7 * B
+    x = np.stack([synth.white_noise(1009, c % 5, n) for c in range(C)])
+    h = synth.decaying_ir(2000, Lh)
+    P = -(-Lh // B)
+    with eng.Engine(B, P, C, 1) as e:
+        e.set_ir(0, h)
+        assert e.mac_plan() == (False, 1, 1)                   # enough tiles: the shared-IR kernel
+        l0 = e.launches
+        a = e.process_stream(x)
+        fused_launches = e.launches - l0
+        e.reset()
+        e.set_fused_step(False)
+        l0 = e.launches
+        b = e.process_stream(x)
+        assert e.launches - l0 == 2 * fused_launches == 2 * 7   # one launch per block instead of two
+        fdl_b = [e.fdl_spectrum(C // 2, age) for age in range(min(P, 4))]
+        e.reset()
+        e.set_fused_step(True)
+        e.process_stream(x)
+        fdl_a = [e.fdl_spectrum(C // 2, age) for age in range(min(P, 4))]
+    assert np.array_equal(a, b)
+    assert all(np.array_equal(u, v) for u, v in zip(fdl_a, fdl_b))      # the fused kernel writes the same spectra into the FDL
+    for c in (0, C - 1):
+        _check(a[c:c + 1], orc.convolve_periodic(x[c], h, B)[:, :n])
+
+
+def test_fused_step_with_staged_ir_refresh_rows(eng, orc):
+    """Round-robin IR refresh rows still run (their own k_fwd launch) next to the fused block step."""
+    B, C, P = 256, 600, 6
+    nb = 4 * P
+    n = nb * B
+    x = np.stack([synth.white_noise(1005, c % 3, n) for c in range(C)])
+    h0, h1 = synth.decaying_ir(2000, P * B), synth.decaying_ir(2001, P * B, 1)
+    want = _rt_oracle_run(orc, B, B, x[:3], h0, P + 2, h1)
+    with eng.Engine(B, P, C, 1) as e:
+        e.stage_ir(0, h0)
+        assert e.mac_plan() == (False, 1, 1)
+        blocks = np.ascontiguousarray(x.reshape(C, nb, B).transpose(1, 0, 2))
+        ys = []
+        for k in range(nb):
+            if k == P + 2:
+                e.stage_ir(0, h1)
+            ys.append(e.process(blocks[k]))
+    y = np.ascontiguousarray(np.stack(ys).transpose(1, 0, 2)).reshape(C, n)
+    _check(y[:3, :n - B], want[:, B:])
+    assert np.array_equal(y[:3], y[3:6])                       # channels repeat every 3: same input, same output
