@@ -133,19 +133,35 @@ int launch_slots_t(const irb::MacArgs& a, int cl, cudaStream_t st) {
     if (tiles <= 0) return 0;
     const size_t smem = sizeof(irb::SlotSmem<M>);
     static thread_local int configured_dev = -1;
+    static thread_local int usable[17] = {0};
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
         CK(cudaFuncSetAttribute(irb::k_mac_slots<M, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         CK(cudaFuncSetAttribute(irb::k_mac_slots<M, INV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         configured_dev = dev;
+        for (int& u : usable) u = 0;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned) (tiles * cl)); cfg.blockDim = dim3(irb::kThreads + 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.blockDim = dim3(irb::kThreads + 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned) cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    // the largest cluster this device can co-schedule, found once per (device, size): a partitioned or busy GPU may not
+    // have 16 SMs free in one GPC; the kernel reads its cluster size at run time, so a smaller one just splits less
+    if (usable[cl] == 0) {
+        int c = cl;
+        for (; c > 1; c /= 2) {
+            cfg.gridDim = dim3((unsigned) c); at[0].val.clusterDim.x = (unsigned) c;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, irb::k_mac_slots<M, INV>, &cfg) == cudaSuccess && n > 0) break;
+            cudaGetLastError();
+        }
+        usable[cl] = c;
+    }
+    cl = usable[cl];
+    cfg.gridDim = dim3((unsigned) (tiles * cl)); at[0].val.clusterDim.x = (unsigned) cl;
     CK(cudaLaunchKernelEx(&cfg, irb::k_mac_slots<M, INV>, a));
     g_launches++;
     return 0;
@@ -200,6 +216,17 @@ struct irb_engine {
     DevBuf rr_ptrs, rr_pos, rr_list;
     std::unique_ptr<DevBuf> cb_in, cb_out;          // irb_engine_process_callback staging, grown on demand
     int cb_blocks = 0;
+    // The latency path (one small block per call): copy-in, the step's kernels and copy-out are captured ONCE into a CUDA
+    // graph over pinned staging owned by the engine and replayed with a single launch per block.  The signature records
+    // everything the captured launches baked in; a change re-captures.
+    struct GraphSig { int n_rr, split_in, cluster, slots, fuse; cudaStream_t stream; bool operator==(const GraphSig& o) const {
+        return n_rr == o.n_rr && split_in == o.split_in && cluster == o.cluster && slots == o.slots && fuse == o.fuse && stream == o.stream; } };
+    cudaGraphExec_t g_exec = nullptr;
+    GraphSig g_sig{-1, 0, 0, 0, 0, nullptr};
+    float *g_hin = nullptr, *g_hout = nullptr;
+    int g_kernels = 0;
+    bool g_warm = false;                             // a plain step with this signature has run (kernel attributes are set)
+    bool use_graph = true;
     size_t bytes = 0;
     long long launches = 0;
     // host path: copy streams + events so block b+1 uploads and block b-1 downloads while block b computes
@@ -218,6 +245,9 @@ struct irb_engine {
         }
         if (s_in) cudaStreamDestroy(s_in);
         if (s_out) cudaStreamDestroy(s_out);
+        if (g_exec) cudaGraphExecDestroy(g_exec);
+        if (g_hin) cudaFreeHost(g_hin);
+        if (g_hout) cudaFreeHost(g_hout);
     }
 };
 
@@ -542,6 +572,55 @@ int irb_engine_process_device(irb_engine* e, const float* in_dev, float* out_dev
     return 0;
 }
 
+namespace {
+constexpr size_t kGraphMaxBytes = 256 << 10;         // blocks up to this size take the captured-graph path
+
+// one block, host to host, as a single graph launch; *done = false when the caller should take the plain path instead
+int engine_process_one_graphed(irb_engine* e, const float* in_host, float* out_host, bool* done) {
+    *done = false;
+    const size_t bytes = sizeof(float) * (size_t) e->B * e->n_chans;
+    static const bool disabled = getenv("IRB_NO_GRAPH") != nullptr;
+    if (disabled || !e->use_graph || e->timing || bytes > kGraphMaxBytes) return 0;
+    const irb_engine::GraphSig sig{(int) e->h_rr_list.size(), e->split_in, e->cluster_dim, use_slots(e) ? 1 : 0, e->fuse_fwd ? 1 : 0, e->stream};
+    if (!(sig == e->g_sig)) {
+        if (e->g_exec) { cudaGraphExecDestroy(e->g_exec); e->g_exec = nullptr; }
+        e->g_sig = sig;
+        e->g_warm = false;
+    }
+    if (!e->g_warm) { e->g_warm = true; return 0; }          // first block with this signature runs plainly
+    if (!e->g_exec) {
+        if (!e->g_hin) { CK(cudaMallocHost(&e->g_hin, kGraphMaxBytes)); CK(cudaMallocHost(&e->g_hout, kGraphMaxBytes)); }
+        const long long l0 = e->launches;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed));
+        int rc = cudaMemcpyAsync(e->io_in[0].p, e->g_hin, bytes, cudaMemcpyHostToDevice, e->stream) == cudaSuccess ? 0 : IRB_ERR_CUDA;
+        if (!rc) rc = engine_step_device(e, e->io_in[0].as<float>(), e->io_out[0].as<float>());
+        if (!rc && cudaMemcpyAsync(e->g_hout, e->io_out[0].p, bytes, cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = IRB_ERR_CUDA;
+        const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+        e->g_kernels = (int) (e->launches - l0);
+        e->launches = l0;                                    // nothing ran yet
+        g_launches -= e->g_kernels;
+        if (rc || ce != cudaSuccess || !graph) {             // capture refused: fall back to plain launches for good
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            e->use_graph = false;
+            return 0;
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&e->g_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); e->g_exec = nullptr; e->use_graph = false; return 0; }
+    }
+    memcpy(e->g_hin, in_host, bytes);
+    CK(cudaGraphLaunch(e->g_exec, e->stream));
+    e->launches += e->g_kernels;
+    g_launches += e->g_kernels;
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(out_host, e->g_hout, bytes);
+    *done = true;
+    return 0;
+}
+}  // namespace
+
 int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int n_blocks) {
     if (!e || !in_host || !out_host) return fail(IRB_ERR_ARG, "null argument");
     if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
@@ -549,6 +628,17 @@ int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int
     int rc = engine_check_binding(e);
     if (rc) return rc;
     const size_t blk = (size_t) e->B * e->n_chans;
+    if (n_blocks == 1) {
+        // a live callback: one block in, one block out.  Small blocks replay a captured graph (one launch); larger ones
+        // run copy, kernels, copy back to back on the engine's stream -- no cross-stream events to wait on.
+        bool done = false;
+        if ((rc = engine_process_one_graphed(e, in_host, out_host, &done)) || done) return rc;
+        CK(cudaMemcpyAsync(e->io_in[0].p, in_host, sizeof(float) * blk, cudaMemcpyHostToDevice, e->stream));
+        if ((rc = engine_step_device(e, e->io_in[0].as<float>(), e->io_out[0].as<float>()))) return rc;
+        CK(cudaMemcpyAsync(out_host, e->io_out[0].p, sizeof(float) * blk, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        return 0;
+    }
     // three-stage pipeline over double-buffered device staging: upload b+1 | compute b | download b-1
     for (int b = 0; b < n_blocks; ++b) {
         const int q = b & 1;

@@ -681,29 +681,40 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
 
     float2* fin = sm.spec;                                // tile the epilogue reads: rows at fin + r*M
     if (nsplit > 1) {
-        // ---- sum the nsplit partial spectra of every row, ascending q, into rank 0's `red` tile ----
-        float2* red = &sm.h[0][0][0];
-        cluster_sync_all();                               // every CTA's partial sums are in its sm.spec (and its IR ring is idle)
+        // ---- sum the nsplit partial spectra of every row in ascending range order: first the split_in slots of a row inside
+        // this CTA (shared memory), then the per-CTA sums across the cluster (distributed shared memory) into rank 0 ----
+        float4* part = reinterpret_cast<float4*>(&sm.h[0][0][0]);          // this CTA's row sums; the IR ring is idle by now
+        float4* red = part + kTile / 2;                                     // rank 0: the reduced tile
+        const int n4 = rpt * (M / 2);                     // float4 of the reduced tile; n4 % CL == 0 (host guarantees)
         if (tid < kThreads) {
-            const int n4 = rpt * (M / 2);                 // float4 of the reduced tile; n4 % CL == 0 (host guarantees)
+            bar_compute();                                // all partial sums of this CTA are in sm.spec
+            const float4* sp = reinterpret_cast<const float4*>(sm.spec);
+            for (int o = tid; o < n4; o += kThreads) {
+                const int fr = o / (M / 2), c = o % (M / 2);
+                float4 sum = sp[(fr * split_in) * (M / 2) + c];
+                for (int sub = 1; sub < split_in; ++sub) {
+                    const float4 v = sp[(fr * split_in + sub) * (M / 2) + c];
+                    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                }
+                part[o] = sum;
+            }
+        }
+        cluster_sync_all();                               // every CTA's row sums are visible cluster-wide
+        if (tid < kThreads && CL > 1) {
             const int per = n4 / CL;
             const uint32_t red0 = dsmem_addr(red, 0);
             for (int o = crank * per + tid; o < (crank + 1) * per; o += kThreads) {
-                const int fr = o / (M / 2), c = o % (M / 2);
-                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int rk = 0; rk < CL; ++rk) {
-                    const uint32_t base = dsmem_addr(sm.spec, (uint32_t) rk);
-                    for (int sub = 0; sub < split_in; ++sub) {
-                        const float4 v = dsmem_ld4(base + (uint32_t) (((fr * split_in + sub) * (M / 2) + c) * sizeof(float4)));
-                        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-                    }
+                float4 sum = dsmem_ld4(dsmem_addr(part, 0) + (uint32_t) (o * sizeof(float4)));
+                for (int rk = 1; rk < CL; ++rk) {
+                    const float4 v = dsmem_ld4(dsmem_addr(part, (uint32_t) rk) + (uint32_t) (o * sizeof(float4)));
+                    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
                 }
                 dsmem_st4(red0 + (uint32_t) (o * sizeof(float4)), sum);
             }
         }
         cluster_sync_all();                               // rank 0 holds the reduced tile; nobody reads remote memory any more
         if (crank != 0) return;
-        fin = red;
+        fin = reinterpret_cast<float2*>(CL > 1 ? red : part);
     }
     if (tid >= kThreads) return;
     if (nsplit == 1) bar_compute();                       // the tile is complete in shared memory

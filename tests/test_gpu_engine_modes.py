@@ -226,3 +226,39 @@ def test_fused_step_with_staged_ir_refresh_rows(eng, orc):
     y = np.ascontiguousarray(np.stack(ys).transpose(1, 0, 2)).reshape(C, n)
     _check(y[:3, :n - B], want[:, B:])
     assert np.array_equal(y[:3], y[3:6])                       # channels repeat every 3: same input, same output
+
+
+def test_single_block_calls_replay_a_graph_with_identical_results(eng, orc):
+    """One small block per call (the live-callback shape): from the second call on, copy-in, the step's kernels and copy-out
+    are one captured CUDA graph.  Results equal the multi-block pipelined call bit for bit, across an IR switch, a reset and
+    a change of the launch plan (each of which re-captures)."""
+    B, C, P = 256, 2, 12
+    nb = 30
+    x = np.stack([synth.white_noise(1010, c, nb * B) for c in range(C)])
+    h0, h1 = synth.decaying_ir(2000, P * B), synth.decaying_ir(2001, P * B - 9, 1)
+    blocks = np.ascontiguousarray(x.reshape(C, nb, B).transpose(1, 0, 2))
+    with eng.Engine(B, P, C, 1) as e:
+        e.set_ir(0, h0)
+        whole = e.process(blocks)                                  # pipelined multi-block path
+        e.reset()
+        one = np.stack([e.process(blocks[k]) for k in range(nb)])  # plain first call, graph replays after
+        assert np.array_equal(one, whole)
+        l0 = e.launches
+        e.process(blocks[0])
+        assert e.launches - l0 == 2                                # the replayed graph holds the step's two kernels
+        e.reset()
+        e.set_mac_split(1, 1)                                      # different plan -> different kernels -> re-capture
+        one2 = np.stack([e.process(blocks[k]) for k in range(nb)])
+        e.reset()
+        e.set_mac_split(0, 0)
+        e.stage_ir(0, h0)                                          # adds a refresh row to the forward launch -> re-capture
+        ys = []
+        for k in range(nb):
+            if k == 10:
+                e.stage_ir(0, h1)
+            ys.append(e.process(blocks[k]))
+    y1 = np.ascontiguousarray(one2.transpose(1, 0, 2)).reshape(C, nb * B)
+    _check(y1, orc.convolve_periodic(x, np.stack([h0, h0]), B)[:, :nb * B])
+    y = np.ascontiguousarray(np.stack(ys).transpose(1, 0, 2)).reshape(C, nb * B)
+    want = _rt_oracle_run(orc, B, B, x, h0, 10, h1)
+    _check(y[:, :-B], want[:, B:])
