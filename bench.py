@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=16384, help="streams per GPU (configs[2] names 1024; >= 10k is the north-star target)")
+    ap.add_argument("--streams", type=int, default=65536, help="streams per GPU (configs[2] names 1024; >= 10k is the north-star target; "
+                                                                "65536 resident streams keep p99 well under the block period)")
     ap.add_argument("--block", type=int, default=512)
     ap.add_argument("--ir-seconds", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -297,6 +298,7 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         K2 = args.e2e_steps or min(args.steps, 32)
+        K2 = max(4, min(K2, (2 << 30) // (S * B * 4)))          # at most ~2 GB of pinned host memory per direction
         if per_stream_ir:
             K2 = min(K2, 8)
         hin = eng.pinned_empty((K2, S, B))

@@ -236,8 +236,10 @@ struct irb_engine {
     bool timing = false;
     std::vector<cudaEvent_t> tev;
     int t_rec = 0;
+    std::vector<cudaEvent_t> ev_grp;                 // single large block: per channel group "uploaded" / "computed"
     ~irb_engine() {
         for (auto ev : tev) cudaEventDestroy(ev);
+        for (auto ev : ev_grp) if (ev) cudaEventDestroy(ev);
         for (int i = 0; i < 2; ++i) {
             if (ev_in[i]) cudaEventDestroy(ev_in[i]);
             if (ev_done[i]) cudaEventDestroy(ev_done[i]);
@@ -290,24 +292,27 @@ int engine_check_binding(irb_engine* e) {
     return 0;
 }
 
-void fill_mac_args(irb_engine* e, irb::MacArgs& m) {
-    m.fdl = e->fdl.as<float2>(); m.fdl_chan_stride = (long long) e->ring * e->M;
-    m.head = e->head.as<int>(); m.ring = e->ring; m.blocks_per_chan = 1; m.n_rows = e->n_chans;
+// Every launch helper takes a channel range [c0, c0 + cn): all per-channel arrays are offset, so a kernel sees rows
+// 0 .. cn-1.  c0 is a multiple of the tile's row count (tiles never straddle a range).
+void fill_mac_args(irb_engine* e, irb::MacArgs& m, int c0, int cn) {
+    m.fdl = e->fdl.as<float2>() + (size_t) c0 * e->ring * e->M; m.fdl_chan_stride = (long long) e->ring * e->M;
+    m.head = e->head.as<int>() + c0; m.ring = e->ring; m.blocks_per_chan = 1; m.n_rows = cn;
     m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
-    m.ir_of_chan = e->ir_of_chan.as<int>(); m.nparts = e->nparts.as<int>(); m.W = e->W;
+    m.ir_of_chan = e->ir_of_chan.as<int>() + c0; m.nparts = e->nparts.as<int>(); m.W = e->W;
     m.B = e->B; m.split_in = e->split_in;
 }
 bool use_slots(const irb_engine* e) { return e->per_row_ir || e->split_in > 1 || e->cluster_dim > 1; }
 
 constexpr int kTimingCap = 16384;
 
-// forward FFT of one block of every channel into the FDL (advances the heads) and/or the round-robin IR refresh rows
-int engine_launch_fwd(irb_engine* e, const float* in_dev, bool audio, bool refresh) {
+// forward FFT of one block of the channels of the range into the FDL (advances their heads) and/or the round-robin IR
+// refresh rows; in_dev / out_dev below are the block's arrays for ALL channels
+int engine_launch_fwd(irb_engine* e, const float* in_dev, bool audio, bool refresh, int c0, int cn) {
     irb::FwdArgs f{};
-    f.src = in_dev; f.src2 = nullptr; f.src_chan_stride = e->B; f.L = e->B; f.B = e->B;
-    f.blocks_per_chan = 1; f.n_rows = audio ? e->n_chans : 0;
-    f.dst = e->fdl.as<float2>(); f.dst_chan_stride = (long long) e->ring * e->M;
-    f.head = e->head.as<int>(); f.ring = e->ring; f.W = e->W;
+    f.src = in_dev ? in_dev + (size_t) c0 * e->B : nullptr; f.src2 = nullptr; f.src_chan_stride = e->B; f.L = e->B; f.B = e->B;
+    f.blocks_per_chan = 1; f.n_rows = audio ? cn : 0;
+    f.dst = e->fdl.as<float2>() + (size_t) c0 * e->ring * e->M; f.dst_chan_stride = (long long) e->ring * e->M;
+    f.head = e->head.as<int>() + c0; f.ring = e->ring; f.W = e->W;
     // one IR partition of every staged IR is re-transformed per block, in the same launch
     f.n_rr = refresh ? (int) e->h_rr_list.size() : 0; f.rr_list = e->rr_list.as<int>(); f.rr_taps = e->rr_ptrs.as<const float*>();
     f.rr_pos = e->rr_pos.as<int>(); f.nparts = e->nparts.as<int>(); f.H = e->H.as<float2>(); f.ir_stride = (long long) e->ring * e->M;
@@ -318,28 +323,36 @@ int engine_launch_fwd(irb_engine* e, const float* in_dev, bool audio, bool refre
     return 0;
 }
 // in_dev != nullptr: the forward transform of that block runs inside the MAC kernel (shared-IR kernel only)
-int engine_launch_mac(irb_engine* e, float* out_dev, int head_back, const float* in_dev = nullptr) {
+int engine_launch_mac(irb_engine* e, float* out_dev, int head_back, const float* in_dev, int c0, int cn) {
     irb::MacArgs m{};
-    fill_mac_args(e, m);
-    m.Y = nullptr; m.out = out_dev; m.out_chan_stride = e->B; m.Lout = e->B;
-    m.ov = e->ov.as<float>(); m.tail = nullptr; m.head_back = head_back;
-    m.in = in_dev; m.in_chan_stride = e->B; m.head_rw = e->head.as<int>();
+    fill_mac_args(e, m, c0, cn);
+    m.Y = nullptr; m.out = out_dev + (size_t) c0 * e->B; m.out_chan_stride = e->B; m.Lout = e->B;
+    m.ov = e->ov.as<float>() + (size_t) c0 * e->B; m.tail = nullptr; m.head_back = head_back;
+    m.in = in_dev ? in_dev + (size_t) c0 * e->B : nullptr; m.in_chan_stride = e->B; m.head_rw = e->head.as<int>() + c0;
     int rc = launch_mac(e->M, true, use_slots(e), e->cluster_dim, m, e->stream);
     if (rc) return rc;
     e->launches += 1;
     return 0;
 }
 
-int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
-    const bool rec = e->timing && e->t_rec < kTimingCap;
-    if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec], e->stream));
+// one block step for the channels [c0, c0+cn); refresh: also run the staged IRs' refresh rows (once per block)
+int engine_step_range(irb_engine* e, const float* in_dev, float* out_dev, int c0, int cn, bool refresh) {
     // Shared-IR tiles: ONE launch per block step, the forward transform is the MAC kernel's prologue (staged IRs still
     // get their refresh rows through a k_fwd launch of their own).  The slot kernel keeps the two-launch form.
     const bool fused = !use_slots(e) && e->fuse_fwd;
-    int rc = engine_launch_fwd(e, in_dev, !fused, true);
+    int rc = engine_launch_fwd(e, in_dev, !fused, refresh, c0, cn);
+    if (rc) return rc;
+    return engine_launch_mac(e, out_dev, 0, fused ? in_dev : nullptr, c0, cn);
+}
+
+int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
+    const bool rec = e->timing && e->t_rec < kTimingCap;
+    if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec], e->stream));
+    const bool fused = !use_slots(e) && e->fuse_fwd;
+    int rc = engine_launch_fwd(e, in_dev, !fused, true, 0, e->n_chans);
     if (rc) return rc;
     if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec + 1], e->stream));
-    if ((rc = engine_launch_mac(e, out_dev, 0, fused ? in_dev : nullptr))) return rc;
+    if ((rc = engine_launch_mac(e, out_dev, 0, fused ? in_dev : nullptr, 0, e->n_chans))) return rc;
     if (rec) { CK(cudaEventRecord(e->tev[3 * e->t_rec + 2], e->stream)); e->t_rec++; }
     return 0;
 }
@@ -574,6 +587,7 @@ int irb_engine_process_device(irb_engine* e, const float* in_dev, float* out_dev
 
 namespace {
 constexpr size_t kGraphMaxBytes = 256 << 10;         // blocks up to this size take the captured-graph path
+constexpr int kMaxGroups = 8;                        // channel groups a large single block is pipelined over
 
 // one block, host to host, as a single graph launch; *done = false when the caller should take the plain path instead
 int engine_process_one_graphed(irb_engine* e, const float* in_host, float* out_host, bool* done) {
@@ -633,9 +647,35 @@ int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int
         // run copy, kernels, copy back to back on the engine's stream -- no cross-stream events to wait on.
         bool done = false;
         if ((rc = engine_process_one_graphed(e, in_host, out_host, &done)) || done) return rc;
-        CK(cudaMemcpyAsync(e->io_in[0].p, in_host, sizeof(float) * blk, cudaMemcpyHostToDevice, e->stream));
-        if ((rc = engine_step_device(e, e->io_in[0].as<float>(), e->io_out[0].as<float>()))) return rc;
-        CK(cudaMemcpyAsync(out_host, e->io_out[0].p, sizeof(float) * blk, cudaMemcpyDeviceToHost, e->stream));
+        const int rows = tile_rows(e->M);
+        const int tiles = (e->n_chans + rows - 1) / rows;
+        const int groups = (e->timing || sizeof(float) * blk < (4u << 20)) ? 1 : (int) std::min<long long>(kMaxGroups, tiles / (4LL * e->num_sms) > 0 ? tiles / (4LL * e->num_sms) : 1);
+        if (groups <= 1) {
+            CK(cudaMemcpyAsync(e->io_in[0].p, in_host, sizeof(float) * blk, cudaMemcpyHostToDevice, e->stream));
+            if ((rc = engine_step_device(e, e->io_in[0].as<float>(), e->io_out[0].as<float>()))) return rc;
+            CK(cudaMemcpyAsync(out_host, e->io_out[0].p, sizeof(float) * blk, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaStreamSynchronize(e->stream));
+            return 0;
+        }
+        // A large block: cut the channels into groups of whole tiles and pipeline upload | kernels | download across the
+        // groups, so the block's latency is about its kernel time plus ONE group's copies instead of kernel time plus
+        // all copies (what keeps a live feed of tens of thousands of channels inside its block period).
+        if (e->ev_grp.empty()) {
+            e->ev_grp.resize(2 * kMaxGroups, nullptr);
+            for (auto& ev : e->ev_grp) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        }
+        for (int g = 0; g < groups; ++g) {
+            const int c0 = (int) ((long long) tiles * g / groups) * rows, c1 = std::min(e->n_chans, (int) ((long long) tiles * (g + 1) / groups) * rows);
+            const size_t off = (size_t) c0 * e->B, cnt = (size_t) (c1 - c0) * e->B;
+            CK(cudaMemcpyAsync(e->io_in[0].as<float>() + off, in_host + off, sizeof(float) * cnt, cudaMemcpyHostToDevice, e->s_in));
+            CK(cudaEventRecord(e->ev_grp[2 * g], e->s_in));
+            CK(cudaStreamWaitEvent(e->stream, e->ev_grp[2 * g], 0));
+            if ((rc = engine_step_range(e, e->io_in[0].as<float>(), e->io_out[0].as<float>(), c0, c1 - c0, g == 0))) return rc;
+            CK(cudaEventRecord(e->ev_grp[2 * g + 1], e->stream));
+            CK(cudaStreamWaitEvent(e->s_out, e->ev_grp[2 * g + 1], 0));
+            CK(cudaMemcpyAsync(out_host + off, e->io_out[0].as<float>() + off, sizeof(float) * cnt, cudaMemcpyDeviceToHost, e->s_out));
+        }
+        CK(cudaStreamSynchronize(e->s_out));
         CK(cudaStreamSynchronize(e->stream));
         return 0;
     }
@@ -684,10 +724,10 @@ int irb_engine_process_callback(irb_engine* e, const float* in_host, float* out_
     float* dout = e->cb_out->as<float>();
     CK(cudaMemcpyAsync(din, in_host, sizeof(float) * blk * n_blocks, cudaMemcpyHostToDevice, e->stream));
     for (int b = 0; b < n_blocks; ++b)
-        if ((rc = engine_launch_fwd(e, din + b * blk, true, false))) return rc;
+        if ((rc = engine_launch_fwd(e, din + b * blk, true, false, 0, e->n_chans))) return rc;
     for (int b = 0; b < n_blocks; ++b) {
-        if ((rc = engine_launch_fwd(e, nullptr, false, true))) return rc;
-        if ((rc = engine_launch_mac(e, dout + b * blk, n_blocks - 1 - b))) return rc;
+        if ((rc = engine_launch_fwd(e, nullptr, false, true, 0, e->n_chans))) return rc;
+        if ((rc = engine_launch_mac(e, dout + b * blk, n_blocks - 1 - b, nullptr, 0, e->n_chans))) return rc;
     }
     CK(cudaMemcpyAsync(out_host, dout, sizeof(float) * blk * n_blocks, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -758,7 +798,7 @@ int irb_engine_mac_only_device(irb_engine* e, float* acc_dev) {
     int rc = engine_check_binding(e);
     if (rc) return rc;
     irb::MacArgs m{};
-    fill_mac_args(e, m);
+    fill_mac_args(e, m, 0, e->n_chans);
     m.Y = (float2*) acc_dev;
     rc = launch_mac(e->M, false, use_slots(e), e->cluster_dim, m, e->stream);
     if (rc) return rc;

@@ -54,13 +54,14 @@ def launches(src, dst, cmd):
     agg = collections.OrderedDict()
     for r in rows[1:]:
         agg.setdefault(r[ki], []).append(float(r[vi].replace(',', '')))
-    tot = sum(sum(v) for k, v in agg.items() if 'irb::' in k)
+    ours = lambda k: 'at::' not in k and 'cub::' not in k and 'nccl' not in k.lower()      # everything that is not a torch / library kernel
+    tot = sum(sum(v) for k, v in agg.items() if ours(k))
     with open(dst, 'w') as f:
         f.write('# ncu --metrics gpu__time_duration.sum --clock-control none : %s\n' % cmd)
-        f.write('# per-launch times are cold-cache and serialised: compare SHARES. share = of all irb:: kernel time\n')
+        f.write('# per-launch times are cold-cache and serialised: compare SHARES. share = of the time of this library\'s kernels\n')
         f.write('kernel,launches,avg_ns,total_ns,share\n')
         for k, v in agg.items():
-            f.write('"%s",%d,%.1f,%.1f,%s\n' % (k[:96], len(v), sum(v) / len(v), sum(v), '%.4f' % (sum(v) / tot) if 'irb::' in k else ''))
+            f.write('"%s",%d,%.1f,%.1f,%s\n' % (k[:96], len(v), sum(v) / len(v), sum(v), '%.4f' % (sum(v) / tot) if ours(k) else ''))
 
 
 if __name__ == '__main__':

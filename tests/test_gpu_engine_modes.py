@@ -262,3 +262,25 @@ def test_single_block_calls_replay_a_graph_with_identical_results(eng, orc):
     y = np.ascontiguousarray(np.stack(ys).transpose(1, 0, 2)).reshape(C, nb * B)
     want = _rt_oracle_run(orc, B, B, x, h0, 10, h1)
     _check(y[:, :-B], want[:, B:])
+
+
+@pytest.mark.parametrize("B,C,ns", [(64, 40000, 1), (512, 9500, 1), (256, 5000, 5000)])
+def test_large_single_block_calls_pipeline_channel_groups(eng, B, C, ns):
+    """A single-block call with megabytes of audio is cut into channel groups whose upload, kernels and download overlap.
+    Same results, bit for bit, as the multi-block call (which pipelines whole blocks) -- shared IR and per-stream IRs."""
+    nb, P = 5, 3
+    rng = np.random.default_rng(B)
+    x = (rng.random((nb, C, B), dtype=np.float32) * 2 - 1).astype(np.float32)
+    with eng.Engine(B, P, C, ns) as e:
+        if ns == 1:
+            e.set_ir(0, synth.decaying_ir(2000, P * B - 5))
+        else:
+            irs = [synth.decaying_ir(2100 + j, P * B - j, j) for j in range(4)]
+            for c in range(C):
+                e.set_ir(c, irs[c % 4])
+                e.bind(c, c + 1, c)
+        whole = e.process(x)
+        e.reset()
+        single = np.stack([e.process(x[k]) for k in range(nb)])
+    assert np.array_equal(single, whole)
+    assert np.abs(whole).max() > 0.1
