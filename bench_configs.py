@@ -131,6 +131,39 @@ def c3cap(eng, synth, args):
             "block_period_ms": period, "runs": rows, "rt_channels_sustained": max(ok) if ok else 0}
 
 
+def group(eng, synth, args):
+    """configs[2] shape through ONE process driving every visible GPU (irb_group_*): host buffers in, host buffers out."""
+    B, Lh = 512, 96000
+    P = int(np.ceil(np.float32(Lh) / np.float32(B)))
+    nd = eng.device_count()
+    S = args.group_streams * nd
+    K = args.group_blocks
+    h = synth.decaying_ir(2000, Lh)
+    with eng.Group(list(range(nd)), B, P, S, 1) as g:
+        g.set_ir(0, h)
+        x = eng.pinned_empty((K, S, B))
+        y = eng.pinned_empty((K, S, B))
+        rng = np.random.default_rng(1003)
+        x[:] = rng.random((K, S, B), dtype=np.float32) * 2 - 1
+        for _ in range(-(-P // K) + 1):                           # fill the FDLs
+            g.process(x, y)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            g.process(x, y)
+            ts.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for i in range(min(K, 8)):
+            g.process(x[i], y[i])
+        one = (time.perf_counter() - t0) / min(K, 8)
+        out = {"config": "group", "what": "one process, %d GPU(s), %d streams each sharing one 2 s IR, B=512: irb_group_process(host in, host out, %d blocks), "
+                                         "pinned buffers, wall clock" % (nd, args.group_streams, K),
+               "gpus": nd, "streams_total": S, "ranges": g.ranges, "seconds_best": min(ts), "rt_channels_e2e": S * B * K / min(ts) / SR,
+               "ms_per_block": 1e3 * min(ts) / K, "single_block_roundtrip_ms": 1e3 * one, "block_period_ms": 1e3 * B / SR, "checksum": float(np.abs(y[-1]).sum())}
+        eng.pinned_free(x); eng.pinned_free(y)
+    return out
+
+
 def c4(eng, synth, args):
     import torch
     B, Lh = 1024, 480000
@@ -217,6 +250,8 @@ def main():
     ap.add_argument("--c2-split", default="", help="force the few-row MAC split 'split_in,cluster' (default: automatic)")
     ap.add_argument("--c3cap-streams", default="65536,81920,86016")
     ap.add_argument("--c3cap-steps", type=int, default=300)
+    ap.add_argument("--group-streams", type=int, default=16384, help="group: streams per GPU")
+    ap.add_argument("--group-blocks", type=int, default=16)
     ap.add_argument("--c4-streams", type=int, default=8192)
     ap.add_argument("--c4-steps", type=int, default=30)
     ap.add_argument("--c5-captures", type=int, default=256)
@@ -226,7 +261,7 @@ def main():
     eng.set_device(0)
     res = []
     for name in args.configs.split(","):
-        r = {"c1": c1, "c2": c2, "c3cap": c3cap, "c4": c4, "c5": c5}[name](eng, synth, args)
+        r = {"c1": c1, "c2": c2, "c3cap": c3cap, "c4": c4, "c5": c5, "group": group}[name](eng, synth, args)
         print(json.dumps(r, default=float), flush=True)
         res.append(r)
     if args.out:

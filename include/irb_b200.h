@@ -124,6 +124,25 @@ double irb_last_compute_ms(void);
  * n_channels * M complex; used to time the roofline kernel in isolation */
 int irb_engine_mac_only_device(irb_engine* e, float* acc_dev);
 
+/* ---- several GPUs from one process ---------------------------------------------------------------------
+ * Streams never interact (fp/convolution.cpp:160-215 has no cross-channel term), so n_channels are cut into contiguous
+ * ranges of whole kernel tiles, one irb_engine per device.  n_irs > 0: shared IRs, replicated on every device, bound with
+ * irb_group_bind.  n_irs == 0: every channel owns an IR that lives on the channel's device; ir_id then means the channel.
+ * No device-to-device traffic and no collective: each device reads its channel range of the caller's
+ * [n_blocks][n_channels][block_size] arrays and writes its range of the output (the "host-side gather").  One host thread
+ * feeds all devices: every device's copies and kernels are enqueued before the first is waited for. */
+typedef struct irb_group irb_group;
+int irb_group_create(irb_group** out, const int* devices, int n_devices, int block_size, int max_partitions, int n_channels, int n_irs);
+int irb_group_destroy(irb_group* g);
+int irb_group_device_count(const irb_group* g);
+int irb_group_channel_range(const irb_group* g, int index, int* begin, int* end);
+int irb_group_set_ir(irb_group* g, int ir_id, const float* left, const float* right, int n_taps);
+int irb_group_stage_ir(irb_group* g, int ir_id, const float* left, const float* right, int n_taps, int n_partitions);
+int irb_group_bind(irb_group* g, int chan_begin, int chan_end, int ir_id);
+int irb_group_reset(irb_group* g);
+int irb_group_process(irb_group* g, const float* in_host, float* out_host, int n_blocks);
+size_t irb_group_state_bytes(const irb_group* g);
+
 /* ---- offline functions ------------------------------------------------------------------------------
  * fp::convolution::convolvePeriodic (fp/convolution.hpp:31, fp/convolution.cpp:14-242): planar
  * x[ch_x][len_x], h[ch_h][len_h] -> out[ch_x][len_x+len_h-1].  Same channel layouts (mono/stereo x

@@ -635,9 +635,17 @@ int engine_process_one_graphed(irb_engine* e, const float* in_host, float* out_h
 }
 }  // namespace
 
-int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int n_blocks) {
-    if (!e || !in_host || !out_host) return fail(IRB_ERR_ARG, "null argument");
-    if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
+namespace {
+// Host-buffer block steps: block b of this engine's channels starts at in_host + b*stride (stride == n_channels*B for a
+// dense array; larger when the engine owns a channel range of a wider array).  wait == false returns once everything
+// is enqueued (engine_process_wait completes it) so that one host thread can keep several devices busy.
+int engine_process_wait(irb_engine* e) {
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->s_out));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+int engine_process_enqueue(irb_engine* e, const float* in_host, float* out_host, int n_blocks, size_t stride, bool allow_graph) {
     CK(cudaSetDevice(e->device));
     int rc = engine_check_binding(e);
     if (rc) return rc;
@@ -645,8 +653,10 @@ int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int
     if (n_blocks == 1) {
         // a live callback: one block in, one block out.  Small blocks replay a captured graph (one launch); larger ones
         // run copy, kernels, copy back to back on the engine's stream -- no cross-stream events to wait on.
-        bool done = false;
-        if ((rc = engine_process_one_graphed(e, in_host, out_host, &done)) || done) return rc;
+        if (allow_graph) {
+            bool done = false;
+            if ((rc = engine_process_one_graphed(e, in_host, out_host, &done)) || done) return rc;
+        }
         const int rows = tile_rows(e->M);
         const int tiles = (e->n_chans + rows - 1) / rows;
         const int groups = (e->timing || sizeof(float) * blk < (4u << 20)) ? 1 : (int) std::min<long long>(kMaxGroups, tiles / (4LL * e->num_sms) > 0 ? tiles / (4LL * e->num_sms) : 1);
@@ -654,7 +664,6 @@ int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int
             CK(cudaMemcpyAsync(e->io_in[0].p, in_host, sizeof(float) * blk, cudaMemcpyHostToDevice, e->stream));
             if ((rc = engine_step_device(e, e->io_in[0].as<float>(), e->io_out[0].as<float>()))) return rc;
             CK(cudaMemcpyAsync(out_host, e->io_out[0].p, sizeof(float) * blk, cudaMemcpyDeviceToHost, e->stream));
-            CK(cudaStreamSynchronize(e->stream));
             return 0;
         }
         // A large block: cut the channels into groups of whole tiles and pipeline upload | kernels | download across the
@@ -675,27 +684,32 @@ int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int
             CK(cudaStreamWaitEvent(e->s_out, e->ev_grp[2 * g + 1], 0));
             CK(cudaMemcpyAsync(out_host + off, e->io_out[0].as<float>() + off, sizeof(float) * cnt, cudaMemcpyDeviceToHost, e->s_out));
         }
-        CK(cudaStreamSynchronize(e->s_out));
-        CK(cudaStreamSynchronize(e->stream));
         return 0;
     }
     // three-stage pipeline over double-buffered device staging: upload b+1 | compute b | download b-1
     for (int b = 0; b < n_blocks; ++b) {
         const int q = b & 1;
         if (b >= 2) CK(cudaStreamWaitEvent(e->s_in, e->ev_done[q], 0));            // compute b-2 has consumed io_in[q]
-        CK(cudaMemcpyAsync(e->io_in[q].p, in_host + b * blk, sizeof(float) * blk, cudaMemcpyHostToDevice, e->s_in));
+        CK(cudaMemcpyAsync(e->io_in[q].p, in_host + b * stride, sizeof(float) * blk, cudaMemcpyHostToDevice, e->s_in));
         CK(cudaEventRecord(e->ev_in[q], e->s_in));
         CK(cudaStreamWaitEvent(e->stream, e->ev_in[q], 0));
         if (b >= 2) CK(cudaStreamWaitEvent(e->stream, e->ev_out[q], 0));           // download b-2 has drained io_out[q]
         if ((rc = engine_step_device(e, e->io_in[q].as<float>(), e->io_out[q].as<float>()))) return rc;
         CK(cudaEventRecord(e->ev_done[q], e->stream));
         CK(cudaStreamWaitEvent(e->s_out, e->ev_done[q], 0));
-        CK(cudaMemcpyAsync(out_host + b * blk, e->io_out[q].p, sizeof(float) * blk, cudaMemcpyDeviceToHost, e->s_out));
+        CK(cudaMemcpyAsync(out_host + b * stride, e->io_out[q].p, sizeof(float) * blk, cudaMemcpyDeviceToHost, e->s_out));
         CK(cudaEventRecord(e->ev_out[q], e->s_out));
     }
-    CK(cudaStreamSynchronize(e->s_out));
-    CK(cudaStreamSynchronize(e->stream));
     return 0;
+}
+}  // namespace
+
+int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int n_blocks) {
+    if (!e || !in_host || !out_host) return fail(IRB_ERR_ARG, "null argument");
+    if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
+    int rc = engine_process_enqueue(e, in_host, out_host, n_blocks, (size_t) e->B * e->n_chans, true);
+    if (rc) return rc;
+    return engine_process_wait(e);
 }
 
 // The order of one plug-in callback (PluginProcessor.cpp:421-518): EVERY block completed by the callback is transformed
@@ -904,4 +918,110 @@ int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, i
     return tm.collect();
 }
 
+// ---- several GPUs driven from one process: streams sharded by contiguous, tile-aligned channel ranges, shared
+// IR spectra replicated on every device, per-channel IRs (n_irs == 0) living with their channel; no device-to-device
+// traffic -- every device reads its channel range of the caller's arrays and writes its range of the output.
+struct irb_group {
+    std::vector<irb_engine*> eng;
+    std::vector<int> begin;            // eng[i] owns channels [begin[i], begin[i+1])
+    int B = 0, n_chans = 0, n_irs = 0;
+    bool private_irs = false;
+    int owner(int chan) const { int i = 0; while (i + 1 < (int) eng.size() && chan >= begin[i + 1]) ++i; return i; }
+};
+
+int irb_group_create(irb_group** out, const int* devices, int n_devices, int block_size, int max_partitions, int n_channels, int n_irs) {
+    if (!out) return fail(IRB_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (!devices || n_devices < 1) return fail(IRB_ERR_ARG, "no devices");
+    if (block_size < 1 || half_size_for_block(block_size) > kMaxM) return fail(IRB_ERR_ARG, "block_size %d outside [1, %d]", block_size, kMaxM);
+    if (n_channels < n_devices || n_irs < 0) return fail(IRB_ERR_ARG, "need at least one channel per device and n_irs >= 0");
+    std::unique_ptr<irb_group> g(new (std::nothrow) irb_group);
+    if (!g) return fail(IRB_ERR_ARG, "out of host memory");
+    g->B = block_size; g->n_chans = n_channels; g->n_irs = n_irs; g->private_irs = n_irs == 0;
+    const int rows = tile_rows(half_size_for_block(block_size));
+    const int tiles = (n_channels + rows - 1) / rows;
+    if (tiles < n_devices) return fail(IRB_ERR_ARG, "%d channels are fewer than one kernel tile (%d channels) per device", n_channels, rows);
+    for (int i = 0; i <= n_devices; ++i) g->begin.push_back(std::min(n_channels, (int) ((long long) tiles * i / n_devices) * rows));
+    for (int i = 0; i < n_devices; ++i) {
+        irb_engine* e = nullptr;
+        const int local = g->begin[i + 1] - g->begin[i];
+        int rc = irb_engine_create(&e, devices[i], block_size, max_partitions, local, g->private_irs ? local : n_irs);
+        if (rc) { for (auto* p : g->eng) irb_engine_destroy(p); return rc; }
+        g->eng.push_back(e);
+        if (g->private_irs) for (int c = 0; c < local; ++c) e->h_ir_of_chan[c] = c;      // channel c convolves with its own IR
+        e->binding_dirty = true;
+    }
+    *out = g.release();
+    return 0;
+}
+int irb_group_destroy(irb_group* g) {
+    if (!g) return 0;
+    for (auto* e : g->eng) irb_engine_destroy(e);
+    delete g;
+    return 0;
+}
+int irb_group_device_count(const irb_group* g) { return g ? (int) g->eng.size() : fail(IRB_ERR_ARG, "group is null"); }
+int irb_group_channel_range(const irb_group* g, int index, int* begin, int* end) {
+    if (!g || index < 0 || index >= (int) g->eng.size()) return fail(IRB_ERR_ARG, "bad group or index");
+    if (begin) *begin = g->begin[index];
+    if (end) *end = g->begin[index + 1];
+    return 0;
+}
+// shared IRs (n_irs > 0): ir_id on every device.  Private IRs (n_irs == 0): ir_id is the CHANNEL whose IR this is.
+int irb_group_set_ir(irb_group* g, int ir_id, const float* left, const float* right, int n_taps) {
+    if (!g) return fail(IRB_ERR_ARG, "group is null");
+    if (g->private_irs) {
+        if (ir_id < 0 || ir_id >= g->n_chans) return fail(IRB_ERR_ARG, "channel %d outside [0, %d)", ir_id, g->n_chans);
+        const int i = g->owner(ir_id);
+        return irb_engine_set_ir(g->eng[i], ir_id - g->begin[i], left, right, n_taps);
+    }
+    for (auto* e : g->eng) { int rc = irb_engine_set_ir(e, ir_id, left, right, n_taps); if (rc) return rc; }
+    return 0;
+}
+int irb_group_stage_ir(irb_group* g, int ir_id, const float* left, const float* right, int n_taps, int n_partitions) {
+    if (!g) return fail(IRB_ERR_ARG, "group is null");
+    if (g->private_irs) {
+        if (ir_id < 0 || ir_id >= g->n_chans) return fail(IRB_ERR_ARG, "channel %d outside [0, %d)", ir_id, g->n_chans);
+        const int i = g->owner(ir_id);
+        return irb_engine_stage_ir(g->eng[i], ir_id - g->begin[i], left, right, n_taps, n_partitions);
+    }
+    for (auto* e : g->eng) { int rc = irb_engine_stage_ir(e, ir_id, left, right, n_taps, n_partitions); if (rc) return rc; }
+    return 0;
+}
+int irb_group_bind(irb_group* g, int chan_begin, int chan_end, int ir_id) {
+    if (!g) return fail(IRB_ERR_ARG, "group is null");
+    if (g->private_irs) return fail(IRB_ERR_STATE, "a group created with n_irs == 0 binds every channel to its own IR");
+    if (chan_begin < 0 || chan_end > g->n_chans || chan_begin > chan_end) return fail(IRB_ERR_ARG, "channel range [%d, %d) outside [0, %d)", chan_begin, chan_end, g->n_chans);
+    for (size_t i = 0; i < g->eng.size(); ++i) {
+        const int b = std::max(chan_begin, g->begin[i]), e = std::min(chan_end, g->begin[i + 1]);
+        if (b < e) { int rc = irb_engine_bind(g->eng[i], b - g->begin[i], e - g->begin[i], ir_id); if (rc) return rc; }
+    }
+    return 0;
+}
+int irb_group_reset(irb_group* g) {
+    if (!g) return fail(IRB_ERR_ARG, "group is null");
+    for (auto* e : g->eng) { int rc = irb_engine_reset(e); if (rc) return rc; }
+    return 0;
+}
+// in/out: HOST [n_blocks][n_channels][block_size] for ALL channels; every device is fed from one thread (enqueue all, then wait all)
+int irb_group_process(irb_group* g, const float* in_host, float* out_host, int n_blocks) {
+    if (!g || !in_host || !out_host) return fail(IRB_ERR_ARG, "null argument");
+    if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
+    const size_t stride = (size_t) g->B * g->n_chans;
+    int rc = 0;
+    size_t started = 0;
+    for (; started < g->eng.size() && !rc; ++started) {
+        const size_t off = (size_t) g->begin[started] * g->B;
+        rc = engine_process_enqueue(g->eng[started], in_host + off, out_host + off, n_blocks, stride, false);
+    }
+    for (size_t i = 0; i < started; ++i) { const int w = engine_process_wait(g->eng[i]); if (!rc) rc = w; }
+    return rc;
+}
+size_t irb_group_state_bytes(const irb_group* g) {
+    size_t n = 0;
+    if (g) for (auto* e : g->eng) n += e->bytes;
+    return n;
+}
+
 }  // extern "C"
+

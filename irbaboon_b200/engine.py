@@ -60,6 +60,16 @@ _SIGS = {
     "irb_launch_count": (ctypes.c_longlong, []),
     "irb_last_compute_ms": (ctypes.c_double, []),
     "irb_engine_mac_only_device": (ctypes.c_int, [_vp, _vp]),
+    "irb_group_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_int)] + [ctypes.c_int] * 5),
+    "irb_group_destroy": (ctypes.c_int, [_vp]),
+    "irb_group_device_count": (ctypes.c_int, [_vp]),
+    "irb_group_channel_range": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "irb_group_set_ir": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int]),
+    "irb_group_stage_ir": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int]),
+    "irb_group_bind": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "irb_group_reset": (ctypes.c_int, [_vp]),
+    "irb_group_process": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
+    "irb_group_state_bytes": (ctypes.c_size_t, [_vp]),
     "irb_convolve_periodic": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_convolve_nonperiodic": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_deconvolve": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
@@ -386,6 +396,70 @@ class Engine:
         out = np.zeros(self.fft_size, np.float32)
         _ck(lib().irb_engine_read_fdl_spectrum(self._h, int(chan), int(age), _ptr(out)))
         return out
+
+
+class Group:
+    """Several GPUs driven from one process: channels sharded by contiguous tile-aligned ranges (irb_group_*).
+    n_irs > 0: shared IRs replicated on every device; n_irs == 0: one private IR per channel, living on its device."""
+
+    def __init__(self, devices, block_size, max_partitions, n_channels, n_irs=1):
+        self._h = _vp()
+        devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        _ck(lib().irb_group_create(ctypes.byref(self._h), devs, len(devices), int(block_size), int(max_partitions), int(n_channels), int(n_irs)))
+        self.block_size, self.n_channels, self.n_irs = block_size, n_channels, n_irs
+
+    def close(self):
+        if self._h:
+            lib().irb_group_destroy(self._h)
+            self._h = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def ranges(self):
+        out = []
+        for i in range(_ck(lib().irb_group_device_count(self._h))):
+            b, e = ctypes.c_int(), ctypes.c_int()
+            _ck(lib().irb_group_channel_range(self._h, i, ctypes.byref(b), ctypes.byref(e)))
+            out.append((b.value, e.value))
+        return out
+
+    def set_ir(self, ir_id, taps):
+        t = np.ascontiguousarray(_planar(taps)[0])
+        _ck(lib().irb_group_set_ir(self._h, int(ir_id), _ptr(t), None, len(t)))
+
+    def stage_ir(self, ir_id, taps, n_partitions=0):
+        t = np.ascontiguousarray(_planar(taps)[0])
+        _ck(lib().irb_group_stage_ir(self._h, int(ir_id), _ptr(t), None, len(t), int(n_partitions)))
+
+    def bind(self, chan_begin, chan_end, ir_id):
+        _ck(lib().irb_group_bind(self._h, int(chan_begin), int(chan_end), int(ir_id)))
+
+    def reset(self):
+        _ck(lib().irb_group_reset(self._h))
+
+    def process(self, x, out=None):
+        x = np.ascontiguousarray(x, np.float32)
+        nb = 1 if x.ndim == 2 else x.shape[0]
+        assert x.shape[-2:] == (self.n_channels, self.block_size), x.shape
+        if out is None:
+            out = np.empty(x.shape, np.float32)
+        _ck(lib().irb_group_process(self._h, _ptr(x), _ptr(out), nb))
+        return out
+
+    @property
+    def state_bytes(self):
+        return lib().irb_group_state_bytes(self._h)
 
 
 def unpack_spectrum(packed):
