@@ -25,6 +25,7 @@ def test_group_equals_single_engine_shared_irs(eng, B, C, n_dev):
         e.set_ir(0, h0); e.set_ir(1, h1)
         e.bind(T, min(C, 3 * T), 1)
         want = e.process(x)
+        e.reset()
         want1 = np.stack([e.process(x[k]) for k in range(nb)])
     with eng.Group(_devices(eng, n_dev), B, P, C, 2) as g:
         r = g.ranges
