@@ -11,6 +11,7 @@
 #include <vector>
 
 struct irb_engine;
+struct irb_group;
 
 namespace fp {
 namespace b200 {
@@ -41,6 +42,24 @@ private:
     irb_engine* engine = nullptr;
     int blockSize, channels;
     std::vector<float> stageIn, stageOut;
+};
+
+// The same over several GPUs driven from this process (irb_group_*): channels are sharded by contiguous ranges, shared IRs are
+// replicated on every device (numIRs > 0) or every channel owns the IR with its own number (numIRs == 0).
+class MultiGpuConvolver {
+public:
+    MultiGpuConvolver(const std::vector<int>& devices, int blockSize, int maxPartitions, int channels, int numIRs = 1);
+    ~MultiGpuConvolver();
+    MultiGpuConvolver(const MultiGpuConvolver&) = delete;
+    MultiGpuConvolver& operator=(const MultiGpuConvolver&) = delete;
+    void setIR(int irId, const AudioBuffer<float>& ir, bool foldStereo = false);
+    void bind(int channelBegin, int channelEnd, int irId);
+    void reset();
+    void process(const float* in, float* out, int nBlocks);   // dense [nBlocks][channels][blockSize] host arrays
+    irb_group* handle() const { return group; }
+
+private:
+    irb_group* group = nullptr;
 };
 
 }  // namespace b200

@@ -161,6 +161,25 @@ void StreamingConvolver::process(const float* in, float* out, int nBlocks) {
     if (irb_engine_process(engine, in, out, nBlocks) != IRB_OK) raise("irb_engine_process");
 }
 
+// ---- MultiGpuConvolver ----------------------------------------------------------------------------------
+MultiGpuConvolver::MultiGpuConvolver(const std::vector<int>& devices, int blockSize, int maxPartitions, int channels, int numIRs) {
+    if (irb_group_create(&group, devices.data(), (int) devices.size(), blockSize, maxPartitions, channels, numIRs) != IRB_OK) raise("irb_group_create");
+}
+MultiGpuConvolver::~MultiGpuConvolver() { irb_group_destroy(group); }
+void MultiGpuConvolver::setIR(int irId, const AudioBuffer<float>& ir, bool foldStereo) {
+    const float* r = (foldStereo && ir.getNumChannels() == 2) ? ir.getReadPointer(1) : nullptr;
+    if (irb_group_set_ir(group, irId, ir.getReadPointer(0), r, ir.getNumSamples()) != IRB_OK) raise("irb_group_set_ir");
+}
+void MultiGpuConvolver::bind(int channelBegin, int channelEnd, int irId) {
+    if (irb_group_bind(group, channelBegin, channelEnd, irId) != IRB_OK) raise("irb_group_bind");
+}
+void MultiGpuConvolver::reset() {
+    if (irb_group_reset(group) != IRB_OK) raise("irb_group_reset");
+}
+void MultiGpuConvolver::process(const float* in, float* out, int nBlocks) {
+    if (irb_group_process(group, in, out, nBlocks) != IRB_OK) raise("irb_group_process");
+}
+
 // ---- PluginConvolver ------------------------------------------------------------------------------------
 PluginConvolver::PluginConvolver(int processBlockSize, int channels_, int device_) : B(processBlockSize), channels(channels_), device(device_) {
     latency = B;                                                                      // PluginProcessor.cpp:59
