@@ -98,6 +98,12 @@ int mac_u_pref() {
     return u;
 }
 
+// FDL loads of the shared-IR kernel as 32-byte LDG.256 with L2 evict-first (IRB_MAC_WIDE=0 selects the 16-byte form)
+bool mac_wide_pref() {
+    static bool w = [] { const char* s = getenv("IRB_MAC_WIDE"); return s ? atoi(s) != 0 : true; }();
+    return w;
+}
+
 template <int M>
 int launch_fwd_t(const irb::FwdArgs& a, cudaStream_t st) {
     constexpr int R = irb::Tile<M>::ROWS;
@@ -108,7 +114,7 @@ int launch_fwd_t(const irb::FwdArgs& a, cudaStream_t st) {
     CK(cudaGetLastError());
     return 0;
 }
-template <int M, int U, bool INV, bool FUSE = false>
+template <int M, int U, bool INV, bool FUSE = false, bool WIDE = false>
 int launch_mac_u(const irb::MacArgs& a, cudaStream_t st) {
     const int grid = (a.n_rows + irb::Tile<M>::ROWS - 1) / irb::Tile<M>::ROWS;
     if (grid <= 0) return 0;
@@ -117,10 +123,10 @@ int launch_mac_u(const irb::MacArgs& a, cudaStream_t st) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
-        CK(cudaFuncSetAttribute(irb::k_mac<M, U, INV, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CK(cudaFuncSetAttribute(irb::k_mac<M, U, INV, FUSE, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         configured_dev = dev;
     }
-    irb::k_mac<M, U, INV, FUSE><<<grid, irb::kThreads + 32, smem, st>>>(a);
+    irb::k_mac<M, U, INV, FUSE, WIDE><<<grid, irb::kThreads + 32, smem, st>>>(a);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
@@ -169,7 +175,12 @@ int launch_slots_t(const irb::MacArgs& a, int cl, cudaStream_t st) {
 template <int M, bool INV>
 int launch_mac_t(const irb::MacArgs& a, bool slots, int cl, cudaStream_t st) {
     if (slots) return launch_slots_t<M, INV>(a, cl, st);
-    if constexpr (INV) { if (a.in) return launch_mac_u<M, 1, true, true>(a, st); }      // forward transform fused into the prologue
+    if constexpr (INV) {
+        if (a.head) {                                   // streaming block step
+            if (mac_wide_pref()) return a.in ? launch_mac_u<M, 1, true, true, true>(a, st) : launch_mac_u<M, 1, true, false, true>(a, st);
+            if (a.in) return launch_mac_u<M, 1, true, true>(a, st);      // forward transform fused into the prologue
+        }
+    }
     if constexpr (M <= 512) { if (mac_u_pref() == 2) return launch_mac_u<M, 2, INV>(a, st); }
     return launch_mac_u<M, 1, INV>(a, st);
 }

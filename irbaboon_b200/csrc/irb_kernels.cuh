@@ -72,6 +72,24 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     return r;
 }
 
+// 32-byte streaming load (sm_100: LDG.E.NA.EFL2.256): read-once FDL data, not allocated in L1, first in line for L2 eviction
+__device__ __forceinline__ void ldg_stream256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+// MAC layout of the shared-IR kernel: a thread owns V float4 of each of K rows (K*V = 4).  Narrow: the float4 are TPR apart
+// (a warp instruction reads 512 contiguous bytes).  WIDE: they come in adjacent pairs, one 32-byte load each (1 KB per warp
+// instruction, half the load instructions for the same bytes in flight).
+template <int M, bool WIDE> struct MacLayout {
+    static constexpr int CH = M > 1024 ? M / 1024 : 1;                    // 32-byte chunks per thread per row (WIDE)
+    static constexpr int V = WIDE ? 2 * CH : Tile<M>::V;
+    static constexpr int TPR = WIDE ? M / (4 * CH) : Tile<M>::TPR;        // threads per row
+    static constexpr int G = kThreads / TPR;
+    static constexpr int K = 4 / V;
+    static_assert(G * K == kTile / M, "the layout covers the tile");
+    __device__ static __forceinline__ int f4(int c0, int vv) { return WIDE ? 2 * (c0 + (vv >> 1) * TPR) + (vv & 1) : c0 + vv * TPR; }
+};
+
 // ---- full M-point transform of the 8 registers of an FFT-layout thread ----------------------------
 template <int M, bool INV, int PASS = 0, int PS = 1>
 __device__ __forceinline__ void fft_run(float2 (&v)[kPts], int t, float2* srow, const float2* __restrict__ W) {
@@ -306,7 +324,7 @@ struct MacSmem {
     uint64_t full[kStages], empty[kStages];
 };
 
-template <int M, int U, bool INV, bool FUSE = false>
+template <int M, int U, bool INV, bool FUSE = false, bool WIDE = false>
 __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const MacArgs a) {
     static_assert(!FUSE || INV, "the fused forward transform belongs to the streaming block step");
     using T = Tile<M>;
@@ -363,9 +381,9 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
             const float* p = a.in + row * a.in_chan_stride;
 #pragma unroll
             for (int j = 0; j < kPts; ++j) {
-                const int m = 2 * (t + j * T::TPF);
-                if (m + 1 < a.B) v[j] = *reinterpret_cast<const float2*>(p + m);
-                else if (m < a.B) v[j].x = p[m];
+                const int m = 2 * (t + j * T::TPF);                  // scalar loads: a row starts at an odd float offset when B is odd
+                if (m < a.B) v[j].x = p[m];
+                if (m + 1 < a.B) v[j].y = p[m + 1];
             }
         }
         float2* srow = sm.spec + rf * M;
@@ -377,13 +395,14 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
     }
 
     // ===== compute threads, MAC layout =====
-    const int g_ = tid / T::TPR, c0 = tid % T::TPR;
-    const float4* xptr[T::K];      // points at the float4 of the next partition to load (partition 0 = the newest slot)
-    int slot[T::K], nvalid[T::K];
-    float4 xa[U][T::K][T::V], xb[U][T::K][T::V];
+    using L = MacLayout<M, WIDE>;
+    const int g_ = tid / L::TPR, c0 = tid % L::TPR;
+    const float4* xptr[L::K];      // row of the next partition to load (partition 0 = the newest slot)
+    int slot[L::K], nvalid[L::K];
+    float4 xa[U][L::K][L::V], xb[U][L::K][L::V];
 #pragma unroll
-    for (int s = 0; s < T::K; ++s) {
-        const int rl = s * T::G + g_, row = row0 + rl;
+    for (int s = 0; s < L::K; ++s) {
+        const int rl = s * L::G + g_, row = row0 + rl;
         nvalid[s] = 0; slot[s] = 0; xptr[s] = nullptr;
         if (row < a.n_rows) {
             const int chan = row / a.blocks_per_chan, blk = row % a.blocks_per_chan;
@@ -391,7 +410,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
             if (a.head) { hd = a.head[chan] - a.head_back; if (hd < 0) hd += a.ring; }
             nvalid[s] = a.head ? np : (blk + 1 < np ? blk + 1 : np);
             slot[s] = hd;
-            xptr[s] = reinterpret_cast<const float4*>(a.fdl + chan * a.fdl_chan_stride + (long long) hd * M) + c0;
+            xptr[s] = reinterpret_cast<const float4*>(a.fdl + chan * a.fdl_chan_stride + (long long) hd * M);
             if constexpr (FUSE) {
                 // packed spectrum of the new block: into the slot after the old head, and kept as partition 0's operand;
                 // the loads below then start at partition 1 = the old head
@@ -399,40 +418,48 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
                 const float2* z = sm.spec + rl * M;
                 float4* d = reinterpret_cast<float4*>(const_cast<float2*>(a.fdl) + chan * a.fdl_chan_stride + (long long) ns * M);
 #pragma unroll
-                for (int vv = 0; vv < T::V; ++vv) {
-                    const int k = 2 * (c0 + vv * T::TPR);
+                for (int vv = 0; vv < L::V; ++vv) {
+                    const int k = 2 * L::f4(c0, vv);
                     const float2 x0 = real_split(z[k], z[(M - k) & (M - 1)], root<false>(a.W, k), k);
                     const float2 x1 = real_split(z[k + 1], z[M - k - 1], root<false>(a.W, k + 1), k + 1);
                     xa[0][s][vv] = make_float4(x0.x, x0.y, x1.x, x1.y);
-                    d[c0 + vv * T::TPR] = xa[0][s][vv];
+                    d[L::f4(c0, vv)] = xa[0][s][vv];
                 }
             }
         } else if constexpr (FUSE) {
 #pragma unroll
-            for (int vv = 0; vv < T::V; ++vv) xa[0][s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int vv = 0; vv < L::V; ++vv) xa[0][s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     if constexpr (FUSE) {
         bar_compute();                                    // every read of the tile and of the old heads is done
         if (tid < T::ROWS && row0 + tid < a.n_rows) { const int h = a.head_rw[row0 + tid] + 1; a.head_rw[row0 + tid] = h >= a.ring ? 0 : h; }
     }
-    float4 acc[T::K][T::V];
+    float4 acc[L::K][L::V];
 #pragma unroll
-    for (int s = 0; s < T::K; ++s)
+    for (int s = 0; s < L::K; ++s)
 #pragma unroll
-        for (int vv = 0; vv < T::V; ++vv) acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int vv = 0; vv < L::V; ++vv) acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    auto load_group = [&](float4 (&x)[U][T::K][T::V], int g) {
+    auto load_group = [&](float4 (&x)[U][L::K][L::V], int g) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int p = g * U + u;
             if (FUSE && p == 0) continue;                 // partition 0 already sits in xa[0] (registers)
 #pragma unroll
-            for (int s = 0; s < T::K; ++s) {
+            for (int s = 0; s < L::K; ++s) {
                 const bool ok = p < nvalid[s];
+                if constexpr (WIDE) {
 #pragma unroll
-                for (int vv = 0; vv < T::V; ++vv)
-                    x[u][s][vv] = ok ? ldg_stream(xptr[s] + vv * T::TPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int vv = 0; vv < L::V; vv += 2) {
+                        x[u][s][vv] = x[u][s][vv + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) ldg_stream256(xptr[s] + L::f4(c0, vv), x[u][s][vv], x[u][s][vv + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int vv = 0; vv < L::V; ++vv)
+                        x[u][s][vv] = ok ? ldg_stream(xptr[s] + L::f4(c0, vv)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 // step one slot back in the ring (wrap to the top)
                 if (ok) {
                     if (slot[s] == 0) { slot[s] = a.ring - 1; xptr[s] += (long long) (a.ring - 1) * (M / 2); }
@@ -441,20 +468,20 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
             }
         }
     };
-    auto consume_group = [&](float4 (&x)[U][T::K][T::V], int g) {
+    auto consume_group = [&](float4 (&x)[U][L::K][L::V], int g) {
         const int st = g % kStages;
         mbar_wait(&sm.full[st], (g / kStages) & 1);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (g * U + u < pmax) {
 #pragma unroll
-                for (int vv = 0; vv < T::V; ++vv) {
-                    const int c = c0 + vv * T::TPR;
+                for (int vv = 0; vv < L::V; ++vv) {
+                    const int c = L::f4(c0, vv);
                     const float4 h = *reinterpret_cast<const float4*>(&sm.h[st][u][2 * c]);
                     // bin 0 is the packed {DC, Nyquist} pair: two real products instead of a complex one
                     const float h0i = c == 0 ? 0.f : h.y, h0q = c == 0 ? h.y : h.x;
 #pragma unroll
-                    for (int s = 0; s < T::K; ++s) {
+                    for (int s = 0; s < L::K; ++s) {
                         const float4 xv = x[u][s][vv];
                         float4& ac = acc[s][vv];
                         ac.x = fmaf(xv.x, h.x, fmaf(-xv.y, h0i, ac.x));
@@ -481,20 +508,20 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
 
     if constexpr (!INV) {
 #pragma unroll
-        for (int s = 0; s < T::K; ++s) {
-            const int row = row0 + s * T::G + g_;
+        for (int s = 0; s < L::K; ++s) {
+            const int row = row0 + s * L::G + g_;
             if (row >= a.n_rows) continue;
 #pragma unroll
-            for (int vv = 0; vv < T::V; ++vv)
-                reinterpret_cast<float4*>(a.Y + (long long) row * M)[c0 + vv * T::TPR] = acc[s][vv];
+            for (int vv = 0; vv < L::V; ++vv)
+                reinterpret_cast<float4*>(a.Y + (long long) row * M)[L::f4(c0, vv)] = acc[s][vv];
         }
     } else {
         // ---- accumulators -> shared tile (MAC layout), then inverse real FFT in FFT layout ----
 #pragma unroll
-        for (int s = 0; s < T::K; ++s)
+        for (int s = 0; s < L::K; ++s)
 #pragma unroll
-            for (int vv = 0; vv < T::V; ++vv)
-                reinterpret_cast<float4*>(sm.spec + (s * T::G + g_) * M)[c0 + vv * T::TPR] = acc[s][vv];
+            for (int vv = 0; vv < L::V; ++vv)
+                reinterpret_cast<float4*>(sm.spec + (s * L::G + g_) * M)[L::f4(c0, vv)] = acc[s][vv];
         bar_compute();
         inv_epilogue<M>(a, sm.spec, tid, row0, T::ROWS);
     }
@@ -538,9 +565,10 @@ __device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <int M, bool INV>
+template <int M, bool INV, bool WIDE = true>
 __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a) {
     using T = Tile<M>;
+    using L = MacLayout<M, WIDE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SlotSmem<M>& sm = *reinterpret_cast<SlotSmem<M>*>(smem_raw);
     const int tid = threadIdx.x;
@@ -595,12 +623,12 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
         }
     } else {
         // ===== compute threads, MAC layout: thread owns V float4 of the K slots s*G + g_ =====
-        const int g_ = tid / T::TPR, c0 = tid % T::TPR;
-        const float4* xptr[T::K];
-        int slot[T::K], nvalid[T::K];
+        const int g_ = tid / L::TPR, c0 = tid % L::TPR;
+        const float4* xptr[L::K];
+        int slot[L::K], nvalid[L::K];
 #pragma unroll
-        for (int s = 0; s < T::K; ++s) {
-            const int sl = s * T::G + g_;
+        for (int s = 0; s < L::K; ++s) {
+            const int sl = s * L::G + g_;
             const int row = row0 + sl / split_in;
             nvalid[s] = sm.pcnt[sl]; slot[s] = 0; xptr[s] = nullptr;
             if (nvalid[s] > 0) {
@@ -608,38 +636,46 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
                 int hd = a.head[chan] - a.head_back - sm.pbeg[sl];      // partition p meets slot (head - p) mod ring
                 while (hd < 0) hd += a.ring;
                 slot[s] = hd;
-                xptr[s] = reinterpret_cast<const float4*>(a.fdl + chan * a.fdl_chan_stride + (long long) hd * M) + c0;
+                xptr[s] = reinterpret_cast<const float4*>(a.fdl + chan * a.fdl_chan_stride + (long long) hd * M);
             }
         }
-        float4 acc[T::K][T::V];
+        float4 acc[L::K][L::V];
 #pragma unroll
-        for (int s = 0; s < T::K; ++s)
+        for (int s = 0; s < L::K; ++s)
 #pragma unroll
-            for (int vv = 0; vv < T::V; ++vv) acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int vv = 0; vv < L::V; ++vv) acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        float4 xa[T::K][T::V], xb[T::K][T::V];
-        auto load_group = [&](float4 (&x)[T::K][T::V], int g) {
+        float4 xa[L::K][L::V], xb[L::K][L::V];
+        auto load_group = [&](float4 (&x)[L::K][L::V], int g) {
 #pragma unroll
-            for (int s = 0; s < T::K; ++s) {
+            for (int s = 0; s < L::K; ++s) {
                 const bool ok = g < nvalid[s];
+                if constexpr (WIDE) {
 #pragma unroll
-                for (int vv = 0; vv < T::V; ++vv) x[s][vv] = ok ? ldg_stream(xptr[s] + vv * T::TPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int vv = 0; vv < L::V; vv += 2) {
+                        x[s][vv] = x[s][vv + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) ldg_stream256(xptr[s] + L::f4(c0, vv), x[s][vv], x[s][vv + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int vv = 0; vv < L::V; ++vv) x[s][vv] = ok ? ldg_stream(xptr[s] + L::f4(c0, vv)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 if (ok) {
                     if (slot[s] == 0) { slot[s] = a.ring - 1; xptr[s] += (long long) (a.ring - 1) * (M / 2); }
                     else { --slot[s]; xptr[s] -= M / 2; }
                 }
             }
         };
-        auto consume_group = [&](float4 (&x)[T::K][T::V], int g) {
+        auto consume_group = [&](float4 (&x)[L::K][L::V], int g) {
             const int st = g % kStages;
             mbar_wait(&sm.full[st], (g / kStages) & 1);
 #pragma unroll
-            for (int vv = 0; vv < T::V; ++vv) {
-                const int c = c0 + vv * T::TPR;
+            for (int vv = 0; vv < L::V; ++vv) {
+                const int c = L::f4(c0, vv);
 #pragma unroll
-                for (int s = 0; s < T::K; ++s) {
+                for (int s = 0; s < L::K; ++s) {
                     if (g >= nvalid[s]) continue;          // this slot's range is shorter: its stage entry was not filled
-                    const float4 h = *reinterpret_cast<const float4*>(&sm.h[st][s * T::G + g_][2 * c]);
+                    const float4 h = *reinterpret_cast<const float4*>(&sm.h[st][s * L::G + g_][2 * c]);
                     const float h0i = c == 0 ? 0.f : h.y, h0q = c == 0 ? h.y : h.x;    // bin 0 = packed {DC, Nyquist}
                     const float4 xv = x[s][vv];
                     float4& ac = acc[s][vv];
@@ -663,18 +699,18 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
         }
         if (!INV && nsplit == 1) {
 #pragma unroll
-            for (int s = 0; s < T::K; ++s) {
-                const int row = row0 + s * T::G + g_;
+            for (int s = 0; s < L::K; ++s) {
+                const int row = row0 + s * L::G + g_;
                 if (row >= a.n_rows) continue;
 #pragma unroll
-                for (int vv = 0; vv < T::V; ++vv) reinterpret_cast<float4*>(a.Y + (long long) row * M)[c0 + vv * T::TPR] = acc[s][vv];
+                for (int vv = 0; vv < L::V; ++vv) reinterpret_cast<float4*>(a.Y + (long long) row * M)[L::f4(c0, vv)] = acc[s][vv];
             }
         } else {
 #pragma unroll
-            for (int s = 0; s < T::K; ++s)
+            for (int s = 0; s < L::K; ++s)
 #pragma unroll
-                for (int vv = 0; vv < T::V; ++vv)
-                    reinterpret_cast<float4*>(sm.spec + (s * T::G + g_) * M)[c0 + vv * T::TPR] = acc[s][vv];
+                for (int vv = 0; vv < L::V; ++vv)
+                    reinterpret_cast<float4*>(sm.spec + (s * L::G + g_) * M)[L::f4(c0, vv)] = acc[s][vv];
         }
     }
     if (!INV && nsplit == 1) return;

@@ -178,7 +178,7 @@ def test_callback_order_matches_oracle_when_host_block_exceeds_B(eng, orc, B, H,
 
 
 # ---- one launch per block step: forward transform fused into the MAC kernel --------------------------------------
-@pytest.mark.parametrize("B,C,Lh", [(512, 300, 512 * 9 + 5), (256, 1200, 256 * 3), (1024, 150, 1024 * 5), (2048, 160, 2048 * 2 + 1), (64, 5000, 64 * 7), (100, 2000, 900)])
+@pytest.mark.parametrize("B,C,Lh", [(512, 300, 512 * 9 + 5), (256, 1200, 256 * 3), (1024, 150, 1024 * 5), (2048, 160, 2048 * 2 + 1), (64, 5000, 64 * 7), (100, 2000, 900), (101, 1500, 700), (33, 9000, 100)])
 def test_fused_step_is_bit_identical_to_two_launches_and_matches_oracle(eng, orc, B, C, Lh):
     n = 7 * B
     x = np.stack([synth.white_noise(1009, c % 5, n) for c in range(C)])
