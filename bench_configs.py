@@ -7,6 +7,8 @@ configs[2]): one JSON object per configuration, written to stdout and, with --ou
   c4  S streams with per-stream 10 s IRs (480k taps), B=1024 (per-row-IR MAC kernel); S defaults to what one GPU holds
   c5  batched ESS IR capture: 2^20-sample sweep captures deconvolved by spectral division
 
+The CPU reference legs (c1, c5) run the reference's own object code (oracle/_ref) as the reported baseline and as the
+checker, exactly like bench.py's cpu_baseline leg -- never as the thing measured as "ours".
 Synthetic inputs (irbaboon_b200/synth.py).  Times are CUDA-event device times where the library records them and
 wall-clock around the C-ABI call otherwise (stated per entry).
 """

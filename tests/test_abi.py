@@ -35,7 +35,8 @@ def test_hot_kernel_uses_bulk_tma_and_128bit_loads(eng):
     import subprocess
     sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", eng.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS.ARRIVE.TRANS64" in sass          # cp.async.bulk + mbarrier expect_tx
-    assert re.search(r"LDG\.E\.[A-Z.]*128", sass)                       # 16-byte FDL loads
+    assert re.search(r"LDG\.E\.[A-Z0-9.]*256", sass)                    # 32-byte FDL loads (sm_100 LDG.256, L2 evict-first)
+    assert re.search(r"LDG\.E\.[A-Z.]*128", sass)                       # the 16-byte form is still there for A/B
     assert "HMMA" not in sass and "UTCHMMA" not in sass
     ldd = subprocess.run(["ldd", eng.LIB_PATH], capture_output=True, text=True).stdout
     assert "cufft" not in ldd.lower()
