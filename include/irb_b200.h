@@ -146,7 +146,8 @@ size_t irb_group_state_bytes(const irb_group* g);
 /* ---- offline functions ------------------------------------------------------------------------------
  * fp::convolution::convolvePeriodic (fp/convolution.hpp:31, fp/convolution.cpp:14-242): planar
  * x[ch_x][len_x], h[ch_h][len_h] -> out[ch_x][len_x+len_h-1].  Same channel layouts (mono/stereo x
- * mono/stereo), partition count, iteration count and unflushed tail as the reference. */
+ * mono/stereo), partition count, iteration count and unflushed tail as the reference.  Any block_size >= 1: sizes above
+ * irb_max_block_size() are computed with the largest block the kernels take and cut at the reference's output length. */
 int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, int ch_h, int len_h, int block_size, float* out);
 
 

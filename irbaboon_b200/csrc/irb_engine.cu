@@ -868,21 +868,28 @@ int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, i
     memset(out, 0, sizeof(float) * (size_t) ch_x * Lout);
     if (!((ch_x == 1 || ch_x == 2) && (ch_h == 1 || ch_h == 2)))
         return fail(IRB_ERR_LAYOUT, "audio has %d channels and the IR %d: only mono/stereo layouts exist (fp/convolution.cpp:28-42)", ch_x, ch_h);
-    const int B = block_size;
-    if (B < 1 || half_size_for_block(B) > kMaxM) return fail(IRB_ERR_ARG, "block_size %d outside [1, %d]", B, kMaxM);
+    if (block_size < 1) return fail(IRB_ERR_ARG, "block_size %d < 1", block_size);
     if (Lout > 0x7fffffffLL) return fail(IRB_ERR_ARG, "output too long");
     CK(cudaSetDevice(irbh::g_device));
+    // What the reference's block size decides about the RESULT is only how much of the linear convolution gets written:
+    // iters = Lx/B + P blocks, the last overlap never flushed (:104-233,233-238).  Every sample before that point is the
+    // same linear convolution for any partitioning, so block sizes above the block kernels' range are
+    // computed with the largest supported block and cut at the reference's length.
+    const int P_ref = (int) std::ceil((float) len_h / (float) block_size);
+    const long long iters_ref = (long long) len_x / block_size + P_ref;
+    const long long Lw = Lout < iters_ref * block_size ? Lout : iters_ref * block_size;
+    const bool native = half_size_for_block(block_size) <= kMaxM;
+    const int B = native ? block_size : kMaxM;
     const int M = half_size_for_block(B);
     const float2* W = nullptr;
     int rc = irbh::twiddles(irbh::g_device, M, &W);
     if (rc) return rc;
     const int P = (int) std::ceil((float) len_h / (float) B);
-    const int iters = len_x / B + P;                       // the do-while of :104-233
+    const int iters = native ? (int) iters_ref : (int) ((Lw + B - 1) / B);      // blocks past the input are zero blocks
     const int rows = tile_rows(M);
     const int bpc = (iters + rows - 1) / rows * rows;      // padded so no tile straddles two channels
     const bool fold = (ch_h == 2 && ch_x == 1);            // IRStereoAudioMono: (L+R)/2, :120-121
     const int n_ir = (ch_h == 2 && ch_x == 2) ? 2 : 1;     // IRStereoAudioStereo is channel-wise, :176-181
-    const long long Lw = Lout < (long long) iters * B ? Lout : (long long) iters * B;   // the tail is never flushed, :233-238
 
     cudaStream_t st = nullptr;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));

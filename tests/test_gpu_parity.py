@@ -66,6 +66,19 @@ def test_convolve_periodic_block_sizes(eng, orc, B):
     _check(eng.convolve_periodic(x, h, B), orc.convolve_periodic(x, h, B))
 
 
+@pytest.mark.parametrize("Lx,Lh,B", [(20000, 3000, 4096), (20000, 9000, 5000), (50000, 70000, 16384), (3000, 500, 30000), (8192, 8192, 8192)])
+def test_convolve_periodic_block_sizes_above_the_block_kernels(eng, orc, Lx, Lh, B):
+    """processBlockSize > 2048: the samples are those of any other partitioning (KA4); what the reference's block size
+    decides is where the output stops (iters*B, the unflushed tail) -- reproduced exactly."""
+    x = synth.white_noise(1001, 2, Lx)
+    h = synth.decaying_ir(2002, Lh)
+    want = orc.convolve_periodic(x, h, B)
+    got = eng.convolve_periodic(x, h, B)
+    _check(got, want)
+    written = min(Lx + Lh - 1, orc.periodic_iterations(Lx, Lh, B) * B)
+    assert not got[:, written:].any() and (written == 0 or got[0, written - 1] != 0 or want[0, written - 1] == 0)
+
+
 @pytest.mark.parametrize("chx,chh", [(1, 1), (2, 1), (1, 2), (2, 2)])
 def test_convolve_periodic_channel_layouts(eng, orc, chx, chh):
     x = np.stack([synth.white_noise(1001, c, 3000) for c in range(chx)])
