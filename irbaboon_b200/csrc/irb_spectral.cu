@@ -18,7 +18,7 @@ using irbh::fail;
 using irbh::g_launches;
 
 constexpr int kMinM = 8;                 // smallest half size the Stockham passes take (N = 16)
-constexpr int kMaxBigM = 1 << 20;        // N up to 2^21
+constexpr int kMaxBigM = 1 << 21;        // N up to 2^22 (87 s at 48 kHz)
 
 template <int L, bool INV>
 int launch_line_t(const irb::LineArgs& a, int batch, cudaStream_t st) {
@@ -91,6 +91,7 @@ struct Plan {
             while ((1 << lg) < M) ++lg;
             M1 = 1 << (lg / 2);
             M2 = M / M1;
+            if (M2 > 1024) { M2 = 1024; M1 = M / M2; }           // rows stay within the row-pair kernel's range; columns take up to 2048
             if ((rc = irbh::twiddles(dev, M1, &W1)) || (rc = irbh::twiddles(dev, M2, &W2)) || (rc = irbh::twiddles2(dev, M, &Thi, &Tlo)) ||
                 (rc = irbh::twiddles2(dev, 2 * M, &Nhi, &Nlo)))
                 return rc;
@@ -222,7 +223,7 @@ struct Smoother {
 int fft_size_for(int len, int* N) {
     int n = irbh::next_pow2(len);
     if (n < 2 * kMinM) return fail(IRB_ERR_ARG, "length %d gives an FFT of %d points; the device transforms start at %d", len, n, 2 * kMinM);
-    if (n > 2 * kMaxBigM) return fail(IRB_ERR_ARG, "length %d needs an FFT above 2^21 points", len);
+    if (n > 2 * kMaxBigM) return fail(IRB_ERR_ARG, "length %d needs an FFT above 2^22 points", len);
     *N = n;
     return 0;
 }
@@ -239,7 +240,7 @@ int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h
         return fail(IRB_ERR_LAYOUT, "audio has %d channels and the IR %d: only mono/stereo layouts exist (fp/convolution.cpp:259-275)", ch_x, ch_h);
     const long long Lout = (long long) len_x + len_h - 1;
     int N = 1;
-    while (N < Lout) { N *= 2; if (N > 2 * kMaxBigM) return fail(IRB_ERR_ARG, "result of %lld samples needs an FFT above 2^21 points", Lout); }
+    while (N < Lout) { N *= 2; if (N > 2 * kMaxBigM) return fail(IRB_ERR_ARG, "result of %lld samples needs an FFT above 2^22 points", Lout); }
     if (N < 2 * kMinM) N = 2 * kMinM;                    // a longer zero-padded transform yields the same linear convolution
     const int M = N / 2, dev = irbh::current_device();
     CK(cudaSetDevice(dev));

@@ -1,7 +1,7 @@
 // irb_spectral.cuh -- sm_100a kernels of the single large real FFT path: fp::convolution::convolveNonPeriodic
 // (fp/convolution.cpp:246-347), deconvolve (:351-403), averagingFilter (:406-546), tools::fftTransform /
 // fftInvTransform (fp/tools.cpp:321-369).  These replace the third-party juce::dsp::FFT calls at
-// fp/convolution.cpp:286-288,308,315,336 and fp/tools.cpp:331-335,359-363 for N = 2^4 ... 2^21.
+// fp/convolution.cpp:286-288,308,315,336 and fp/tools.cpp:331-335,359-363 for N = 2^4 ... 2^22.
 //
 // An N-point real transform is one M = N/2 point complex FFT of z[n] = x[2n] + i x[2n+1] plus a split pass.
 // M <= 2048 is one shared-memory Stockham FFT per line.  Larger M = M1*M2 is the four-step scheme in two

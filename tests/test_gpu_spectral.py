@@ -18,7 +18,7 @@ def _check(got, want, tol=TOL, l2tol=None):
 
 
 # ---- tools::fftTransform / fftInvTransform: every size class (one pass, two passes) ---------------------
-@pytest.mark.parametrize("n", [16, 17, 100, 1000, 4096, 5000, 8192, 16384, 70000, 1 << 17, (1 << 18) + 5])
+@pytest.mark.parametrize("n", [16, 17, 100, 1000, 4096, 5000, 8192, 16384, 70000, 1 << 17, (1 << 18) + 5, (1 << 20) + 1, (1 << 21) + 77])
 def test_fft_transform_matches_float64(eng, n):
     x = synth.white_noise(1005, n, n)
     got = eng.fft_transform(x)
@@ -57,7 +57,7 @@ def test_fft_sizes_outside_range_are_rejected(eng):
 
 
 # ---- convolveNonPeriodic ----------------------------------------------------------------------------------
-@pytest.mark.parametrize("Lx,Lh", [(1, 1), (10, 3), (1500, 600), (4096, 4096), (5000, 30000), (100000, 48000)])
+@pytest.mark.parametrize("Lx,Lh", [(1, 1), (10, 3), (1500, 600), (4096, 4096), (5000, 30000), (100000, 48000), (2500000, 96000)])
 def test_convolve_nonperiodic_lengths(eng, orc, Lx, Lh):
     x = synth.white_noise(1001, 0, Lx)
     h = synth.decaying_ir(2000, Lh)
