@@ -177,10 +177,14 @@ int launch_mac_t(const irb::MacArgs& a, bool slots, int cl, cudaStream_t st) {
     if (slots) return launch_slots_t<M, INV>(a, cl, st);
     if constexpr (INV) {
         if (a.head) {                                   // streaming block step
+            if constexpr (M <= 512) {
+                if (mac_wide_pref() && mac_u_pref() == 2) return a.in ? launch_mac_u<M, 2, true, true, true>(a, st) : launch_mac_u<M, 2, true, false, true>(a, st);
+            }
             if (mac_wide_pref()) return a.in ? launch_mac_u<M, 1, true, true, true>(a, st) : launch_mac_u<M, 1, true, false, true>(a, st);
             if (a.in) return launch_mac_u<M, 1, true, true>(a, st);      // forward transform fused into the prologue
         }
     }
+    if constexpr (!INV) { if (a.head && mac_wide_pref()) return launch_mac_u<M, 1, false, false, true>(a, st); }   // the bare MAC (measurement)
     if constexpr (M <= 512) { if (mac_u_pref() == 2) return launch_mac_u<M, 2, INV>(a, st); }
     return launch_mac_u<M, 1, INV>(a, st);
 }
