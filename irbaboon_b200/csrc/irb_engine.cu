@@ -212,6 +212,10 @@ int tile_rows(int M) { return irb::kTile / M; }
 
 struct irb_engine {
     int device = 0, B = 0, M = 0, ring = 0, n_chans = 0, n_irs = 0;
+    // FDL layout [chan / fdl_group][slot][chan % fdl_group][M], fdl_group = channels per kernel tile (irb_kernels.cuh, MacArgs)
+    int fdl_group = 1;
+    long long fdl_group_stride() const { return (long long) ring * fdl_group * M; }
+    size_t fdl_bytes() const { return sizeof(float2) * (size_t) ((n_chans + fdl_group - 1) / fdl_group) * (size_t) fdl_group_stride(); }
     cudaStream_t own_stream = nullptr, stream = nullptr;
     const float2* W = nullptr;
     DevBuf fdl, H, ov, head, ir_of_chan, nparts, io_in[2], io_out[2], taps;
@@ -310,7 +314,8 @@ int engine_check_binding(irb_engine* e) {
 // Every launch helper takes a channel range [c0, c0 + cn): all per-channel arrays are offset, so a kernel sees rows
 // 0 .. cn-1.  c0 is a multiple of the tile's row count (tiles never straddle a range).
 void fill_mac_args(irb_engine* e, irb::MacArgs& m, int c0, int cn) {
-    m.fdl = e->fdl.as<float2>() + (size_t) c0 * e->ring * e->M; m.fdl_chan_stride = (long long) e->ring * e->M;
+    m.fdl = e->fdl.as<float2>() + (size_t) (c0 / e->fdl_group) * e->fdl_group_stride(); m.fdl_chan_stride = e->fdl_group_stride();
+    m.fdl_group = e->fdl_group; m.fdl_slot_stride = (long long) e->fdl_group * e->M;
     m.head = e->head.as<int>() + c0; m.ring = e->ring; m.blocks_per_chan = 1; m.n_rows = cn;
     m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
     m.ir_of_chan = e->ir_of_chan.as<int>() + c0; m.nparts = e->nparts.as<int>(); m.W = e->W;
@@ -326,7 +331,8 @@ int engine_launch_fwd(irb_engine* e, const float* in_dev, bool audio, bool refre
     irb::FwdArgs f{};
     f.src = in_dev ? in_dev + (size_t) c0 * e->B : nullptr; f.src2 = nullptr; f.src_chan_stride = e->B; f.L = e->B; f.B = e->B;
     f.blocks_per_chan = 1; f.n_rows = audio ? cn : 0;
-    f.dst = e->fdl.as<float2>() + (size_t) c0 * e->ring * e->M; f.dst_chan_stride = (long long) e->ring * e->M;
+    f.dst = e->fdl.as<float2>() + (size_t) (c0 / e->fdl_group) * e->fdl_group_stride(); f.dst_chan_stride = e->fdl_group_stride();
+    f.dst_group = e->fdl_group; f.dst_slot_stride = (long long) e->fdl_group * e->M;
     f.head = e->head.as<int>() + c0; f.ring = e->ring; f.W = e->W;
     // one IR partition of every staged IR is re-transformed per block, in the same launch
     f.n_rr = refresh ? (int) e->h_rr_list.size() : 0; f.rr_list = e->rr_list.as<int>(); f.rr_taps = e->rr_ptrs.as<const float*>();
@@ -411,7 +417,9 @@ int irb_engine_create(irb_engine** out, int device, int block_size, int max_part
     int rc = irbh::twiddles(device, e->M, &e->W);
     if (rc) { delete e; return rc; }
     const size_t spec = sizeof(float2) * (size_t) e->M;
-    const size_t b_fdl = spec * e->ring * n_channels, b_H = spec * e->ring * n_irs, b_io = sizeof(float) * (size_t) e->B * n_channels;
+    static const bool plain_fdl = getenv("IRB_FDL_PLAIN") != nullptr;        // A/B: [chan][slot][M] instead of the tile-interleaved layout
+    e->fdl_group = plain_fdl ? 1 : tile_rows(e->M);
+    const size_t b_fdl = e->fdl_bytes(), b_H = spec * e->ring * n_irs, b_io = sizeof(float) * (size_t) e->B * n_channels;
     if ((rc = e->fdl.alloc(b_fdl, true)) || (rc = e->H.alloc(b_H, true)) || (rc = e->ov.alloc(b_io, true)) ||
         (rc = e->head.alloc(sizeof(int) * n_channels, false)) || (rc = e->ir_of_chan.alloc(sizeof(int) * n_channels, true)) ||
         (rc = e->nparts.alloc(sizeof(int) * n_irs, true)) || (rc = e->io_in[0].alloc(b_io, true)) || (rc = e->io_out[0].alloc(b_io, true)) ||
@@ -460,7 +468,7 @@ int irb_engine_reset(irb_engine* e) {
     if (!e) return fail(IRB_ERR_ARG, "engine is null");
     CK(cudaSetDevice(e->device));
     const size_t spec = sizeof(float2) * (size_t) e->M;
-    CK(cudaMemsetAsync(e->fdl.p, 0, spec * e->ring * e->n_chans, e->stream));
+    CK(cudaMemsetAsync(e->fdl.p, 0, e->fdl_bytes(), e->stream));
     CK(cudaMemsetAsync(e->ov.p, 0, sizeof(float) * (size_t) e->B * e->n_chans, e->stream));
     std::vector<int> h(e->n_chans, e->ring - 1);     // first block lands in slot 0
     CK(cudaMemcpyAsync(e->head.p, h.data(), sizeof(int) * e->n_chans, cudaMemcpyHostToDevice, e->stream));
@@ -817,7 +825,8 @@ int irb_engine_read_fdl_spectrum(irb_engine* e, int chan, int age, float* out_pa
     int head = 0;
     CK(cudaMemcpy(&head, e->head.as<int>() + chan, sizeof(int), cudaMemcpyDeviceToHost));
     const int slot = ((head - age) % e->ring + e->ring) % e->ring;
-    CK(cudaMemcpy(out_packed, e->fdl.as<float2>() + ((size_t) chan * e->ring + slot) * e->M, sizeof(float2) * e->M, cudaMemcpyDeviceToHost));
+    const size_t off = (size_t) (chan / e->fdl_group) * e->fdl_group_stride() + ((size_t) slot * e->fdl_group + chan % e->fdl_group) * e->M;
+    CK(cudaMemcpy(out_packed, e->fdl.as<float2>() + off, sizeof(float2) * e->M, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -118,7 +118,9 @@ struct FwdArgs {
     int blocks_per_chan;
     int n_rows;
     float2* dst;               // packed spectra
-    long long dst_chan_stride; // float2 units
+    long long dst_chan_stride; // float2 units between channel groups
+    int dst_group;             // channels per group (0/1: plain [chan][slot][M]); see MacArgs::fdl_group
+    long long dst_slot_stride; // float2 units between slots (0: M)
     int* head;                 // per-chan ring head (nullable)
     int ring;                  // ring slots per chan
     const float2* W;           // N = 2M roots of unity
@@ -151,7 +153,8 @@ __device__ __forceinline__ FwdRow fwd_row(const FwdArgs& a, int main_tiles, int 
         w.q = a.src2 ? a.src2 + off : nullptr;
         int slot = blk;
         if (a.head) { slot = a.head[chan] + 1; if (slot >= a.ring) slot = 0; }
-        w.d = a.dst + chan * a.dst_chan_stride + (long long) slot * M;
+        const int grp = a.dst_group > 1 ? a.dst_group : 1;
+        w.d = a.dst + (chan / grp) * a.dst_chan_stride + (long long) (chan % grp) * M + (long long) slot * (a.dst_slot_stride ? a.dst_slot_stride : M);
     } else {
         const int i = (tile - main_tiles) * ROWS + r;
         if (i >= a.n_rr) return w;
@@ -236,8 +239,13 @@ __global__ void __launch_bounds__(kThreads) k_fwd(const FwdArgs a) {
 // k_mac: Y[row][bin] = sum_{p < nvalid} FDL[row][(head - p) mod ring][bin] * H[ir][p][bin], ascending p
 // (the summation order of fp/convolution.cpp:171-202), then -- when INV -- inverse FFT and overlap-add.
 struct MacArgs {
-    const float2* fdl;         // packed spectra rows: fdl + chan*fdl_chan_stride + slot*M
-    long long fdl_chan_stride; // float2 units
+    // packed spectra rows.  Plain layout [chan][slot][M]: fdl + chan*fdl_chan_stride + slot*M.  Streaming engine: the
+    // fdl_group = ROWS channels of a kernel tile are interleaved per slot, [chan/ROWS][slot][chan%ROWS][M], so one block
+    // step reads ONE contiguous ROWS*M*8-byte piece per tile and partition (16 KB) instead of ROWS pieces 0.8 MB apart.
+    const float2* fdl;
+    long long fdl_chan_stride; // float2 units between channel groups
+    int fdl_group;             // channels per group (0/1: plain layout)
+    long long fdl_slot_stride; // float2 units between slots (0: M)
     const int* head;           // per-chan newest slot; nullptr => head = blk (offline: block index)
     int ring;                  // slots per chan (wrap); offline: unused because nvalid <= blk+1
     int blocks_per_chan;
@@ -315,6 +323,12 @@ __device__ __forceinline__ void inv_epilogue(const MacArgs& a, float2* tile, int
         }
     }
 }
+
+__device__ __forceinline__ long long fdl_row_offset(const MacArgs& a, int chan, int M) {
+    const int grp = a.fdl_group > 1 ? a.fdl_group : 1;
+    return (chan / grp) * a.fdl_chan_stride + (long long) (chan % grp) * M;
+}
+template <int M> __device__ __forceinline__ long long fdl_slot_stride(const MacArgs& a) { return a.fdl_slot_stride ? a.fdl_slot_stride : M; }
 
 // Shared-IR kernel: the whole tile is bound to one IR and a ring stage holds U consecutive partitions of it.
 template <int M, int U>
@@ -410,13 +424,13 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
             if (a.head) { hd = a.head[chan] - a.head_back; if (hd < 0) hd += a.ring; }
             nvalid[s] = a.head ? np : (blk + 1 < np ? blk + 1 : np);
             slot[s] = hd;
-            xptr[s] = reinterpret_cast<const float4*>(a.fdl + chan * a.fdl_chan_stride + (long long) hd * M);
+            xptr[s] = reinterpret_cast<const float4*>(a.fdl + fdl_row_offset(a, chan, M) + (long long) hd * fdl_slot_stride<M>(a));
             if constexpr (FUSE) {
                 // packed spectrum of the new block: into the slot after the old head, and kept as partition 0's operand;
                 // the loads below then start at partition 1 = the old head
                 const int ns = hd + 1 >= a.ring ? 0 : hd + 1;
                 const float2* z = sm.spec + rl * M;
-                float4* d = reinterpret_cast<float4*>(const_cast<float2*>(a.fdl) + chan * a.fdl_chan_stride + (long long) ns * M);
+                float4* d = reinterpret_cast<float4*>(const_cast<float2*>(a.fdl) + fdl_row_offset(a, chan, M) + (long long) ns * fdl_slot_stride<M>(a));
 #pragma unroll
                 for (int vv = 0; vv < L::V; ++vv) {
                     const int k = 2 * L::f4(c0, vv);
@@ -441,6 +455,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
 #pragma unroll
         for (int vv = 0; vv < L::V; ++vv) acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    const long long sstep = fdl_slot_stride<M>(a) / 2;    // float4 between ring slots
     auto load_group = [&](float4 (&x)[U][L::K][L::V], int g) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -462,8 +477,8 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
                 }
                 // step one slot back in the ring (wrap to the top)
                 if (ok) {
-                    if (slot[s] == 0) { slot[s] = a.ring - 1; xptr[s] += (long long) (a.ring - 1) * (M / 2); }
-                    else { --slot[s]; xptr[s] -= M / 2; }
+                    if (slot[s] == 0) { slot[s] = a.ring - 1; xptr[s] += (long long) (a.ring - 1) * sstep; }
+                    else { --slot[s]; xptr[s] -= sstep; }
                 }
             }
         }
@@ -636,7 +651,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
                 int hd = a.head[chan] - a.head_back - sm.pbeg[sl];      // partition p meets slot (head - p) mod ring
                 while (hd < 0) hd += a.ring;
                 slot[s] = hd;
-                xptr[s] = reinterpret_cast<const float4*>(a.fdl + chan * a.fdl_chan_stride + (long long) hd * M);
+                xptr[s] = reinterpret_cast<const float4*>(a.fdl + fdl_row_offset(a, chan, M) + (long long) hd * fdl_slot_stride<M>(a));
             }
         }
         float4 acc[L::K][L::V];
@@ -646,6 +661,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
             for (int vv = 0; vv < L::V; ++vv) acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
 
         float4 xa[L::K][L::V], xb[L::K][L::V];
+        const long long sstep = fdl_slot_stride<M>(a) / 2;    // float4 between ring slots
         auto load_group = [&](float4 (&x)[L::K][L::V], int g) {
 #pragma unroll
             for (int s = 0; s < L::K; ++s) {
@@ -661,8 +677,8 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
                     for (int vv = 0; vv < L::V; ++vv) x[s][vv] = ok ? ldg_stream(xptr[s] + L::f4(c0, vv)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 if (ok) {
-                    if (slot[s] == 0) { slot[s] = a.ring - 1; xptr[s] += (long long) (a.ring - 1) * (M / 2); }
-                    else { --slot[s]; xptr[s] -= M / 2; }
+                    if (slot[s] == 0) { slot[s] = a.ring - 1; xptr[s] += (long long) (a.ring - 1) * sstep; }
+                    else { --slot[s]; xptr[s] -= sstep; }
                 }
             }
         };
