@@ -117,6 +117,10 @@ int irb_engine_read_fdl_spectrum(irb_engine* e, int chan, int age, float* out_pa
 /* kernel launches issued by this engine so far, and by the whole library */
 long long irb_engine_launch_count(const irb_engine* e);
 long long irb_launch_count(void);
+/* The offline functions recycle their device scratch buffers through a process-wide pool (at most 12 GB of free blocks) so
+ * that repeated calls do not pay cudaMalloc / cudaFree of gigabytes each time; this returns the pool to the driver and
+ * reports how many bytes it held.  Engines do not use the pool. */
+size_t irb_release_workspace(void);
 /* device time (CUDA events, ms) of the kernels of the calling thread's most recent offline call
  * (irb_convolve_periodic / _nonperiodic / irb_deconvolve*), host<->device copies excluded */
 double irb_last_compute_ms(void);

@@ -21,12 +21,37 @@ extern std::atomic<long long> g_launches;
         if (e_ != cudaSuccess) return irbh::fail(IRB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Scratch memory of the offline functions is recycled through a small process-wide pool (blocks tagged with their device):
+// cudaMalloc / cudaFree of the gigabytes a batched deconvolution needs cost tens to hundreds of milliseconds and vary from
+// call to call.  irb_release_workspace() returns everything to the driver.  Engines never use the pool.
+void* pool_get(int dev, size_t bytes, size_t* got);
+void pool_put(int dev, void* p, size_t bytes);
+size_t pool_release();
+
 struct DevBuf {
     void* p = nullptr;
+    size_t pooled_bytes = 0;       // > 0: the block goes back to the pool instead of cudaFree
+    int pooled_dev = 0;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) { if (pooled_bytes) pool_put(pooled_dev, p, pooled_bytes); else cudaFree(p); } }
+    int alloc_scratch(size_t bytes, bool zero) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        const size_t want = bytes ? bytes : 16;
+        p = pool_get(dev, want, &pooled_bytes);
+        pooled_dev = dev;
+        if (!p) {
+            CK(cudaMalloc(&p, want));
+            pooled_bytes = want;
+        }
+        if (zero) {
+            CK(cudaMemset(p, 0, want));
+            CK(cudaStreamSynchronize(cudaStreamLegacy));
+        }
+        return 0;
+    }
     int alloc(size_t bytes, bool zero) {
         CK(cudaMalloc(&p, bytes ? bytes : 16));
         if (zero) {
@@ -61,6 +86,11 @@ struct ComputeTimer {
         set_last_compute_ms(total);
         return 0;
     }
+};
+
+// DevBuf whose alloc() draws from the scratch pool: what the offline functions declare
+struct ScratchBuf : DevBuf {
+    int alloc(size_t bytes, bool zero) { return alloc_scratch(bytes, zero); }
 };
 
 struct StreamGuard {

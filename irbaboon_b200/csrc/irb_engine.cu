@@ -50,6 +50,48 @@ int twiddles(int dev, int M, const float2** out) {
     return 0;
 }
 
+// ---- scratch pool ------------------------------------------------------------------------------------
+namespace {
+struct PoolBlock { void* p; size_t bytes; int dev; };
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool;
+size_t g_pool_bytes = 0;
+constexpr size_t kPoolCap = 12ull << 30;         // free blocks kept at most
+}  // namespace
+void* pool_get(int dev, size_t bytes, size_t* got) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < (int) g_pool.size(); ++i)
+        if (g_pool[i].dev == dev && g_pool[i].bytes >= bytes && g_pool[i].bytes <= 2 * bytes + (1u << 20) && (best < 0 || g_pool[i].bytes < g_pool[best].bytes)) best = i;
+    if (best < 0) { *got = 0; return nullptr; }
+    void* p = g_pool[best].p;
+    *got = g_pool[best].bytes;
+    g_pool_bytes -= g_pool[best].bytes;
+    g_pool.erase(g_pool.begin() + best);
+    return p;
+}
+void pool_put(int dev, void* p, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool_bytes + bytes <= kPoolCap) { g_pool.push_back({p, bytes, dev}); g_pool_bytes += bytes; return; }
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != dev) cudaSetDevice(dev);
+    cudaFree(p);
+    if (cur != dev) cudaSetDevice(cur);
+}
+size_t pool_release() {
+    std::vector<PoolBlock> blocks;
+    size_t n = 0;
+    { std::lock_guard<std::mutex> lk(g_pool_mu); blocks.swap(g_pool); n = g_pool_bytes; g_pool_bytes = 0; }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& b : blocks) { cudaSetDevice(b.dev); cudaFree(b.p); }
+    cudaSetDevice(cur);
+    return n;
+}
+
 int twiddles2(int dev, int M, const float2** hi, const float2** lo) {
     struct Entry { int dev, M; float2 *hi, *lo; };
     static std::mutex mu;
@@ -402,6 +444,7 @@ void* irb_host_alloc(size_t bytes) {
 }
 void irb_host_free(void* p) { if (p) cudaFreeHost(p); }
 long long irb_launch_count(void) { return g_launches.load(); }
+size_t irb_release_workspace(void) { return irbh::pool_release(); }
 double irb_last_compute_ms(void) { return irbh::g_last_compute_ms; }
 
 int irb_engine_create(irb_engine** out, int device, int block_size, int max_partitions, int n_channels, int n_irs) {
@@ -857,7 +900,7 @@ int irb_ir_to_real_fft_raw(const float* x, int len, int part_size, float* out) {
     if (rc) return rc;
     irbh::StreamGuard sg;
     if ((rc = sg.create())) return rc;
-    DevBuf dx, dH;
+    irbh::ScratchBuf dx, dH;
     if ((rc = dx.alloc(sizeof(float) * (size_t) len, false)) || (rc = dH.alloc(sizeof(float2) * (size_t) M * parts, true))) return rc;
     CK(cudaMemcpyAsync(dx.p, x, sizeof(float) * (size_t) len, cudaMemcpyHostToDevice, sg.s));
     irb::FwdArgs f{};
@@ -907,7 +950,7 @@ int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, i
     cudaStream_t st = nullptr;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{st};
-    DevBuf dx, dh, dX, dH, dout, dtail, dnp, dir;
+    irbh::ScratchBuf dx, dh, dX, dH, dout, dtail, dnp, dir;
     const size_t spec = sizeof(float2) * (size_t) M;
     if ((rc = dx.alloc(sizeof(float) * (size_t) ch_x * len_x, false)) || (rc = dh.alloc(sizeof(float) * (size_t) ch_h * len_h, false)) ||
         (rc = dX.alloc(spec * bpc * ch_x, false)) || (rc = dH.alloc(spec * P * n_ir, false)) ||

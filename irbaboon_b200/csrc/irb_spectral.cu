@@ -13,7 +13,7 @@
 
 namespace {
 
-using irbh::DevBuf;
+using DevBuf = irbh::ScratchBuf;      // every buffer in this file is call-scoped scratch: recycled through the pool
 using irbh::fail;
 using irbh::g_launches;
 
@@ -312,13 +312,17 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
     // captures per sub-batch: about 48 MB of spectra (IRB_DECONV_SUB overrides), never more than the batch
     static const int sub_env = [] { const char* v = getenv("IRB_DECONV_SUB"); return v ? atoi(v) : 0; }();
     int sub = sub_env > 0 ? sub_env : (int) std::max<long long>(1, (48LL << 20) / ((long long) sizeof(float2) * M));
-    // smoothing: the running sum is one sequential chain per capture, so the whole batch (up to ~6 GB of state) goes at once
-    if (smoothing) sub = (int) std::max<long long>(1, (6LL << 30) / (28LL * N));
     sub = std::min(sub, batch);
+    // smoothing: the running sum is one sequential chain per capture and costs the same few milliseconds per pass for 1 or
+    // 500 captures, so a whole GROUP of captures (about 5 GB of spectra and sums) is smoothed at once, between a first phase
+    // (upload | forward transform, split, divide) and a last phase (merge, inverse transform | download) that both run in
+    // sub-batches with their copies overlapped.
+    const int grp = smoothing ? (int) std::min<long long>(batch, std::max<long long>(sub, (5LL << 30) / (16LL * (M + 1)))) : batch;
     const bool fused = plan.big() && !smoothing;
-    struct Slot { DevBuf dn, Zn, dy, dy2, tmp, S; cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr, t0 = nullptr, t1 = nullptr;
+    struct Slot { DevBuf dn, Zn, dy, dy2, tmp; cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr, t0 = nullptr, t1 = nullptr;
+                  bool dn_busy = false, dy_busy = false, timed = false;
                   ~Slot() { for (cudaEvent_t e : {ev_in, ev_done, ev_out, t0, t1}) if (e) cudaEventDestroy(e); } } slot[2];
-    DevBuf dd, Zd, Bd, Sd, dtmp;
+    DevBuf dd, Zd, Bd, Sd, dtmp, Sall;
     Smoother sm;
     const float smooth_per_avg = 1.0 / 13.0;                                          // fp/convolution.cpp:390 (a float there)
     const int nslots = batch > sub ? 2 : 1;
@@ -328,14 +332,15 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
             (rc = q.dy.alloc(sizeof(float2) * (size_t) M * sub, false)))
             return rc;
         if (!fused && (rc = q.tmp.alloc(sizeof(float2) * (size_t) M * sub, false))) return rc;
-        if (smoothing && (rc = q.S.alloc(sizeof(float2) * (size_t) (M + 1) * sub, false))) return rc;
         if (!include_phase && (rc = q.dy2.alloc(sizeof(float) * (size_t) N * sub, false))) return rc;
         CK(cudaEventCreateWithFlags(&q.ev_in, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&q.ev_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&q.ev_out, cudaEventDisableTiming)); CK(cudaEventCreate(&q.t0)); CK(cudaEventCreate(&q.t1));
     }
     if ((rc = dd.alloc(sizeof(float) * lde, true)) || (rc = Zd.alloc(sizeof(float2) * (size_t) M, false)) || (rc = dtmp.alloc(sizeof(float2) * (size_t) M, false))) return rc;
     if (fused && (rc = Bd.alloc(sizeof(float2) * (size_t) M, false))) return rc;
-    if (smoothing && ((rc = Sd.alloc(sizeof(float2) * (size_t) (M + 1), false)) || (rc = sm.init(M, sub, (double) smooth_per_avg, sample_rate, 1, st)))) return rc;
+    if (smoothing && ((rc = Sd.alloc(sizeof(float2) * (size_t) (M + 1), false)) || (rc = Sall.alloc(sizeof(float2) * (size_t) (M + 1) * grp, false)) ||
+                      (rc = sm.init(M, grp, (double) smooth_per_avg, sample_rate, 1, st))))
+        return rc;
     irbh::set_last_compute_ms(0.0);
     // the denominator's spectrum, once
     CK(cudaMemcpyAsync(dd.p, den, sizeof(float) * len_den, cudaMemcpyHostToDevice, st));
@@ -349,46 +354,28 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
         }
     }
     double total_ms = 0.0;
-    int it = 0;
-    auto collect = [&](Slot& q) -> int {          // kernel time of the sub-batch that last used this slot
+    cudaEvent_t sm0 = nullptr, sm1 = nullptr;
+    struct EvGuard { cudaEvent_t& a; cudaEvent_t& b; ~EvGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg{sm0, sm1};
+    if (smoothing) { CK(cudaEventCreate(&sm0)); CK(cudaEventCreate(&sm1)); }
+    auto collect = [&](Slot& q) -> int {          // kernel time of the section that last used this slot
+        if (!q.timed) return 0;
         CK(cudaEventSynchronize(q.t1));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, q.t0, q.t1));
         total_ms += ms;
+        q.timed = false;
         return 0;
     };
-    for (int b0 = 0; b0 < batch; b0 += sub, ++it) {
-        Slot& q = slot[it & 1];
-        const int nb = std::min(sub, batch - b0);
-        if (it >= 2) {
-            CK(cudaStreamWaitEvent(sg_in.s, q.ev_done, 0));                          // kernels of it-2 have consumed q.dn
-            if ((rc = collect(q))) return rc;
-        }
+    // upload of a sub-batch into q.dn (after the kernels that last read it), and the compute stream waiting for it
+    auto upload = [&](Slot& q, int b0, int nb) -> int {
+        if (q.dn_busy) CK(cudaStreamWaitEvent(sg_in.s, q.ev_done, 0));
         CK(cudaMemcpy2DAsync(q.dn.p, sizeof(float) * lne, nums + (size_t) b0 * len_num, sizeof(float) * len_num, sizeof(float) * len_num, nb, cudaMemcpyHostToDevice, sg_in.s));
         CK(cudaEventRecord(q.ev_in, sg_in.s));
         CK(cudaStreamWaitEvent(st, q.ev_in, 0));
-        if (it >= 2) CK(cudaStreamWaitEvent(st, q.ev_out, 0));                       // download of it-2 has drained q.dy
-        CK(cudaEventRecord(q.t0, st));
-        if (fused) {
-            if ((rc = plan.cols_fwd(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), nb, st)) || (rc = plan.rows_binop(q.Zn.as<float2>(), Bd.as<float2>(), 0, nb, st)) ||
-                (rc = plan.cols_inv(q.Zn.as<float2>(), q.dy.as<float2>(), M, nb, 1.0f / (float) N, st)))
-                return rc;
-        } else {
-            if ((rc = plan.run(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), M, q.tmp.as<float2>(), nb, false, 1.0f, st))) return rc;
-            if (!smoothing) {
-                irb::k_spec_fused<true><<<grid1(M / 2 + 1, nb), 256, 0, st>>>(q.Zn.as<float2>(), M, Zd.as<float2>(), 0, q.Zn.as<float2>(), M, M, plan.WN);
-                LAUNCHED();
-            } else {
-                irb::k_spec_split<<<grid1(M + 1, nb), 256, 0, st>>>(q.Zn.as<float2>(), M, q.S.as<float2>(), M + 1, M, 0, plan.WN);
-                LAUNCHED();
-                irb::k_spec_binop<true><<<grid1(M + 1, nb), 256, 0, st>>>(q.S.as<float2>(), M + 1, Sd.as<float2>(), 0, M);
-                LAUNCHED();
-                if ((rc = sm.run(q.S.as<float2>(), M + 1, nb, 3, 1, include_phase, include_amplitude, st))) return rc;
-                irb::k_spec_merge<<<grid1(M, nb), 256, 0, st>>>(q.S.as<float2>(), M + 1, q.Zn.as<float2>(), M, M, plan.WN);
-                LAUNCHED();
-            }
-            if ((rc = plan.run(q.Zn.p, M, -1, q.dy.as<float2>(), M, q.tmp.as<float2>(), nb, true, 1.0f / (float) N, st))) return rc;
-        }
+        return 0;
+    };
+    // inverse-transformed sub-batch in q.dy -> (half swap) -> host
+    auto download = [&](Slot& q, int b0, int nb) -> int {
         const float* res = q.dy.as<float>();
         if (!include_phase) {                                                        // ir::shifteroo, fp/convolution.cpp:400
             irb::k_shifteroo<<<grid1(N, nb), 256, 0, st>>>(q.dy.as<float>(), q.dy2.as<float>(), N, N);
@@ -400,10 +387,65 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
         CK(cudaStreamWaitEvent(sg_out.s, q.ev_done, 0));
         CK(cudaMemcpyAsync(out + (size_t) b0 * N, res, sizeof(float) * (size_t) N * nb, cudaMemcpyDeviceToHost, sg_out.s));
         CK(cudaEventRecord(q.ev_out, sg_out.s));
+        q.dy_busy = true;
+        return 0;
+    };
+    int it = 0;
+    for (int g0 = 0; g0 < batch; g0 += grp) {
+        const int gn = std::min(grp, batch - g0);
+        for (int b0 = g0; b0 < g0 + gn; b0 += sub, ++it) {                           // first phase (the only one without smoothing)
+            Slot& q = slot[it % nslots];
+            const int nb = std::min(sub, g0 + gn - b0);
+            if ((rc = collect(q)) || (rc = upload(q, b0, nb))) return rc;
+            if (!smoothing && q.dy_busy) CK(cudaStreamWaitEvent(st, q.ev_out, 0));   // the previous download has drained q.dy
+            CK(cudaEventRecord(q.t0, st));
+            q.timed = true;
+            if (fused) {
+                if ((rc = plan.cols_fwd(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), nb, st)) || (rc = plan.rows_binop(q.Zn.as<float2>(), Bd.as<float2>(), 0, nb, st)) ||
+                    (rc = plan.cols_inv(q.Zn.as<float2>(), q.dy.as<float2>(), M, nb, 1.0f / (float) N, st)))
+                    return rc;
+            } else {
+                if ((rc = plan.run(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), M, q.tmp.as<float2>(), nb, false, 1.0f, st))) return rc;
+                if (!smoothing) {
+                    irb::k_spec_fused<true><<<grid1(M / 2 + 1, nb), 256, 0, st>>>(q.Zn.as<float2>(), M, Zd.as<float2>(), 0, q.Zn.as<float2>(), M, M, plan.WN);
+                    LAUNCHED();
+                    if ((rc = plan.run(q.Zn.p, M, -1, q.dy.as<float2>(), M, q.tmp.as<float2>(), nb, true, 1.0f / (float) N, st))) return rc;
+                } else {
+                    float2* Sg = Sall.as<float2>() + (size_t) (b0 - g0) * (M + 1);
+                    irb::k_spec_split<<<grid1(M + 1, nb), 256, 0, st>>>(q.Zn.as<float2>(), M, Sg, M + 1, M, 0, plan.WN);
+                    LAUNCHED();
+                    irb::k_spec_binop<true><<<grid1(M + 1, nb), 256, 0, st>>>(Sg, M + 1, Sd.as<float2>(), 0, M);
+                    LAUNCHED();
+                }
+            }
+            if (!smoothing) { if ((rc = download(q, b0, nb))) return rc; }
+            else { CK(cudaEventRecord(q.t1, st)); CK(cudaEventRecord(q.ev_done, st)); }
+            q.dn_busy = true;
+        }
+        if (!smoothing) continue;
+        CK(cudaEventRecord(sm0, st));
+        if ((rc = sm.run(Sall.as<float2>(), M + 1, gn, 3, 1, include_phase, include_amplitude, st))) return rc;
+        CK(cudaEventRecord(sm1, st));
+        for (int b0 = g0; b0 < g0 + gn; b0 += sub, ++it) {                           // last phase
+            Slot& q = slot[it % nslots];
+            const int nb = std::min(sub, g0 + gn - b0);
+            if ((rc = collect(q))) return rc;
+            if (q.dy_busy) CK(cudaStreamWaitEvent(st, q.ev_out, 0));
+            CK(cudaEventRecord(q.t0, st));
+            q.timed = true;
+            irb::k_spec_merge<<<grid1(M, nb), 256, 0, st>>>(Sall.as<float2>() + (size_t) (b0 - g0) * (M + 1), M + 1, q.Zn.as<float2>(), M, M, plan.WN);
+            LAUNCHED();
+            if ((rc = plan.run(q.Zn.p, M, -1, q.dy.as<float2>(), M, q.tmp.as<float2>(), nb, true, 1.0f / (float) N, st))) return rc;
+            if ((rc = download(q, b0, nb))) return rc;
+        }
+        CK(cudaEventSynchronize(sm1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, sm0, sm1));
+        total_ms += ms;
     }
     CK(cudaStreamSynchronize(sg_out.s));
     CK(cudaStreamSynchronize(st));
-    for (int i = 0; i < std::min(it, 2); ++i) if ((rc = collect(slot[i]))) return rc;
+    for (int i = 0; i < nslots; ++i) if ((rc = collect(slot[i]))) return rc;
     irbh::set_last_compute_ms(total_ms);
     return 0;
 }

@@ -58,6 +58,7 @@ _SIGS = {
     "irb_engine_read_fdl_spectrum": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_engine_launch_count": (ctypes.c_longlong, [_vp]),
     "irb_launch_count": (ctypes.c_longlong, []),
+    "irb_release_workspace": (ctypes.c_size_t, []),
     "irb_last_compute_ms": (ctypes.c_double, []),
     "irb_engine_mac_only_device": (ctypes.c_int, [_vp, _vp]),
     "irb_group_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_int)] + [ctypes.c_int] * 5),
@@ -123,6 +124,11 @@ def set_device(device):
 
 def launch_count():
     return lib().irb_launch_count()
+
+
+def release_workspace():
+    """Return the offline functions' recycled device scratch buffers to the driver; -> bytes released."""
+    return lib().irb_release_workspace()
 
 
 def last_compute_ms():

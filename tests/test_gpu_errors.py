@@ -88,3 +88,21 @@ def test_many_engines_and_repeated_create_destroy_do_not_leak(eng):
         e.close()
     torch.cuda.synchronize()
     assert free0 - torch.cuda.mem_get_info()[0] < 64 << 20            # twiddle tables stay cached, nothing else
+
+
+def test_offline_scratch_pool_recycles_and_releases(eng):
+    import torch
+    x = synth.white_noise(1001, 0, 1 << 16)
+    h = synth.decaying_ir(2000, 1 << 14)
+    eng.release_workspace()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    a = eng.convolve_nonperiodic(x, h)
+    b = eng.convolve_nonperiodic(x, h)                       # second call runs out of recycled blocks
+    c = eng.deconvolve(a[0, :1 << 16], x, 48000.0, True)
+    assert np.array_equal(a, b) and c.shape == (1, 1 << 16)
+    held = free0 - torch.cuda.mem_get_info()[0]
+    assert held > 1 << 20                                    # the pool keeps the scratch of the calls above
+    released = eng.release_workspace()
+    assert released > 1 << 20 and eng.release_workspace() == 0
+    assert free0 - torch.cuda.mem_get_info()[0] < 16 << 20   # back to where it started (tables stay cached)
