@@ -122,7 +122,7 @@ def workload(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(args, target_seconds, threads=None):
+def cpu_reference_sample(args, target_seconds, threads=None, probe=None):
     """The reference's convolvePeriodic (oracle/_ref; the C port if _ref did not travel) on the host cores:
     `threads` workers, one whole mono stream each, same IR / block size as the GPU workload."""
     import oracle
@@ -132,8 +132,10 @@ def cpu_reference_sample(args, target_seconds, threads=None):
     if oracle.have_reference():
         ref = oracle.Reference()
         T = threads or max(1, ref.hardware_threads())
-        secs, _ = ref.bench_convolve_periodic(T, T, int(SR // 4), h, B, 1003)              # probe: 0.25 s of audio per stream
-        per_audio_second = max(secs, 1e-3) / 0.25                                           # wall seconds per audio second with T streams on T threads
+        if probe is None:
+            secs, _ = ref.bench_convolve_periodic(T, T, int(SR // 4), h, B, 1003)          # probe: 0.25 s of audio per stream
+            probe = max(secs, 1e-3) / 0.25
+        per_audio_second = probe                                                            # wall seconds per audio second with T streams on T threads
         # T..8T streams of up to 10 s each: about target_seconds of wall time on all host threads
         audio_s = float(np.clip(target_seconds / per_audio_second, 0.5, 10.0))
         rounds = int(np.clip(target_seconds / (audio_s * per_audio_second), 1, 8))
@@ -150,7 +152,7 @@ def cpu_reference_sample(args, target_seconds, threads=None):
         orc.convolve_periodic(x, h, B)
         secs, chk, kind = time.perf_counter() - t0, 0.0, "port"
     rt = streams * (Lx / SR) / secs
-    return {"value": rt, "unit": UNIT, "cores": T, "kind": kind, "seconds": secs,
+    return {"value": rt, "unit": UNIT, "cores": T, "kind": kind, "seconds": secs, "probe": probe,
             "sample": "%d streams x %.2f s white noise each through fp::convolution::convolvePeriodic(B=%d, %d-tap IR), %d threads, one stream per thread"
                       % (streams, Lx / SR, B, Lh, T)}
 
@@ -159,11 +161,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    per_step = float(np.clip(budget, 1.0, args.cpu_seconds))
+    # every step is a bounded sample of the workload; the whole run (warm-up included) is sized for about two minutes
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    per_step = float(np.clip(budget, 0.25, args.cpu_seconds))
     vals, last = [], None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_sample(args, per_step)
+        last = cpu_reference_sample(args, per_step, probe=last["probe"] if last else None)
         if i >= args.warmup:
             vals.append(last)
     secs = sum(v["seconds"] for v in vals)
@@ -327,6 +330,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(args, args.cpu_seconds)
         cpu.pop("seconds", None)
+        cpu.pop("probe", None)
 
     if rank == 0:
         wl = ("configs[3]: %d streams with per-stream %.0f s IRs (%d taps, %d partitions), block %d, sharded by stream over %d GPU(s)"

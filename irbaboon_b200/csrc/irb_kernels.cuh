@@ -4,17 +4,20 @@
 // in the streaming engine, one output block in the offline functions).  256 compute threads work in two
 // layouts over the same 16 KB of shared memory:
 //   * FFT layout : M/8 threads per row, 8 complex points each (irb_fft.cuh);
-//   * MAC layout : each thread owns V float4 (= 2V bins) of K rows, K*V = 4, so that one warp instruction
-//                  reads 512 contiguous bytes of a frequency-domain delay line (FDL) row.
+//   * MAC layout : each thread owns V float4 (= 2V bins) of K rows, K*V = 4; in the streaming kernels the float4 come in
+//                  adjacent pairs read with one 32-byte load, so that one warp instruction reads 1 KB of a
+//                  frequency-domain delay line (FDL) row (MacLayout).
 // A 9th warp is the TMA producer that streams impulse-response partition spectra into a shared-memory
 // ring (cp.async.bulk + mbarrier), so every row of the tile -- every stream sharing that IR -- reuses them.
 //
 // Reference loops replaced (paths relative to /root/reference):
-//   k_fwd      fp/convolution.cpp:106-125 (IR partition load + FFT), :128-149 (audio block load + FFT),
-//              Source/PluginProcessor.cpp:430-436,455-461
-//   k_mac      fp/convolution.cpp:160-215 (MAC over partitions, inverse FFT, overlap-add),
-//              Source/PluginProcessor.cpp:480-510
-//   k_ola_tail fp/convolution.cpp:210-213 for the offline (all blocks at once) formulation
+//   k_fwd       fp/convolution.cpp:106-125 (IR partition load + FFT), :128-149 (audio block load + FFT),
+//               Source/PluginProcessor.cpp:430-436,455-461 (incl. the round-robin IR refresh rows)
+//   k_mac       fp/convolution.cpp:160-215 (MAC over partitions, inverse FFT, overlap-add), Source/PluginProcessor.cpp:480-510;
+//               with FUSE also k_fwd's work for the tile's new blocks: one launch per streaming block step
+//   k_mac_slots the same loop when a tile's rows do not share an IR (per-stream IRs) or when there are so few rows that
+//               each row's partitions are split over tile slots and the CTAs of a thread-block cluster
+//   k_ola_tail  fp/convolution.cpp:210-213 for the offline (all blocks at once) formulation
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
