@@ -122,8 +122,9 @@ def c3cap(eng, synth, args):
         step_ms, mac_ms = e.timings()
         e.set_timing(False)
         alg = (S + 1) * P * (B + 1) * 8
-        rows.append({"streams": S, "state_gb": e.state_bytes / 1e9, "step_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)),
-                     "max": float(step_ms.max())}, "mac_gbs": alg / (mac_ms.mean() * 1e-3) / 1e9, "realtime": bool(np.percentile(step_ms, 99) < period),
+        rows.append({"streams": S, "state_gb": e.state_bytes / 1e9, "steps": int(len(step_ms)),
+                     "step_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)), "p99.9": float(np.percentile(step_ms, 99.9)),
+                                 "max": float(step_ms.max()), "over_period": int((step_ms >= period).sum())}, "mac_gbs": alg / (mac_ms.mean() * 1e-3) / 1e9, "realtime": bool(np.percentile(step_ms, 99) < period),
                      "headroom": float(period / np.percentile(step_ms, 99))})
         e.close()
         del d_in, d_out
