@@ -41,7 +41,7 @@ __device__ __forceinline__ float2 root_big(const float2* __restrict__ hi, const 
 }
 
 template <int L, bool INV>
-static __global__ void __launch_bounds__(kThreads, L >= 1024 ? 2 : 3) k_line_fft(const LineArgs a) {
+static __global__ void __launch_bounds__(kThreads, L >= 1024 ? 2 : 4) k_line_fft(const LineArgs a) {
     using T = LineTile<L>;
     extern __shared__ __align__(16) float2 s_lines[];
     const int tid = threadIdx.x;
@@ -232,7 +232,7 @@ __device__ __forceinline__ float2 pair_op(float2 zk, float2 zm, float2 bk, float
 // forward result, from which a thread reads the partners Z[M-k] of its own 8 bins; both owners of a pair evaluate
 // the pair, each keeping its own half, which costs arithmetic but no second exchange.
 template <int L>
-static __global__ void __launch_bounds__(kThreads, 3) k_rowpair(const PairArgs a) {
+static __global__ void __launch_bounds__(kThreads, 4) k_rowpair(const PairArgs a) {
     using T = PairTile<L>;
     extern __shared__ __align__(16) float2 s_lines[];
     const int tid = threadIdx.x, M1 = a.M1;
