@@ -8,8 +8,10 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "../fp/PluginConvolver.hpp"
 #include "../fp/StreamingConvolver.hpp"
 #include "../fp/convolution.hpp"
+#include "../fp/tools.hpp"
 
 static uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -55,6 +57,39 @@ int main(int argc, char** argv) {
         }
         const double dts = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         printf("streaming blocks=%d seconds=%.6f us_per_block=%.1f sum=%.9e max_abs_vs_offline=%.3e\n", nb, dts, 1e6 * dts / nb, ssum, maxdiff);
+
+        // the plug-in's own situation: stereo, processBlockSize 256, a host that delivers 480-sample buffers, the default IR
+        // generatePulse(2048, 100) -> the output is the input delayed by 100 samples plus the re-blocking latency, times -30 dB
+        const int hostBlock = 480, nhost = 200;
+        AudioBuffer<float> pulse = fp::tools::generatePulse(2048, 100);
+        fp::b200::PluginConvolver plug(256, 2);
+        plug.prepareToPlay(48000.0, hostBlock, pulse);
+        std::vector<float> in2((size_t) 2 * hostBlock * nhost), out2(in2.size());
+        for (int c = 0; c < 2; ++c)
+            for (int i = 0; i < hostBlock * nhost; ++i) in2[(size_t) c * hostBlock * nhost + i] = noise(1002, (uint64_t) c, (uint64_t) i);
+        AudioBuffer<float> hb(2, hostBlock);
+        t0 = std::chrono::steady_clock::now();
+        for (int k = 0; k < nhost; ++k) {
+            for (int c = 0; c < 2; ++c) hb.copyFrom(c, 0, &in2[(size_t) c * hostBlock * nhost + (size_t) k * hostBlock], hostBlock);
+            plug.processBlock(hb);
+            for (int c = 0; c < 2; ++c) std::copy_n(hb.getReadPointer(c), hostBlock, &out2[(size_t) c * hostBlock * nhost + (size_t) k * hostBlock]);
+        }
+        const double dtp = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        // find the delay from the data (the reference's output ring decides it), then measure the deviation from gain * delayed input
+        const float g30 = fp::tools::dBToLin(-30.0f);
+        int delay = -1;
+        for (int d = 0; d < 4 * hostBlock && delay < 0; ++d) {
+            double err = 0.0;
+            for (int i = 2000; i < 4000; ++i) err = std::max(err, (double) std::fabs(out2[(size_t) i + d] - g30 * in2[(size_t) i]));
+            if (err < 1e-6) delay = d;
+        }
+        double dev = 0.0;
+        if (delay >= 0)
+            for (int c = 0; c < 2; ++c)
+                for (int i = 0; i + delay < hostBlock * nhost; ++i)
+                    dev = std::max(dev, (double) std::fabs(out2[(size_t) c * hostBlock * nhost + i + delay] - g30 * in2[(size_t) c * hostBlock * nhost + i]));
+        printf("plugin hostBlock=%d callbacks=%d us_per_callback=%.1f reported_latency=%d measured_delay=%d max_dev_from_delayed_input=%.3e\n", hostBlock, nhost,
+               1e6 * dtp / nhost, plug.getLatencySamples(), delay, dev);
     } catch (const std::exception& ex) {
         fprintf(stderr, "headless_convolve: %s\n", ex.what());
         return 1;

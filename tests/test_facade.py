@@ -139,6 +139,10 @@ def test_headless_harness_config1(built, orc):
     assert abs(float(kv["sumsq"]) - (want ** 2).sum()) <= 1e-4 * (want ** 2).sum()
     skv = dict(t.split("=") for t in lines["streaming"].split())
     assert float(skv["max_abs_vs_offline"]) <= 1e-5
+    # the plug-in situation through fp::b200::PluginConvolver: pulse IR -> attenuated, delayed input
+    pkv = dict(t.split("=") for t in lines["plugin"].split())
+    assert int(pkv["reported_latency"]) == 480 and int(pkv["measured_delay"]) >= 100 + 256
+    assert float(pkv["max_dev_from_delayed_input"]) <= 1e-6
 
 
 def test_facade_fails_loudly_without_a_gpu(fac, eng):
