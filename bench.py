@@ -311,9 +311,12 @@ def run_b200(args):
         e.set_stream(None)
         e.process(hin[:4], hout[:4])                      # warm-up of the copy path
         barrier()
+        REP = 4                                           # the feed is continuous: REP back-to-back submissions of K2 blocks, one wait
         t0 = time.perf_counter()
-        e.process(hin, hout)                              # returns when every output block is back on the host
-        dt = time.perf_counter() - t0
+        for _ in range(REP):
+            e.submit(hin, hout)                           # copies and kernels enqueued; the pipeline stays full across submissions
+        e.wait()                                          # every output block is back on the host
+        dt = (time.perf_counter() - t0) / REP
         dt = sharding.max_over_ranks(dt, device="cuda")
         # strict block-by-block round trip (what a live host callback sees)
         t0 = time.perf_counter()
@@ -321,7 +324,7 @@ def run_b200(args):
             e.process(hin[i], hout[i])
         dt1 = (time.perf_counter() - t0) / min(K2, 16)
         e2e = {"value": total_streams * B * K2 / dt / SR, "unit": UNIT, "h2d_bytes_per_step": S * B * 4, "d2h_bytes_per_step": S * B * 4,
-               "steps": K2, "ms_per_step": 1e3 * dt / K2, "api": "irb_engine_process(host in, host out, n_blocks=%d), pinned buffers, wall clock" % K2,
+               "steps": K2, "ms_per_step": 1e3 * dt / K2, "api": "4 x irb_engine_submit(host in, host out, n_blocks=%d) + irb_engine_wait, pinned buffers, wall clock" % K2,
                "blockwise_roundtrip_ms": 1e3 * dt1, "checksum": float(np.abs(hout[-1]).sum())}
         eng.pinned_free(hin)
         eng.pinned_free(hout)

@@ -100,6 +100,12 @@ int irb_engine_process_device(irb_engine* e, const float* in_dev, float* out_dev
  * unless max_partitions >= partitions + n_blocks - 1).  HOST buffers [n_blocks][n_channels][block_size]. */
 int irb_engine_process_callback(irb_engine* e, const float* in_host, float* out_host, int n_blocks);
 int irb_engine_synchronize(irb_engine* e);
+/* Asynchronous host path for a continuous feed: _submit returns once the copies and kernels of n_blocks (>= 2) blocks are
+ * enqueued -- the host arrays must be pinned (irb_host_alloc) and stay valid until _wait; consecutive submits keep the
+ * upload | kernels | download pipeline full instead of draining it at every call.  _wait returns when everything
+ * submitted so far is back in host memory. */
+int irb_engine_submit(irb_engine* e, const float* in_host, float* out_host, int n_blocks);
+int irb_engine_wait(irb_engine* e);
 
 /* Per-step device timing with CUDA events on the engine's stream: whole block step (k_fwd + k_mac) and the
  * FDL-MAC kernel alone.  set_timing(1) clears the record; get_timings returns the number of steps copied. */

@@ -298,6 +298,8 @@ struct irb_engine {
     std::vector<cudaEvent_t> tev;
     int t_rec = 0;
     std::vector<cudaEvent_t> ev_grp;                 // single large block: per channel group "uploaded" / "computed"
+    unsigned long long pipe_seq = 0;                 // blocks that went through the multi-block pipeline (staging slot = seq & 1)
+    bool pipe_pending = false;                       // submitted work not yet waited for
     ~irb_engine() {
         for (auto ev : tev) cudaEventDestroy(ev);
         for (auto ev : ev_grp) if (ev) cudaEventDestroy(ev);
@@ -709,6 +711,7 @@ int engine_process_wait(irb_engine* e) {
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->s_out));
     CK(cudaStreamSynchronize(e->stream));
+    e->pipe_pending = false;
     return 0;
 }
 int engine_process_enqueue(irb_engine* e, const float* in_host, float* out_host, int n_blocks, size_t stride, bool allow_graph) {
@@ -717,6 +720,7 @@ int engine_process_enqueue(irb_engine* e, const float* in_host, float* out_host,
     if (rc) return rc;
     const size_t blk = (size_t) e->B * e->n_chans;
     if (n_blocks == 1) {
+        if (e->pipe_pending && (rc = engine_process_wait(e))) return rc;               // submitted blocks still own the staging slots
         // a live callback: one block in, one block out.  Small blocks replay a captured graph (one launch); larger ones
         // run copy, kernels, copy back to back on the engine's stream -- no cross-stream events to wait on.
         if (allow_graph) {
@@ -752,20 +756,24 @@ int engine_process_enqueue(irb_engine* e, const float* in_host, float* out_host,
         }
         return 0;
     }
-    // three-stage pipeline over double-buffered device staging: upload b+1 | compute b | download b-1
+    // three-stage pipeline over double-buffered device staging: upload b+1 | compute b | download b-1.  The staging slots
+    // and their events persist across calls (pipe_seq), so back-to-back irb_engine_submit calls keep the pipeline full.
     for (int b = 0; b < n_blocks; ++b) {
-        const int q = b & 1;
-        if (b >= 2) CK(cudaStreamWaitEvent(e->s_in, e->ev_done[q], 0));            // compute b-2 has consumed io_in[q]
+        const int q = (int) (e->pipe_seq & 1);
+        const bool reused = e->pipe_seq >= 2;
+        ++e->pipe_seq;
+        if (reused) CK(cudaStreamWaitEvent(e->s_in, e->ev_done[q], 0));            // the step two blocks back has consumed io_in[q]
         CK(cudaMemcpyAsync(e->io_in[q].p, in_host + b * stride, sizeof(float) * blk, cudaMemcpyHostToDevice, e->s_in));
         CK(cudaEventRecord(e->ev_in[q], e->s_in));
         CK(cudaStreamWaitEvent(e->stream, e->ev_in[q], 0));
-        if (b >= 2) CK(cudaStreamWaitEvent(e->stream, e->ev_out[q], 0));           // download b-2 has drained io_out[q]
+        if (reused) CK(cudaStreamWaitEvent(e->stream, e->ev_out[q], 0));           // its download has drained io_out[q]
         if ((rc = engine_step_device(e, e->io_in[q].as<float>(), e->io_out[q].as<float>()))) return rc;
         CK(cudaEventRecord(e->ev_done[q], e->stream));
         CK(cudaStreamWaitEvent(e->s_out, e->ev_done[q], 0));
         CK(cudaMemcpyAsync(out_host + b * stride, e->io_out[q].p, sizeof(float) * blk, cudaMemcpyDeviceToHost, e->s_out));
         CK(cudaEventRecord(e->ev_out[q], e->s_out));
     }
+    e->pipe_pending = true;
     return 0;
 }
 }  // namespace
@@ -775,6 +783,21 @@ int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int
     if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
     int rc = engine_process_enqueue(e, in_host, out_host, n_blocks, (size_t) e->B * e->n_chans, true);
     if (rc) return rc;
+    return engine_process_wait(e);
+}
+
+// Asynchronous host path for a continuous feed: submit returns once the copies and kernels of the blocks are enqueued
+// (the host arrays must stay valid and pinned until the wait); consecutive submits keep the three-stage pipeline full
+// instead of draining it at every call.  irb_engine_wait returns when everything submitted so far is back in host memory.
+int irb_engine_submit(irb_engine* e, const float* in_host, float* out_host, int n_blocks) {
+    if (!e || !in_host || !out_host) return fail(IRB_ERR_ARG, "null argument");
+    if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
+    if (n_blocks == 0) return 0;
+    if (n_blocks == 1) return fail(IRB_ERR_ARG, "irb_engine_submit takes at least two blocks per call (one block at a time is irb_engine_process)");
+    return engine_process_enqueue(e, in_host, out_host, n_blocks, (size_t) e->B * e->n_chans, false);
+}
+int irb_engine_wait(irb_engine* e) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
     return engine_process_wait(e);
 }
 

@@ -49,6 +49,8 @@ _SIGS = {
     "irb_engine_process_callback": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "irb_engine_process_device": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "irb_engine_synchronize": (ctypes.c_int, [_vp]),
+    "irb_engine_submit": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
+    "irb_engine_wait": (ctypes.c_int, [_vp]),
     "irb_engine_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "irb_engine_get_timings": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "irb_engine_state_bytes": (ctypes.c_size_t, [_vp]),
@@ -349,6 +351,15 @@ class Engine:
         out = np.empty(x.shape, np.float32)
         _ck(lib().irb_engine_process_callback(self._h, _ptr(x), _ptr(out), x.shape[0]))
         return out
+
+    def submit(self, x, out):
+        """Asynchronous multi-block call on pinned host arrays [n_blocks >= 2][n_channels][B]; pair with wait()."""
+        assert x.dtype == np.float32 and out.dtype == np.float32 and x.flags.c_contiguous and out.flags.c_contiguous and x.shape == out.shape
+        assert x.ndim == 3 and x.shape[1:] == (self.n_channels, self.block_size), x.shape
+        _ck(lib().irb_engine_submit(self._h, _ptr(x), _ptr(out), x.shape[0]))
+
+    def wait(self):
+        _ck(lib().irb_engine_wait(self._h))
 
     def process_device(self, in_ptr, out_ptr, n_blocks=1):
         _ck(lib().irb_engine_process_device(self._h, _vp(int(in_ptr)), _vp(int(out_ptr)), int(n_blocks)))

@@ -284,3 +284,31 @@ def test_large_single_block_calls_pipeline_channel_groups(eng, B, C, ns):
         single = np.stack([e.process(x[k]) for k in range(nb)])
     assert np.array_equal(single, whole)
     assert np.abs(whole).max() > 0.1
+
+
+def test_submit_wait_keeps_state_and_results_of_the_synchronous_path(eng):
+    """irb_engine_submit / irb_engine_wait: several submissions in flight, then single-block and multi-block synchronous calls
+    on the same engine -- the output sequence is bit-identical to one synchronous call over all blocks."""
+    B, C, P, nb = 128, 600, 5, 24
+    rng = np.random.default_rng(3)
+    x = (rng.random((nb, C, B), dtype=np.float32) * 2 - 1).astype(np.float32)
+    with eng.Engine(B, P, C, 1) as e:
+        e.set_ir(0, synth.decaying_ir(2000, P * B - 1))
+        want = e.process(x)
+        e.reset()
+        hin, hout = eng.pinned_empty((nb, C, B)), eng.pinned_empty((nb, C, B))
+        hin[:] = x
+        hout[:] = 0
+        e.submit(hin[0:6], hout[0:6])
+        e.submit(hin[6:8], hout[6:8])
+        e.submit(hin[8:13], hout[8:13])
+        e.wait()
+        hout[13] = e.process(hin[13])                      # a live single block drains nothing it should not
+        e.submit(hin[14:20], hout[14:20])
+        hout[20] = e.process(hin[20])                      # single block right behind an un-waited submission
+        hout[21:24] = e.process(hin[21:24])
+        got = np.array(hout)
+        with pytest.raises(eng.IrbError):
+            e.submit(hin[0:1], hout[0:1])
+        eng.pinned_free(hin); eng.pinned_free(hout)
+    assert np.array_equal(got, want)
