@@ -598,8 +598,8 @@ int irb_engine_stage_ir(irb_engine* e, int ir_id, const float* left, const float
         CK(cudaMemcpyAsync(rb, left, sizeof(float) * keep, cudaMemcpyHostToDevice, e->stream));
     }
     if (P != e->h_nparts[ir_id]) {
-        if (e->h_nparts[ir_id] == 0 || first)      // never loaded (or loaded whole before): start from cleared spectra only when nothing was loaded
-            if (e->h_nparts[ir_id] == 0) CK(cudaMemsetAsync(e->H.as<float2>() + (size_t) ir_id * e->ring * e->M, 0, sizeof(float2) * (size_t) e->M * e->ring, e->stream));
+        if (e->h_nparts[ir_id] == 0)               // nothing was ever loaded for this IR: its partitions fade in from cleared spectra
+            CK(cudaMemsetAsync(e->H.as<float2>() + (size_t) ir_id * e->ring * e->M, 0, sizeof(float2) * (size_t) e->M * e->ring, e->stream));
         CK(cudaMemsetAsync(e->rr_pos.as<int>() + ir_id, 0, sizeof(int), e->stream));
         e->h_nparts[ir_id] = P;
         CK(cudaMemcpyAsync(e->nparts.as<int>() + ir_id, &e->h_nparts[ir_id], sizeof(int), cudaMemcpyHostToDevice, e->stream));
