@@ -196,6 +196,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not os.environ.get("IRB_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"             # NCCL_DEBUG=VERSION/INFO prints to stdout, which must carry one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
