@@ -196,9 +196,19 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if not os.environ.get("IRB_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"             # NCCL_DEBUG=VERSION/INFO prints to stdout, which must carry one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL announces its version on stdout when the communicator is created; stdout must carry one JSON line, so the
+        # file descriptor points at stderr while the process group comes up (first barrier included)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
