@@ -364,6 +364,8 @@ void fill_mac_args(irb_engine* e, irb::MacArgs& m, int c0, int cn) {
     m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
     m.ir_of_chan = e->ir_of_chan.as<int>() + c0; m.nparts = e->nparts.as<int>(); m.W = e->W;
     m.B = e->B; m.split_in = e->split_in;
+    static const int sleep_ns = [] { const char* v = getenv("IRB_PRODUCER_SLEEP_NS"); return v ? atoi(v) : 200; }();
+    m.producer_sleep_ns = sleep_ns;
 }
 bool use_slots(const irb_engine* e) { return e->per_row_ir || e->split_in > 1 || e->cluster_dim > 1; }
 

@@ -64,6 +64,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
     while (!mbar_try_wait(b, parity)) {}
 }
+// The producer runs kStages ahead and spends most of its life waiting for a free stage: sleeping between polls keeps its
+// spin loop (a fifth of the kernel's instructions otherwise) off the issue ports and out of the power budget.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* b, uint32_t parity, int ns) {
+    while (!mbar_try_wait(b, parity)) { if (ns) __nanosleep(ns); }
+}
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -275,6 +280,7 @@ struct MacArgs {
     const float* in;
     long long in_chan_stride;
     int* head_rw;
+    int producer_sleep_ns;     // the TMA producer sleeps this long between polls of a busy stage (0: spin)
 };
 
 // Time-domain epilogue of a tile whose accumulated packed spectra sit in shared memory, row r at tile + r*M
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
             const float2* hsrc = a.H + ir * a.ir_stride;
             for (int g = 0; g < ngroups; ++g) {
                 const int st = g % kStages;
-                if (g >= kStages) mbar_wait(&sm.empty[st], ((g / kStages) - 1) & 1);
+                if (g >= kStages) mbar_wait_relaxed(&sm.empty[st], ((g / kStages) - 1) & 1, a.producer_sleep_ns);
                 int cnt = pmax - g * U;
                 if (cnt > U) cnt = U;
                 const uint32_t bytes = (uint32_t) cnt * M * sizeof(float2);
@@ -624,7 +630,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
         const int lane = tid - kThreads;
         for (int g = 0; g < ngroups; ++g) {
             const int st = g % kStages;
-            if (g >= kStages) mbar_wait(&sm.empty[st], ((g / kStages) - 1) & 1);
+            if (g >= kStages) mbar_wait_relaxed(&sm.empty[st], ((g / kStages) - 1) & 1, a.producer_sleep_ns);
             uint32_t total = 0;
             for (int r = lane; r < T::ROWS; r += 32) if (g < sm.pcnt[r]) total += M * sizeof(float2);
 #pragma unroll
