@@ -465,6 +465,19 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
         for (int vv = 0; vv < L::V; ++vv) acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     const long long sstep = fdl_slot_stride<M>(a) / 2;    // float4 between ring slots
+    const long long swrap = (long long) (a.ring - 1) * sstep;   // from slot 0 back to the top of the ring
+    // Streaming with the fused prologue: every live row needs all np partitions, so the per-partition "is this row still
+    // valid" predicate is dropped -- rows past n_rows just re-read the tile's first row (their sums are never stored).
+    if constexpr (FUSE && WIDE) {
+        const int chan0 = row0 / a.blocks_per_chan;       // the first row of a launched tile is always live
+        const int hd0 = a.head[chan0];
+#pragma unroll
+        for (int s = 0; s < L::K; ++s)
+            if (!xptr[s]) {
+                xptr[s] = reinterpret_cast<const float4*>(a.fdl + fdl_row_offset(a, chan0, M) + (long long) hd0 * fdl_slot_stride<M>(a));
+                slot[s] = hd0;
+            }
+    }
     auto load_group = [&](float4 (&x)[U][L::K][L::V], int g) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -472,6 +485,14 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
             if (FUSE && p == 0) continue;                 // partition 0 already sits in xa[0] (registers)
 #pragma unroll
             for (int s = 0; s < L::K; ++s) {
+                if constexpr (FUSE && WIDE) {
+#pragma unroll
+                    for (int vv = 0; vv < L::V; vv += 2) ldg_stream256(xptr[s] + L::f4(c0, vv), x[u][s][vv], x[u][s][vv + 1]);
+                    const bool wrap = slot[s] == 0;
+                    slot[s] = wrap ? a.ring - 1 : slot[s] - 1;
+                    xptr[s] += wrap ? swrap : -sstep;
+                    continue;
+                }
                 const bool ok = p < nvalid[s];
                 if constexpr (WIDE) {
 #pragma unroll
@@ -486,7 +507,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
                 }
                 // step one slot back in the ring (wrap to the top)
                 if (ok) {
-                    if (slot[s] == 0) { slot[s] = a.ring - 1; xptr[s] += (long long) (a.ring - 1) * sstep; }
+                    if (slot[s] == 0) { slot[s] = a.ring - 1; xptr[s] += swrap; }
                     else { --slot[s]; xptr[s] -= sstep; }
                 }
             }

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libirb_b200.so")
+LIB_PATH = os.environ.get("IRB_LIB") or os.path.join(_HERE, "libirb_b200.so")      # IRB_LIB: another build of the library (A/B measurements)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "irb_b200.h")
 
 _f32p = ctypes.POINTER(ctypes.c_float)
