@@ -477,6 +477,8 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
                 xptr[s] = reinterpret_cast<const float4*>(a.fdl + fdl_row_offset(a, chan0, M) + (long long) hd0 * fdl_slot_stride<M>(a));
                 slot[s] = hd0;
             }
+#pragma unroll
+        for (int s = 0; s < L::K; ++s) xptr[s] += L::f4(c0, 0);       // fold the thread's own float4 offset into the row pointers
     }
     auto load_group = [&](float4 (&x)[U][L::K][L::V], int g) {
 #pragma unroll
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
             for (int s = 0; s < L::K; ++s) {
                 if constexpr (FUSE && WIDE) {
 #pragma unroll
-                    for (int vv = 0; vv < L::V; vv += 2) ldg_stream256(xptr[s] + L::f4(c0, vv), x[u][s][vv], x[u][s][vv + 1]);
+                    for (int vv = 0; vv < L::V; vv += 2) ldg_stream256(xptr[s] + (L::f4(0, vv) - L::f4(0, 0)), x[u][s][vv], x[u][s][vv + 1]);   // this thread's offset is folded into xptr
                     const bool wrap = slot[s] == 0;
                     slot[s] = wrap ? a.ring - 1 : slot[s] - 1;
                     xptr[s] += wrap ? swrap : -sstep;
