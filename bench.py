@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--ir-seconds", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the post-run comparison of the measured block step with its two-launch form")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 32))")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the bounded CPU sample")
     ap.add_argument("--two-launch", action="store_true", help="block step as k_fwd + k_mac instead of the fused single launch (A/B measurement)")
@@ -341,6 +342,26 @@ def run_b200(args):
         eng.pinned_free(hin)
         eng.pinned_free(hout)
 
+    # ---- self-check after the timed region, at the bench's own size (the GPU full, every SM holding its resident CTAs): the
+    # block step as measured against its two-launch form on EVERY channel, bit for bit (the oracle comparisons live in tests/) ----
+    selfcheck = None
+    if not args.no_selfcheck:
+        KC = 4
+        rng = np.random.default_rng(77 + rank)
+        xin = (rng.random((KC, S, B), dtype=np.float32) * 2 - 1).astype(np.float32)
+        e.set_stream(None)
+        e.reset()
+        ya = e.process(xin).copy()
+        e.reset()
+        if not per_stream_ir:
+            e.set_fused_step(bool(args.two_launch))     # the other form of the block step
+        yb = e.process(xin).copy()
+        selfcheck = {"blocks": KC, "channels_compared": int(S),
+                     "against": "same step repeated" if per_stream_ir else ("fused step" if args.two_launch else "two-launch step"),
+                     "bit_identical": bool(np.array_equal(ya, yb))}
+        selfcheck["ok"] = sharding.max_over_ranks(0.0 if selfcheck["bit_identical"] else 1.0, device="cuda") == 0.0      # every rank
+        del xin, ya, yb
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(args, args.cpu_seconds)
@@ -359,7 +380,7 @@ def run_b200(args):
                            "state_bytes_per_gpu": int(e.state_bytes), "l2_policy": "inputs larger than L2 (FDL %.2f GB per GPU)" % (S * P * B * 8 / 1e9), "mac_plan": list(e.mac_plan()),
                            "sharding": "contiguous stream ranges by rank, IR replicated, no data-path collective; host gather of outputs",
                            "gathered_output_shape": list(gathered.shape), "channel_samples_per_s": value * SR},
-                "latency": lat, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "latency": lat, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "selfcheck": selfcheck, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     e.close()
     if world > 1:

@@ -51,6 +51,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+// Consumer release of a TMA-filled stage.  `dep` is zero at run time but DERIVED FROM THE VALUES the warp read out of the stage
+// (bits & MacArgs::zero), so the arrive cannot issue before those ld.shared have returned their data.  Without the
+// dependency ptxas places the arrive right behind the last LDS; under load (three CTAs per SM, other CTAs in their FFT
+// phases) that LDS was observed to execute AFTER the producer had seen the stage free and its next bulk copy had landed:
+// one warp then multiplied partition g by the spectrum of partition g + kStages (profiles/r01_ring_release_race.md).
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* b, uint32_t dep) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b) + dep) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -281,6 +289,7 @@ struct MacArgs {
     long long in_chan_stride;
     int* head_rw;
     int producer_sleep_ns;     // the TMA producer sleeps this long between polls of a busy stage (0: spin)
+    unsigned zero;             // always 0; unknown to the compiler (mbar_arrive_after)
 };
 
 // Time-domain epilogue of a tile whose accumulated packed spectra sit in shared memory, row r at tile + r*M
@@ -477,8 +486,6 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
                 xptr[s] = reinterpret_cast<const float4*>(a.fdl + fdl_row_offset(a, chan0, M) + (long long) hd0 * fdl_slot_stride<M>(a));
                 slot[s] = hd0;
             }
-#pragma unroll
-        for (int s = 0; s < L::K; ++s) xptr[s] += L::f4(c0, 0);       // fold the thread's own float4 offset into the row pointers
     }
     auto load_group = [&](float4 (&x)[U][L::K][L::V], int g) {
 #pragma unroll
@@ -489,7 +496,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
             for (int s = 0; s < L::K; ++s) {
                 if constexpr (FUSE && WIDE) {
 #pragma unroll
-                    for (int vv = 0; vv < L::V; vv += 2) ldg_stream256(xptr[s] + (L::f4(0, vv) - L::f4(0, 0)), x[u][s][vv], x[u][s][vv + 1]);   // this thread's offset is folded into xptr
+                    for (int vv = 0; vv < L::V; vv += 2) ldg_stream256(xptr[s] + L::f4(c0, vv), x[u][s][vv], x[u][s][vv + 1]);
                     const bool wrap = slot[s] == 0;
                     slot[s] = wrap ? a.ring - 1 : slot[s] - 1;
                     xptr[s] += wrap ? swrap : -sstep;
@@ -518,6 +525,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
     auto consume_group = [&](float4 (&x)[U][L::K][L::V], int g) {
         const int st = g % kStages;
         mbar_wait(&sm.full[st], (g / kStages) & 1);
+        uint32_t dep = 0;                                 // carries every value read from the stage into the release
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (g * U + u < pmax) {
@@ -525,6 +533,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
                 for (int vv = 0; vv < L::V; ++vv) {
                     const int c = L::f4(c0, vv);
                     const float4 h = *reinterpret_cast<const float4*>(&sm.h[st][u][2 * c]);
+                    dep |= __float_as_uint(h.x);
                     // bin 0 is the packed {DC, Nyquist} pair: two real products instead of a complex one
                     const float h0i = c == 0 ? 0.f : h.y, h0q = c == 0 ? h.y : h.x;
 #pragma unroll
@@ -540,7 +549,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
             }
         }
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&sm.empty[st]);
+        if ((tid & 31) == 0) mbar_arrive_after(&sm.empty[st], dep & a.zero);
     };
 
     if (ngroups > 0) load_group(xa, 0);
@@ -717,6 +726,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
         auto consume_group = [&](float4 (&x)[L::K][L::V], int g) {
             const int st = g % kStages;
             mbar_wait(&sm.full[st], (g / kStages) & 1);
+            uint32_t dep = 0;                              // see mbar_arrive_after
 #pragma unroll
             for (int vv = 0; vv < L::V; ++vv) {
                 const int c = L::f4(c0, vv);
@@ -724,6 +734,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
                 for (int s = 0; s < L::K; ++s) {
                     if (g >= nvalid[s]) continue;          // this slot's range is shorter: its stage entry was not filled
                     const float4 h = *reinterpret_cast<const float4*>(&sm.h[st][s * L::G + g_][2 * c]);
+                    dep |= __float_as_uint(h.x);
                     const float h0i = c == 0 ? 0.f : h.y, h0q = c == 0 ? h.y : h.x;    // bin 0 = packed {DC, Nyquist}
                     const float4 xv = x[s][vv];
                     float4& ac = acc[s][vv];
@@ -734,7 +745,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
                 }
             }
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&sm.empty[st]);
+            if ((tid & 31) == 0) mbar_arrive_after(&sm.empty[st], dep & a.zero);
         };
         if (ngroups > 0) load_group(xa, 0);
         for (int g = 0; g < ngroups; g += 2) {

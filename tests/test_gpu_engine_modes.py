@@ -206,6 +206,50 @@ def test_fused_step_is_bit_identical_to_two_launches_and_matches_oracle(eng, orc
         _check(a[c:c + 1], orc.convolve_periodic(x[c], h, B)[:, :n])
 
 
+# ---- the IR ring under load: more tiles than fit on the GPU at once, several laps of the ring -------------------
+def test_ir_ring_release_under_load_fused_equals_two_launches_on_every_channel(eng, orc):
+    """Regression (profiles/r01_ring_release_race.md): with every SM holding three CTAs, a warp's last ld.shared of an IR
+    stage could still be in flight when its release of the stage was seen by the TMA producer; about 1 % of the (tile,
+    block) pairs then used partition g + kStages for half of a warp's bins.  Small cases never showed it, so this one
+    fills the GPU (513 tiles of 4 channels, 444 fit at once) and compares EVERY channel of every block."""
+    B, C, P, nb = 512, 2050, 48, 24
+    rng = np.random.default_rng(11)
+    h = synth.decaying_ir(2000, P * B - 3)
+    x = (rng.random((nb, C, B), dtype=np.float32) * 2 - 1).astype(np.float32)
+    outs = []
+    for fused in (True, False, True):
+        with eng.Engine(B, P, C, 1) as e:
+            e.set_ir(0, h)
+            e.set_fused_step(fused)
+            assert e.mac_plan() == (False, 1, 1)
+            outs.append(np.concatenate([e.process(x[k:k + 8]) for k in range(0, nb, 8)]))
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[2])
+    for c in (0, 1027, C - 1):
+        xc = np.ascontiguousarray(outs[0][:, c, :]).reshape(1, -1)
+        _check(xc, orc.convolve_periodic(np.ascontiguousarray(x[:, c, :]).reshape(-1), h, B)[:, :nb * B])
+
+
+def test_ir_ring_release_under_load_per_stream_irs(eng, orc):
+    """The same for the slot kernel (every tile slot stages its own IR partitions): repeatable and equal to the oracle."""
+    B, C, P, nb = 512, 1640, 20, 16
+    rng = np.random.default_rng(12)
+    hs = [synth.decaying_ir(3000 + c % 7, P * B - (c % 5), c % 2) for c in range(C)]
+    x = (rng.random((nb, C, B), dtype=np.float32) * 2 - 1).astype(np.float32)
+    outs = []
+    for rep in range(2):
+        with eng.Engine(B, P, C, C) as e:
+            for c in range(C):
+                e.set_ir(c, hs[c])
+                e.bind(c, c + 1, c)
+            assert e.mac_plan()[0]
+            outs.append(np.concatenate([e.process(x[k:k + 8]) for k in range(0, nb, 8)]))
+    assert np.array_equal(outs[0], outs[1])
+    for c in (0, 821, C - 1):
+        xc = np.ascontiguousarray(outs[0][:, c, :]).reshape(1, -1)
+        _check(xc, orc.convolve_periodic(np.ascontiguousarray(x[:, c, :]).reshape(-1), hs[c], B)[:, :nb * B])
+
+
 def test_fused_step_with_staged_ir_refresh_rows(eng, orc):
     """Round-robin IR refresh rows still run (their own k_fwd launch) next to the fused block step."""
     B, C, P = 256, 600, 6
