@@ -3,7 +3,7 @@
   ncu -i gpurun_out/prof_mac.ncu-rep --page raw --csv > /tmp/mac_raw.csv
   python profiles/summarize_ncu.py full /tmp/mac_raw.csv profiles/rNN_k_mac_ncu_full_summary.csv
   python profiles/summarize_ncu.py launches gpurun_out/launches.csv profiles/rNN_launches_summary.csv "<command>"
-  python profiles/summarize_ncu.py traffic /tmp/mac_raw.csv profiles/traffic.json <streams> <block> <partitions>
+  python profiles/summarize_ncu.py traffic /tmp/mac_raw.csv profiles/traffic.json <streams> <block> <partitions> [fused=1]
 """
 import collections
 import csv
@@ -36,15 +36,19 @@ def full(src, dst):
                 f.write('%s,%s,%s\n' % (k, units[i], ','.join('"%s"' % r[i] if ',' in r[i] else r[i] for r in rows[2:])))
 
 
-def traffic(src, dst, streams, block, parts):
+def traffic(src, dst, streams, block, parts, fused=1):
     rows = list(csv.reader(open(src)))
     hdr, units = rows[0], rows[1]
     ri, wi = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
     rd = sum(float(r[ri]) for r in rows[2:]) / (len(rows) - 2) * MUL[units[ri]]
     wr = sum(float(r[wi]) for r in rows[2:]) / (len(rows) - 2) * MUL[units[wi]]
+    alg = (streams + 1) * parts * (block + 1) * 8 + (streams * ((block + 1) * 8 + 2 * block * 4) if fused else 0)
     json.dump({"kernel": rows[2][hdr.index('Kernel Name')], "streams": streams, "block": block, "partitions": parts, "dram_bytes_per_launch": rd + wr,
-               "dram_read_bytes": rd, "dram_write_bytes": wr, "algorithmic_bytes_per_launch": (streams + 1) * parts * (block + 1) * 8,
-               "source": "ncu --set full --clock-control none (%d launches averaged)" % (len(rows) - 2)}, open(dst, 'w'), indent=1)
+               "fused": bool(fused), "dram_read_bytes": rd, "dram_write_bytes": wr,
+               # FDL + shared IR; the fused step also writes the new spectrum and moves the audio block in and out
+               "algorithmic_bytes_per_launch": alg, "ratio": (rd + wr) / alg,
+               "source": "ncu --set full --clock-control none (%d launches averaged): python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-selfcheck" % (len(rows) - 2)},
+              open(dst, 'w'), indent=1)
 
 
 def launches(src, dst, cmd):
@@ -69,6 +73,6 @@ if __name__ == '__main__':
     if mode == 'full':
         full(sys.argv[2], sys.argv[3])
     elif mode == 'traffic':
-        traffic(sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]))
+        traffic(sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]), int(sys.argv[7]) if len(sys.argv) > 7 else 1)
     else:
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else '')

@@ -230,6 +230,25 @@ def test_ir_ring_release_under_load_fused_equals_two_launches_on_every_channel(e
         _check(xc, orc.convolve_periodic(np.ascontiguousarray(x[:, c, :]).reshape(-1), h, B)[:, :nb * B])
 
 
+@pytest.mark.parametrize("B,C,P,nb", [(256, 4100, 24, 16), (1024, 1100, 14, 16), (2048, 620, 11, 8), (100, 8200, 30, 16), (64, 20000, 40, 16)])
+def test_full_gpu_block_steps_other_block_sizes(eng, orc, B, C, P, nb):
+    """Every FFT size of the streaming kernels with more tiles than the GPU holds at once and several ring laps."""
+    rng = np.random.default_rng(13)
+    h = synth.decaying_ir(2000, P * B - 1)
+    x = (rng.random((nb, C, B), dtype=np.float32) * 2 - 1).astype(np.float32)
+    outs = []
+    for fused in (True, False):
+        with eng.Engine(B, P, C, 1) as e:
+            e.set_ir(0, h)
+            e.set_fused_step(fused)
+            assert e.mac_plan() == (False, 1, 1)
+            outs.append(np.concatenate([e.process(x[k:k + 8]) for k in range(0, nb, 8)]))
+    assert np.array_equal(outs[0], outs[1])
+    for c in (0, C // 2, C - 1):
+        xc = np.ascontiguousarray(outs[0][:, c, :]).reshape(1, -1)
+        _check(xc, orc.convolve_periodic(np.ascontiguousarray(x[:, c, :]).reshape(-1), h, B)[:, :nb * B])
+
+
 def test_ir_ring_release_under_load_per_stream_irs(eng, orc):
     """The same for the slot kernel (every tile slot stages its own IR partitions): repeatable and equal to the oracle."""
     B, C, P, nb = 512, 1640, 20, 16

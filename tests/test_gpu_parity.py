@@ -107,6 +107,13 @@ def test_convolve_periodic_ragged_lengths_and_unflushed_tail(eng, orc, Lx, Lh, B
     assert not got[:, written:].any()            # the reference never flushes the last overlap (D6)
 
 
+def test_convolve_periodic_long_input_fills_the_gpu(eng, orc):
+    """Offline form with more tiles than the GPU holds at once (60 s stereo = 2 x 5625 output blocks, 94 partitions)."""
+    x = np.stack([synth.white_noise(1001, c, 60 * 48000) for c in range(2)])
+    h = synth.decaying_ir(2000, 48000)
+    _check(eng.convolve_periodic(x, h, 512), orc.convolve_periodic(x, h, 512))
+
+
 def test_convolve_periodic_sine_input(eng, orc):
     x = synth.sine(20000)
     h = synth.decaying_ir(2000, 4800)
