@@ -156,6 +156,28 @@ int launch_fwd_t(const irb::FwdArgs& a, cudaStream_t st) {
     CK(cudaGetLastError());
     return 0;
 }
+// the fused block step with the FDL streamed through TMA (k_mac_tma); IRB_MAC_TMA=0 selects the register-staged k_mac<FUSE>
+bool mac_tma_pref() {
+    static bool w = [] { const char* s = getenv("IRB_MAC_TMA"); return s ? atoi(s) != 0 : true; }();
+    return w;
+}
+template <int M>
+int launch_mac_tma(const irb::MacArgs& a, cudaStream_t st) {
+    const int grid = (a.n_rows + irb::Tile<M>::ROWS - 1) / irb::Tile<M>::ROWS;
+    if (grid <= 0) return 0;
+    const size_t smem = sizeof(irb::TmaSmem<M>);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CK(cudaFuncSetAttribute(irb::k_mac_tma<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured_dev = dev;
+    }
+    irb::k_mac_tma<M><<<grid, irb::kThreads + 32, smem, st>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
 template <int M, int U, bool INV, bool FUSE = false, bool WIDE = false>
 int launch_mac_u(const irb::MacArgs& a, cudaStream_t st) {
     const int grid = (a.n_rows + irb::Tile<M>::ROWS - 1) / irb::Tile<M>::ROWS;
@@ -219,6 +241,7 @@ int launch_mac_t(const irb::MacArgs& a, bool slots, int cl, cudaStream_t st) {
     if (slots) return launch_slots_t<M, INV>(a, cl, st);
     if constexpr (INV) {
         if (a.head) {                                   // streaming block step
+            if constexpr (M >= 256) { if (a.in && a.blocks_per_chan == 1 && mac_tma_pref()) return launch_mac_tma<M>(a, st); }
             if constexpr (M <= 512) {
                 if (mac_wide_pref() && mac_u_pref() == 2) return a.in ? launch_mac_u<M, 2, true, true, true>(a, st) : launch_mac_u<M, 2, true, false, true>(a, st);
             }

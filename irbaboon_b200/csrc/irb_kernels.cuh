@@ -584,6 +584,182 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
 }
 
 // ===================================================================================================
+// k_mac_tma: the fused streaming block step (k_mac<FUSE>'s job) with the FDL ITSELF streamed through TMA.
+//
+// A ring stage holds one partition of the tile's IR (M spectra bins) AND the tile's FDL slots for that partition (all ROWS rows,
+// 16 KB), both written by bulk async copies of the producer warp's elected lane; the eight compute warps read them with
+// conflict-free 16-byte shared-memory loads.  Against the register-staged loads of k_mac this keeps 3 stages x 20 KB x 3 CTAs
+// = 180 KB of reads in flight per SM instead of 96 KB, issues no global load, no pointer or ring-wrap arithmetic in the
+// compute warps, and frees the registers of the double buffer.  With the tile-interleaved FDL and equal heads (the normal
+// case) a stage's FDL part is ONE 16 KB copy; rows with different heads, or the plain layout, get one copy per row.
+// Stage 0's FDL area doubles as the FFT / epilogue tile: the prologue is finished with it before any warp releases stage 0
+// for the first time (group 0 needs no FDL data: partition 0 is the new block's spectrum, held in registers), and the
+// epilogue takes it back behind a barrier that follows every warp's last group.
+// Same fmaf sequence per bin as k_mac / k_fwd: results are bit-identical to the two-launch form.
+constexpr int kTmaStages = 3;
+template <int M>
+struct TmaSmem {
+    struct Stage { float2 x[kTile]; float2 h[M]; };
+    Stage st[kTmaStages];
+    uint64_t full[kTmaStages], empty[kTmaStages];
+    int hd[kTile / M];                                   // old heads of the tile's rows (-1: dead row)
+};
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
+template <int M>
+__global__ void __launch_bounds__(kThreads + 32, M <= 1024 ? 3 : 2) k_mac_tma(const MacArgs a) {
+    using T = Tile<M>;
+    using L = MacLayout<M, false>;                        // narrow: consecutive lanes read consecutive float4 of shared memory
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TmaSmem<M>& sm = *reinterpret_cast<TmaSmem<M>*>(smem_raw);
+    float2* spec = sm.st[0].x;
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * T::ROWS;                // blocks_per_chan == 1: a row is a channel
+    const int ir = a.ir_of_chan ? a.ir_of_chan[row0] : 0;
+    const int np = a.nparts[ir];
+
+    if (tid == 0) {
+        for (int i = 0; i < kTmaStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], kThreads / 32); }
+        mbar_fence_init();
+    }
+    if (tid < T::ROWS) {
+        int hd = -1;
+        if (row0 + tid < a.n_rows) { hd = a.head[row0 + tid] - a.head_back; if (hd < 0) hd += a.ring; }
+        sm.hd[tid] = hd;
+    }
+    __syncthreads();                                      // the heads are read; they are advanced after the prologue
+
+    if (tid >= kThreads) {
+        // ===== TMA producer =====
+        if (tid == kThreads) {
+            const float2* hsrc = a.H + ir * a.ir_stride;
+            const long long sstride = fdl_slot_stride<M>(a);
+            int nlive = 0;
+            bool uni = a.fdl_group == T::ROWS;
+            for (int r = 0; r < T::ROWS; ++r) {
+                if (sm.hd[r] >= 0) { ++nlive; uni = uni && sm.hd[r] == sm.hd[0]; }
+            }
+            const uint64_t pol = l2_policy_evict_first();
+            int back = 0;                                 // partition g >= 1 meets slot (hd - (g - 1)) mod ring
+            for (int g = 0; g < np; ++g) {
+                const int st = g % kTmaStages;
+                if (g >= kTmaStages) mbar_wait_relaxed(&sm.empty[st], ((g / kTmaStages) - 1) & 1, a.producer_sleep_ns);
+                const uint32_t hb = M * sizeof(float2);
+                mbar_expect_tx(&sm.full[st], hb + (g > 0 ? (uint32_t) nlive * hb : 0u));
+                tma_bulk_g2s(sm.st[st].h, hsrc + (long long) g * M, hb, &sm.full[st]);
+                if (g > 0) {
+                    if (uni) {
+                        int sl = sm.hd[0] - back; if (sl < 0) sl += a.ring;
+                        tma_bulk_g2s_hint(sm.st[st].x, a.fdl + fdl_row_offset(a, row0, M) + (long long) sl * sstride, (uint32_t) nlive * hb, &sm.full[st], pol);
+                    } else {
+                        for (int r = 0; r < nlive; ++r) {
+                            int sl = sm.hd[r] - back; if (sl < 0) sl += a.ring;
+                            tma_bulk_g2s_hint(sm.st[st].x + r * M, a.fdl + fdl_row_offset(a, row0 + r, M) + (long long) sl * sstride, hb, &sm.full[st], pol);
+                        }
+                    }
+                    if (++back >= a.ring) back = 0;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== forward transform of the tile's new blocks (FFT layout), spectrum -> FDL slot head+1 and registers =====
+    {
+        const int rf = tid / T::TPF, t = tid % T::TPF;
+        const int row = row0 + rf;
+        float2 v[kPts];
+#pragma unroll
+        for (int j = 0; j < kPts; ++j) v[j] = make_float2(0.f, 0.f);
+        if (row < a.n_rows) {
+            const float* p = a.in + row * a.in_chan_stride;
+#pragma unroll
+            for (int j = 0; j < kPts; ++j) {
+                const int m = 2 * (t + j * T::TPF);
+                if (m < a.B) v[j].x = p[m];
+                if (m + 1 < a.B) v[j].y = p[m + 1];
+            }
+        }
+        float2* srow = spec + rf * M;
+        fft_run<M, false>(v, t, srow, a.W);
+        bar_compute();
+#pragma unroll
+        for (int j = 0; j < kPts; ++j) srow[t + j * T::TPF] = v[j];
+        bar_compute();
+    }
+    const int g_ = tid / L::TPR, c0 = tid % L::TPR;
+    float4 x0[L::K][L::V], acc[L::K][L::V];
+#pragma unroll
+    for (int s = 0; s < L::K; ++s) {
+        const int rl = s * L::G + g_, hd = sm.hd[rl];
+#pragma unroll
+        for (int vv = 0; vv < L::V; ++vv) { x0[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f); acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        if (hd >= 0) {
+            const int ns = hd + 1 >= a.ring ? 0 : hd + 1;
+            const float2* z = spec + rl * M;
+            float4* d = reinterpret_cast<float4*>(const_cast<float2*>(a.fdl) + fdl_row_offset(a, row0 + rl, M) + (long long) ns * fdl_slot_stride<M>(a));
+#pragma unroll
+            for (int vv = 0; vv < L::V; ++vv) {
+                const int k = 2 * L::f4(c0, vv);
+                const float2 s0 = real_split(z[k], z[(M - k) & (M - 1)], root<false>(a.W, k), k);
+                const float2 s1 = real_split(z[k + 1], z[M - k - 1], root<false>(a.W, k + 1), k + 1);
+                x0[s][vv] = make_float4(s0.x, s0.y, s1.x, s1.y);
+                d[L::f4(c0, vv)] = x0[s][vv];
+            }
+        }
+    }
+    bar_compute();                                        // the tile (stage 0's FDL area) is free; nobody has released stage 0 yet
+    if (tid < T::ROWS && row0 + tid < a.n_rows) { const int h = a.head_rw[row0 + tid] + 1; a.head_rw[row0 + tid] = h >= a.ring ? 0 : h; }
+
+    // ===== multiply-accumulate over the partitions, ascending (fp/convolution.cpp:171-202) =====
+    for (int g = 0; g < np; ++g) {
+        const int st = g % kTmaStages;
+        mbar_wait(&sm.full[st], (g / kTmaStages) & 1);
+        uint32_t dep = 0;                                 // see mbar_arrive_after
+#pragma unroll
+        for (int vv = 0; vv < L::V; ++vv) {
+            const int c = L::f4(c0, vv);
+            const float4 h = *reinterpret_cast<const float4*>(&sm.st[st].h[2 * c]);
+            dep |= __float_as_uint(h.x);
+            const float h0i = c == 0 ? 0.f : h.y, h0q = c == 0 ? h.y : h.x;        // bin 0 = packed {DC, Nyquist}
+#pragma unroll
+            for (int s = 0; s < L::K; ++s) {
+                float4 xv = x0[s][vv];
+                if (g > 0) {
+                    xv = *reinterpret_cast<const float4*>(&sm.st[st].x[(s * L::G + g_) * M + 2 * c]);
+                    dep |= __float_as_uint(xv.x);
+                }
+                float4& ac = acc[s][vv];
+                ac.x = fmaf(xv.x, h.x, fmaf(-xv.y, h0i, ac.x));
+                ac.y = fmaf(xv.y, h0q, fmaf(xv.x, h0i, ac.y));
+                ac.z = fmaf(xv.z, h.z, fmaf(-xv.w, h.w, ac.z));
+                ac.w = fmaf(xv.w, h.z, fmaf(xv.z, h.w, ac.w));
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive_after(&sm.empty[st], dep & a.zero);
+    }
+
+    bar_compute();                                        // every warp is through its last group: stage 0 is the tile again
+#pragma unroll
+    for (int s = 0; s < L::K; ++s)
+#pragma unroll
+        for (int vv = 0; vv < L::V; ++vv)
+            reinterpret_cast<float4*>(spec + (s * L::G + g_) * M)[L::f4(c0, vv)] = acc[s][vv];
+    bar_compute();
+    inv_epilogue<M>(a, spec, tid, row0, T::ROWS);
+}
+
+// ===================================================================================================
 // k_mac_slots: the MAC for (a) rows that do NOT share an IR inside a tile (per-stream IRs, BASELINE config 4) and
 // (b) FEW rows (the single-stream latency path, BASELINE config 2), where one CTA per tile would leave the GPU idle
 // and the load chain of a single row is latency-bound.
