@@ -291,8 +291,10 @@ def run_b200(args):
     mac_avg_ms = float(np.mean(mac_ms)) if len(mac_ms) else float("nan")
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (mac_avg_ms * 1e-3) / 1e9
+    tma = fused and e.fft_size // 2 >= 256 and os.environ.get("IRB_MAC_TMA", "1") != "0"      # the dispatch rule of launch_mac_t (irb_engine.cu)
     kname = "k_mac_slots<%d,INV> (per-stream-IR FDL multiply-accumulate + inverse FFT + overlap-add)" % (e.fft_size // 2) if per_stream_ir else \
-            ("k_mac<%d,INV,FUSE> (one launch per block step: forward FFT + FDL multiply-accumulate + inverse FFT + overlap-add)" if fused else
+            ("k_mac_tma<%d> (one launch per block step: forward FFT + TMA-streamed FDL multiply-accumulate + inverse FFT + overlap-add)" if tma else
+             "k_mac<%d,INV,FUSE> (one launch per block step: forward FFT + FDL multiply-accumulate + inverse FFT + overlap-add)" if fused else
              "k_mac<%d,INV> (FDL multiply-accumulate + inverse FFT + overlap-add)") % (e.fft_size // 2)
     roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
@@ -302,7 +304,8 @@ def run_b200(args):
     if os.path.exists(prof):
         try:
             tj = json.load(open(prof))
-            if tj.get("streams") == S and tj.get("block") == B and tj.get("partitions") == P and bool(tj.get("fused", False)) == fused:
+            if tj.get("streams") == S and tj.get("block") == B and tj.get("partitions") == P and bool(tj.get("fused", False)) == fused \
+                    and ("k_mac_tma" in tj.get("kernel", "")) == tma:
                 roof["traffic"] = tj["dram_bytes_per_launch"]
         except Exception:
             pass
