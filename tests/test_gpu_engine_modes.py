@@ -375,3 +375,35 @@ def test_submit_wait_keeps_state_and_results_of_the_synchronous_path(eng):
             e.submit(hin[0:1], hout[0:1])
         eng.pinned_free(hin); eng.pinned_free(hout)
     assert np.array_equal(got, want)
+
+
+def test_host_pipeline_equals_device_resident_steps_at_scale(eng):
+    """The three-stage host pipeline (upload | kernels | download over double-buffered staging, irb_engine_process /
+    submit / wait) and the single-large-block path against block steps on device-resident buffers: same bits, with enough
+    channels (32 MB per block) that copies and kernels of neighbouring blocks really overlap."""
+    torch = pytest.importorskip("torch")
+    B, C, P, nb = 512, 16384, 12, 12
+    rng = np.random.default_rng(21)
+    h = synth.decaying_ir(2000, P * B - 2)
+    x = (rng.random((nb, C, B), dtype=np.float32) * 2 - 1).astype(np.float32)
+    with eng.Engine(B, P, C, 1) as e:
+        e.set_ir(0, h)
+        d_in = torch.from_numpy(x).cuda()
+        d_out = torch.empty((nb, C, B), device="cuda", dtype=torch.float32)
+        torch.cuda.synchronize()
+        for k in range(nb):
+            e.process_device(d_in[k].data_ptr(), d_out[k].data_ptr(), 1)
+        e.synchronize()
+        want = d_out.cpu().numpy()
+        e.reset()
+        got = np.concatenate([e.process(x[0:5]), e.process(x[5:6]), e.process(x[6:12])])      # pipeline, one large block, pipeline
+        assert np.array_equal(got, want)
+        e.reset()
+        hin, hout = eng.pinned_empty((nb, C, B)), eng.pinned_empty((nb, C, B))
+        hin[:] = x
+        e.submit(hin[:7], hout[:7])
+        e.submit(hin[7:], hout[7:])
+        e.wait()
+        assert np.array_equal(hout, want)
+        eng.pinned_free(hin)
+        eng.pinned_free(hout)
