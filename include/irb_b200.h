@@ -133,6 +133,11 @@ double irb_last_compute_ms(void);
 /* the pure FDL multiply-accumulate (no inverse FFT) on the current state into a device buffer of
  * n_channels * M complex; used to time the roofline kernel in isolation */
 int irb_engine_mac_only_device(irb_engine* e, float* acc_dev);
+/* Measurement aid, not part of the path: GB/s of a kernel that does nothing but read `bytes` of device memory once per
+ * iteration with the MAC kernels' own 32-byte streaming loads (L1 no-allocate, L2 evict-first), grid = resident CTAs;
+ * averaged over `iters` launches after one warm-up.  Gives the read-only ceiling the FDL stream can be held against
+ * (the roofline's `peak` stays the driver-measured copy bandwidth). */
+int irb_hbm_read_probe(size_t bytes, int iters, double* gbs);
 
 /* ---- several GPUs from one process ---------------------------------------------------------------------
  * Streams never interact (fp/convolution.cpp:160-215 has no cross-channel term), so n_channels are cut into contiguous

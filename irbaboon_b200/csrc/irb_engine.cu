@@ -921,6 +921,32 @@ int irb_engine_read_fdl_spectrum(irb_engine* e, int chan, int age, float* out_pa
     return 0;
 }
 
+int irb_hbm_read_probe(size_t bytes, int iters, double* gbs) {
+    if (!gbs || iters < 1 || bytes < (1u << 20)) return fail(IRB_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(irbh::g_device));
+    const size_t pieces = bytes / 16384;
+    DevBuf buf, sink;
+    int rc;
+    if ((rc = buf.alloc(pieces * 16384, true)) || (rc = sink.alloc(sizeof(unsigned), true))) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, irbh::g_device);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int grid = sms * 4;                                  // 4 x 512 threads resident per SM
+    irb::k_read_probe<<<grid, 512>>>(buf.as<float4>(), pieces, sink.as<unsigned>());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) irb::k_read_probe<<<grid, 512>>>(buf.as<float4>(), pieces, sink.as<unsigned>());
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    g_launches += iters + 1;
+    *gbs = (double) (pieces * 16384) * iters / (ms * 1e-3) / 1e9;
+    return 0;
+}
+
 int irb_engine_mac_only_device(irb_engine* e, float* acc_dev) {
     if (!e || !acc_dev) return fail(IRB_ERR_ARG, "null argument");
     CK(cudaSetDevice(e->device));

@@ -999,6 +999,26 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
     }
 }
 
+// read-only bandwidth probe (irb_hbm_read_probe): every CTA walks the buffer grid-strided in 16 KB pieces, four independent
+// 32-byte loads per thread in flight; the XOR of everything read is stored only if it equals a value it never takes
+static __global__ void __launch_bounds__(512) k_read_probe(const float4* __restrict__ p, size_t n_pieces, unsigned* sink) {
+    unsigned acc = 0;
+    size_t piece = blockIdx.x;
+    for (; piece + 3 * (size_t) gridDim.x < n_pieces; piece += 4 * (size_t) gridDim.x) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ldg_stream256(p + (piece + u * (size_t) gridDim.x) * 1024 + 2 * threadIdx.x, a[u], b[u]);   // 16 KB = 512 threads x 32 bytes
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc ^= __float_as_uint(a[u].x) ^ __float_as_uint(a[u].w) ^ __float_as_uint(b[u].y) ^ __float_as_uint(b[u].z);
+    }
+    for (; piece < n_pieces; piece += gridDim.x) {
+        float4 a, b;
+        ldg_stream256(p + piece * 1024 + 2 * threadIdx.x, a, b);
+        acc ^= __float_as_uint(a.x) ^ __float_as_uint(a.w) ^ __float_as_uint(b.y) ^ __float_as_uint(b.z);
+    }
+    if (acc == 0x7fc12345u) *sink = acc;
+}
+
 // (a + b) / 2 : tools::sumToMono (fp/tools.cpp:25-29)
 static __global__ void k_fold_mono(const float* l, const float* r, float* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -63,6 +63,7 @@ _SIGS = {
     "irb_release_workspace": (ctypes.c_size_t, []),
     "irb_last_compute_ms": (ctypes.c_double, []),
     "irb_engine_mac_only_device": (ctypes.c_int, [_vp, _vp]),
+    "irb_hbm_read_probe": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "irb_group_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_int)] + [ctypes.c_int] * 5),
     "irb_group_destroy": (ctypes.c_int, [_vp]),
     "irb_group_device_count": (ctypes.c_int, [_vp]),
@@ -135,6 +136,13 @@ def release_workspace():
 
 def last_compute_ms():
     return lib().irb_last_compute_ms()
+
+
+def hbm_read_probe(nbytes, iters=5):
+    """GB/s of a read-only streaming kernel over nbytes of device memory (measurement aid)."""
+    g = ctypes.c_double(0.0)
+    _ck(lib().irb_hbm_read_probe(int(nbytes), int(iters), ctypes.byref(g)))
+    return g.value
 
 
 def pinned_empty(shape, dtype=np.float32):
