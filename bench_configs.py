@@ -231,6 +231,19 @@ def c5(eng, synth, args):
                     "captures_per_s_device": nb / dev, "min_bytes_per_capture": 2 * n * 4, "four_step_bytes_per_capture": four_step,
                     "device_gbs_at_four_step_bytes": nb * four_step / dev / 1e9, "frac_of_measured_peak": nb * four_step / dev / 1e9 / peak(),
                     "peak_abs": float(np.abs(y).max())}
+    # secondary: the Farina form of the same capture, convolveNonPeriodic(capture, inverse sweep) at N = 2^21,
+    # one irb_convolve_nonperiodic call per capture (no batched entry point: the plug-in itself deconvolves by division)
+    sweep_inv = eng.ess(n / SR, SR, 20.0, 24000.0, 0.0, True).astype(np.float32)
+    eng.convolve_nonperiodic(caps[0], sweep_inv)
+    kf, ts, dev = min(nb, 8), [], []
+    for j in range(kf):
+        t0 = time.perf_counter()
+        yf = eng.convolve_nonperiodic(caps[j], sweep_inv)
+        ts.append(time.perf_counter() - t0)
+        dev.append(eng.last_compute_ms() * 1e-3)
+    out["farina_variant"] = {"what": "convolveNonPeriodic(capture, ExpSineSweep inverse filter), N = 2^21, one call per capture, pageable result",
+                             "captures": kf, "wall_seconds_per_capture_median": float(np.median(ts)), "device_seconds_per_capture_median": float(np.median(dev)),
+                             "output_samples": int(yf.shape[1])}
     try:
         import oracle
         if oracle.have_reference():
