@@ -717,7 +717,10 @@ __global__ void __launch_bounds__(kThreads + 32, M <= 1024 ? 3 : 2) k_mac_tma(co
             }
         }
     }
-    bar_compute();                                        // the tile (stage 0's FDL area) is free; nobody has released stage 0 yet
+    // the tile (stage 0's FDL area) was written and read through the generic proxy; the bulk copy of partition kTmaStages writes it
+    // through the async proxy once every warp has released stage 0: order the two proxies once per tile, ahead of that release
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    bar_compute();                                        // the tile is free; nobody has released stage 0 yet
     if (tid < T::ROWS && row0 + tid < a.n_rows) { const int h = a.head_rw[row0 + tid] + 1; a.head_rw[row0 + tid] = h >= a.ring ? 0 : h; }
 
     // ===== multiply-accumulate over the partitions, ascending (fp/convolution.cpp:171-202) =====
