@@ -13,8 +13,11 @@
 // Reference loops replaced (paths relative to /root/reference):
 //   k_fwd       fp/convolution.cpp:106-125 (IR partition load + FFT), :128-149 (audio block load + FFT),
 //               Source/PluginProcessor.cpp:430-436,455-461 (incl. the round-robin IR refresh rows)
-//   k_mac       fp/convolution.cpp:160-215 (MAC over partitions, inverse FFT, overlap-add), Source/PluginProcessor.cpp:480-510;
-//               with FUSE also k_fwd's work for the tile's new blocks: one launch per streaming block step
+//   k_mac_tma   the streaming block step of shared-IR tiles in ONE launch (FFT half sizes >= 256): k_fwd's work for the tile's new
+//               blocks, then fp/convolution.cpp:160-215 / Source/PluginProcessor.cpp:480-510 with the FDL slots AND the IR
+//               partitions streamed by TMA into a 3-stage shared-memory ring, inverse FFT, overlap-add
+//   k_mac       the same loop with the FDL staged through registers (coalesced 16- / 32-byte loads): offline form, two-launch
+//               streaming form, small FFT sizes; with FUSE also k_fwd's work (the A/B partner of k_mac_tma)
 //   k_mac_slots the same loop when a tile's rows do not share an IR (per-stream IRs) or when there are so few rows that
 //               each row's partitions are split over tile slots and the CTAs of a thread-block cluster
 //   k_ola_tail  fp/convolution.cpp:210-213 for the offline (all blocks at once) formulation
