@@ -42,6 +42,20 @@ def test_hot_kernel_uses_bulk_tma_and_128bit_loads(eng):
     assert "cufft" not in ldd.lower()
 
 
+def test_headline_kernel_streams_fdl_and_ir_through_tma(eng):
+    """SASS of k_mac_tma<512> (the block step behind the headline number): the FDL slots and the IR partitions arrive by bulk
+    TMA copies (the FDL ones with an L2 cache-policy descriptor), there is no global load wider than the 8-byte twiddle /
+    4-byte audio loads of the FFT prologue, and the stage release is predicated on one lane (the arrive whose address
+    carries the data dependency on the values read, see mbar_arrive_after)."""
+    import subprocess
+    sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", "-fun", "_ZN3irb9k_mac_tmaILi512EEEvNS_7MacArgsE", eng.LIB_PATH],
+                          capture_output=True, text=True).stdout
+    assert sass.count("UBLKCP") >= 3 and re.search(r"UBLKCP[^;]*desc\[", sass)
+    assert not re.search(r"LDG\.E\.[A-Z0-9.]*(128|256)", sass)
+    assert "FENCE.VIEW.ASYNC" in sass                                   # generic -> async proxy hand-over of stage 0's memory
+    assert re.search(r"@!?P\d SYNCS\.ARRIVE", sass) and "LDS.128" in sass
+
+
 def test_argument_validation_without_a_device(eng):
     L = eng.lib()
     h = ctypes.c_void_p()
