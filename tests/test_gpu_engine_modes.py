@@ -249,6 +249,30 @@ def test_full_gpu_block_steps_other_block_sizes(eng, orc, B, C, P, nb):
         _check(xc, orc.convolve_periodic(np.ascontiguousarray(x[:, c, :]).reshape(-1), h, B)[:, :nb * B])
 
 
+@pytest.mark.parametrize("B,np_ir", [(512, 0), (512, 1), (512, 2), (512, 3), (512, 4), (256, 2), (1024, 1), (2048, 2)])
+def test_fused_step_with_fewer_partitions_than_ring_stages(eng, orc, B, np_ir):
+    """IRs shorter than the TMA ring (0 = no IR loaded at all: silence, no hang), inside a longer FDL ring, GPU full."""
+    C, ring, nb = 2050 * 512 // B, 8, 10
+    rng = np.random.default_rng(17)
+    x = (rng.random((nb, C, B), dtype=np.float32) * 2 - 1).astype(np.float32)
+    h = synth.decaying_ir(2000, np_ir * B - 1) if np_ir else None
+    outs = []
+    for fused in (True, False):
+        with eng.Engine(B, ring, C, 1) as e:
+            if h is not None:
+                e.set_ir(0, h)
+                assert e.partitions(0) == np_ir
+            e.set_fused_step(fused)
+            outs.append(e.process(x))
+    assert np.array_equal(outs[0], outs[1])
+    if h is None:
+        assert not outs[0].any()
+    else:
+        for c in (0, C - 1):
+            xc = np.ascontiguousarray(outs[0][:, c, :]).reshape(1, -1)
+            _check(xc, orc.convolve_periodic(np.ascontiguousarray(x[:, c, :]).reshape(-1), h, B)[:, :nb * B])
+
+
 def test_ir_ring_release_under_load_per_stream_irs(eng, orc):
     """The same for the slot kernel (every tile slot stages its own IR partitions): repeatable and equal to the oracle."""
     B, C, P, nb = 512, 1640, 20, 16
