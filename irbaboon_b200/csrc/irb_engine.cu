@@ -933,9 +933,12 @@ int irb_hbm_read_probe(size_t bytes, int iters, double* gbs) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const int grid = sms * 4;                                  // 4 x 512 threads resident per SM
-    irb::k_read_probe<<<grid, 512>>>(buf.as<float4>(), pieces, sink.as<unsigned>());
+    // IRB_PROBE_WRITE_EVERY=n: every n-th 16 KB piece is written instead of read (how much a small write share costs the stream)
+    static const int write_every = [] { const char* v = getenv("IRB_PROBE_WRITE_EVERY"); return v ? atoi(v) : 0; }();
+    static const int store_kind = [] { const char* v = getenv("IRB_PROBE_STORE_KIND"); return v ? atoi(v) : 0; }();   // 0 plain, 1 .cs, 2 L2 evict_first, 3 .wt, 4 .cg, 5 L2 evict_last
+    irb::k_read_probe<<<grid, 512>>>(buf.as<float4>(), pieces, sink.as<unsigned>(), write_every, store_kind);
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) irb::k_read_probe<<<grid, 512>>>(buf.as<float4>(), pieces, sink.as<unsigned>());
+    for (int i = 0; i < iters; ++i) irb::k_read_probe<<<grid, 512>>>(buf.as<float4>(), pieces, sink.as<unsigned>(), write_every, store_kind);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     CK(cudaGetLastError());

@@ -1007,13 +1007,31 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
 
 // read-only bandwidth probe (irb_hbm_read_probe): every CTA walks the buffer grid-strided in 16 KB pieces, four independent
 // 32-byte loads per thread in flight; the XOR of everything read is stored only if it equals a value it never takes
-static __global__ void __launch_bounds__(512) k_read_probe(const float4* __restrict__ p, size_t n_pieces, unsigned* sink) {
+__device__ __forceinline__ void probe_store(float4* q, float4 v, int kind, uint64_t pol) {
+    if (kind == 1) asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    else if (kind == 2) asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+    else if (kind == 3) asm volatile("st.global.wt.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    else if (kind == 4) asm volatile("st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    else *q = v;
+}
+static __global__ void __launch_bounds__(512) k_read_probe(float4* __restrict__ p, size_t n_pieces, unsigned* sink, int write_every, int store_kind) {
+    uint64_t pol = 0;
+    if (store_kind == 2) pol = l2_policy_evict_first();
+    if (store_kind == 5) { asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); }
+    const int sk = store_kind == 5 ? 2 : store_kind;
     unsigned acc = 0;
     size_t piece = blockIdx.x;
     for (; piece + 3 * (size_t) gridDim.x < n_pieces; piece += 4 * (size_t) gridDim.x) {
         float4 a[4], b[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) ldg_stream256(p + (piece + u * (size_t) gridDim.x) * 1024 + 2 * threadIdx.x, a[u], b[u]);   // 16 KB = 512 threads x 32 bytes
+        for (int u = 0; u < 4; ++u) {
+            float4* q = p + (piece + u * (size_t) gridDim.x) * 1024 + 2 * threadIdx.x;         // 16 KB = 512 threads x 32 bytes
+            const size_t pc = piece + u * (size_t) gridDim.x;
+            if (write_every > 0 && pc % (size_t) write_every == 0) {                          // a share of the pieces is WRITTEN instead
+                probe_store(q, make_float4(1.f, 2.f, 3.f, 4.f), sk, pol); probe_store(q + 1, make_float4(5.f, 6.f, 7.f, 8.f), sk, pol);
+                a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else ldg_stream256(q, a[u], b[u]);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc ^= __float_as_uint(a[u].x) ^ __float_as_uint(a[u].w) ^ __float_as_uint(b[u].y) ^ __float_as_uint(b[u].z);
     }
