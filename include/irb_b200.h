@@ -136,7 +136,9 @@ int irb_engine_mac_only_device(irb_engine* e, float* acc_dev);
 /* Measurement aid, not part of the path: GB/s of a kernel that does nothing but read `bytes` of device memory once per
  * iteration with the MAC kernels' own 32-byte streaming loads (L1 no-allocate, L2 evict-first), grid = resident CTAs;
  * averaged over `iters` launches after one warm-up.  Gives the read-only ceiling the FDL stream can be held against
- * (the roofline's `peak` stays the driver-measured copy bandwidth). */
+ * (the roofline's `peak` stays the driver-measured copy bandwidth).  Environment, read once: IRB_PROBE_WRITE_EVERY=n writes
+ * every n-th 16 KB piece instead of reading it; IRB_PROBE_STORE_KIND selects the store form (0 plain, 1 .cs, 2 L2 evict-first
+ * hint, 3 .wt, 4 .cg, 5 L2 evict-last hint). */
 int irb_hbm_read_probe(size_t bytes, int iters, double* gbs);
 
 /* ---- several GPUs from one process ---------------------------------------------------------------------
