@@ -4,13 +4,21 @@
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on): S independent mono 48 kHz
 streams sharing one 2 s synthetic IR (96 000 taps -> P = 188 partitions), block B = 512.  One STEP = one UPOLA
 block step for all S streams of a rank: forward FFT of the new block into the frequency-domain delay line (FDL),
-multiply-accumulate over all P partitions, inverse FFT, overlap-add.
+multiply-accumulate over all P partitions, inverse FFT, overlap-add -- ONE launch of the persistent kernel k_mac_p.
 
-  value   real-time 48 kHz channels sustained = S * B / (step time) / 48000, inputs resident in HBM
-  e2e     the same through irb_engine_process(): HOST (pinned) buffers, H2D and D2H inside the timed region
-  roofline  the FDL-MAC kernel: algorithmic bytes / its CUDA-event duration vs the measured HBM peak
+  value   real-time 48 kHz channels per GPU that THIS RUN VERIFIED (channels_RT = max S with p99(block step) <
+          B/48000): a short ladder finds the largest stream count whose p99 over >= 300 consecutive steps stays under the
+          10.667 ms block period; the K timed steps then run at that count.  The throughput equivalent S*B/step/48000 is
+          config.channel_samples_per_s / 48000.  With --streams S the ladder is skipped (value_kind says which).
+  e2e     the same metric through irb_engine_submit/_wait: HOST (pinned) buffers, H2D and D2H inside the timed region;
+          e2e.host_copy_ceiling_gbs is a copy-only probe of the same sizes on the same ranks (no kernels),
+          e2e.rt_streams_per_gpu the largest stream count whose block-by-block host round trip stays inside the period
+  roofline  the block-step kernel: algorithmic bytes / its CUDA-event duration vs the measured HBM peak
   cpu_baseline / --impl reference: the reference's own fp::convolution::convolvePeriodic (oracle/_ref, compiled
           unmodified) on the box's host cores, one whole stream per thread
+
+Other workloads (their own metric names; not the headline): --workload c4 = BASELINE configs[3] (per-stream 10 s IRs,
+block 1024, strong scaling over the ranks), --workload c5 = configs[4] (256 x 2^20-sample ESS captures deconvolved).
 
 Launch: `python bench.py --gpus 1` or, for N > 1, under torchrun (one rank per GPU, streams sharded by rank,
 no data-path collective; torch.distributed is used only for the barrier and the max-over-ranks time).
@@ -39,20 +47,24 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=65536, help="streams per GPU (configs[2] names 1024; >= 10k is the north-star target; "
-                                                                "65536 resident streams keep p99 well under the block period)")
+    ap.add_argument("--streams", type=int, default=0, help="c3: fixed streams per GPU (skips the capacity ladder; configs[2] names 1024)")
+    ap.add_argument("--streams-max", type=int, default=98304, help="c3: streams resident per GPU for the capacity ladder (0.77 MB of FDL each)")
+    ap.add_argument("--ladder-steps", type=int, default=300, help="consecutive steps a stream count must hold p99 < block period for")
     ap.add_argument("--block", type=int, default=512)
     ap.add_argument("--ir-seconds", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-selfcheck", action="store_true", help="skip the post-run comparison of the measured block step with its two-launch form")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the post-run comparison with the two-launch form and the CPU reference")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 32))")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target wall time of the bounded CPU sample")
-    ap.add_argument("--two-launch", action="store_true", help="block step as k_fwd + k_mac instead of the fused single launch (A/B measurement)")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4"],
+    ap.add_argument("--two-launch", action="store_true", help="block step as k_fwd + MAC kernel instead of the fused single launch (A/B measurement)")
+    ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE",
+                    help="launch-policy knob of the library (include/irb_b200_bench.h), e.g. mac_persistent=0 for the one-CTA-per-tile kernel")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"],
                     help="c3 (default, the headline line): streams sharing one IR.  c4: BASELINE configs[3], --streams-total streams with PER-STREAM "
-                         "10 s IRs, block 1024, sharded by stream over the ranks (strong scaling; not the headline metric)")
+                         "10 s IRs, block 1024, sharded by stream over the ranks (strong scaling).  c5: configs[4], batched ESS deconvolution")
     ap.add_argument("--streams-total", type=int, default=8192, help="c4: streams of the whole job")
+    ap.add_argument("--captures", type=int, default=256, help="c5: captures per batch (per GPU)")
     a = ap.parse_args()
     if a.workload == "c4":
         a.block, a.ir_seconds = 1024, 10.0
@@ -61,48 +73,99 @@ def parse():
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock, board power and throttle reasons DURING the timed region, sampled through NVML every few milliseconds
+    with host timestamps (so a slow step can be put next to the clock the GPU ran at); nvidia-smi as the fallback."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.005):
+        self.index, self.period, self.rows, self.stop_flag, self.thread, self.proc = index, period_s, [], False, None, None
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
 
     def start(self):
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), float(mhz), float(pw), int(rs)))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        for r in self.rows:
-            if len(r) < 9:
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 9:
                 continue
             try:
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                bits = 0
+                for bit, v in zip([0x8, 0x40, 0x20, 0x4], c[5:9]):
+                    if v.lower().startswith("active"):
+                        bits |= bit
+                self.max_mhz = float(c[2])
+                self.rows.append((time.perf_counter(), float(c[1]), float(c[3]), bits))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+
+    def summary(self, lo=0, hi=None):
+        rows = self.rows[lo:hi]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+        bits = 0
+        for r in rows:
+            bits |= r[3]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(getattr(self, "max_mhz", 0.0)), "sm_mhz_min": float(min(r[1] for r in rows)),
+                "power_w_max": float(max(r[2] for r in rows)), "power_w_median": float(np.median([r[2] for r in rows])), "samples": len(rows),
+                "source": "nvml" if self.h is not None else "nvidia-smi", "reasons": sorted(n for b, n in self.REASONS.items() if bits & b)}
+
+    def near(self, t):
+        """(sm_mhz, power_w, reasons) of the sample closest to host time t"""
+        if not self.rows:
+            return None
+        ts = np.array([r[0] for r in self.rows])
+        r = self.rows[int(np.argmin(np.abs(ts - t)))]
+        return {"sm_mhz": r[1], "power_w": r[2], "reasons": sorted(n for b, n in self.REASONS.items() if r[3] & b), "dt_ms": 1e3 * (r[0] - t)}
 
 
 def measured_peak_gbs():
@@ -122,12 +185,23 @@ def workload(args):
     return B, Lh, P
 
 
+def metric_of(args):
+    if args.workload == "c4":
+        return "48kHz RT channels (block 1024, per-stream 10s IRs)", UNIT
+    if args.workload == "c5":
+        return "ESS IR captures deconvolved per second (2^20-sample sweep, batched)", "captures/s"
+    return METRIC, UNIT
+
+
 # ---------------------------------------------------------------------------------------------------------
 def cpu_reference_sample(args, target_seconds, threads=None, probe=None):
-    """The reference's convolvePeriodic (oracle/_ref; the C port if _ref did not travel) on the host cores:
-    `threads` workers, one whole mono stream each, same IR / block size as the GPU workload."""
+    """The reference's own code (oracle/_ref; the C port if _ref did not travel) on the host cores, a bounded sample of the
+    workload: convolvePeriodic with `threads` workers, one whole mono stream each, same IR / block size as the GPU workload
+    (c3, c4), or deconvolve of 2^20-sample captures, one capture per thread (c5)."""
     import oracle
     from irbaboon_b200 import synth
+    if args.workload == "c5":
+        return cpu_reference_sample_c5(args, target_seconds, threads)
     B, Lh, P = workload(args)
     h = synth.decaying_ir(2000, Lh)
     if oracle.have_reference():
@@ -158,10 +232,48 @@ def cpu_reference_sample(args, target_seconds, threads=None, probe=None):
                       % (streams, Lx / SR, B, Lh, T)}
 
 
+def c5_inputs(n_captures, n=1 << 20, seed=4000):
+    """Synthetic ESS captures: the sweep convolved with short decaying IRs plus a little noise (numpy only: no GPU, no oracle)."""
+    from irbaboon_b200 import synth
+    t = np.arange(n, dtype=np.float64) / SR
+    T = n / SR
+    w1, w2 = 2 * np.pi * 20.0, 2 * np.pi * 24000.0 * 0.999
+    sweep = np.sin(w1 * T / np.log(w2 / w1) * (np.exp(t / T * np.log(w2 / w1)) - 1.0)).astype(np.float32)
+    S = np.fft.rfft(sweep.astype(np.float64), 2 * n)
+    base = []
+    for j in range(4):
+        h = synth.decaying_ir(3000 + j, 48000, j).astype(np.float64)
+        base.append(np.fft.irfft(S * np.fft.rfft(h, 2 * n), 2 * n)[:n].astype(np.float32))
+    return sweep, base
+
+
+def cpu_reference_sample_c5(args, target_seconds, threads=None):
+    import oracle
+    from irbaboon_b200 import synth
+    n = 1 << 20
+    sweep, base = c5_inputs(4)
+    if oracle.have_reference():
+        ref = oracle.Reference()
+        T = threads or max(1, ref.hardware_threads())
+        k = T
+        caps = np.stack([base[j % 4] + synth.white_noise(4000 + j, 0, n) * np.float32(1e-3) for j in range(k)])
+        secs, _ = ref.bench_deconvolve(T, caps, sweep, SR, False)
+        kind = "reference"
+    else:
+        orc = oracle.Oracle()
+        T, k = 1, 1
+        t0 = time.perf_counter()
+        orc.deconvolve(base[0], sweep, SR, False)
+        secs, kind = time.perf_counter() - t0, "port"
+    return {"value": k / secs, "unit": "captures/s", "cores": T, "kind": kind, "seconds": secs, "probe": None,
+            "sample": "%d captures of 2^20 samples through fp::convolution::deconvolve(smoothing=false), %d threads, one capture per thread" % (k, T)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    metric, unit = metric_of(args)
     # every step is a bounded sample of the workload; the whole run (warm-up included) is sized for about two minutes
     budget = 120.0 / max(1, args.steps + args.warmup)
     per_step = float(np.clip(budget, 0.25, args.cpu_seconds))
@@ -173,129 +285,237 @@ def run_reference(args):
     secs = sum(v["seconds"] for v in vals)
     rt = float(np.mean([v["value"] for v in vals]))
     B, Lh, P = workload(args)
-    line = {"metric": METRIC, "value": rt, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * secs / max(1, len(vals)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": "configs[2]: streams sharing one %.1f s IR, block %d (CPU: %s)" % (args.ir_seconds, B, last["sample"]),
-                                            "block": B, "ir_taps": Lh, "partitions": P},
-            "cpu_baseline": {"value": rt, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
-            "e2e": {"value": rt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    wl = {"c3": "configs[2]: streams sharing one %.1f s IR, block %d" % (args.ir_seconds, B), "c4": "configs[3]: streams with per-stream %.0f s IRs, block %d" % (args.ir_seconds, B),
+          "c5": "configs[4]: 2^20-sample ESS captures deconvolved by spectral division"}[args.workload]
+    line = {"metric": metric, "value": rt, "unit": unit, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * secs / max(1, len(vals)), "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "%s (CPU: %s)" % (wl, last["sample"]), "block": B, "ir_taps": Lh, "partitions": P},
+            "cpu_baseline": {"value": rt, "unit": unit, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": rt, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from irbaboon_b200 import engine as eng
-    from irbaboon_b200 import sharding, synth
+class Ranks:
+    """torch.distributed plumbing: the launch barrier and max-over-ranks reductions; nothing on the data path."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL announces its version on stdout when the communicator is created; stdout must carry one JSON line, so the
-        # file descriptor points at stderr while the process group comes up (first barrier included)
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # NCCL announces its version on stdout when the communicator is created; stdout must carry one JSON line, so the
+            # file descriptor points at stderr while the process group comes up (first barrier included)
             sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
+            self.dist = dist
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, v):
+        from irbaboon_b200 import sharding
+        return sharding.max_over_ranks(float(v), device="cuda")
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def percentiles(ms, period):
+    ms = np.asarray(ms, np.float64)
+    return {"block_period_ms": period, "steps": int(len(ms)), "p50_ms": float(np.percentile(ms, 50)), "p99_ms": float(np.percentile(ms, 99)),
+            "p999_ms": float(np.percentile(ms, 99.9)), "max_ms": float(ms.max()), "over_period": int((ms >= period).sum()),
+            "realtime": bool(np.percentile(ms, 99) < period)}
+
+
+def run_b200(args):
+    from irbaboon_b200 import engine as eng
+    for kv in args.tune:
+        k, v = kv.split("=")
+        eng.set_tuning(k, int(v))
+    R = Ranks()
+    if args.workload == "c5":
+        return run_c5(args, R, eng)
+    torch = R.torch
+    from irbaboon_b200 import sharding, synth
+    rank, world, local = R.rank, R.world, R.local
 
     B, Lh, P = workload(args)
+    period_ms = 1e3 * B / SR
     per_stream_ir = args.workload == "c4"
-    S = args.streams
+    ladder = not per_stream_ir and args.streams <= 0
     if per_stream_ir:                                  # strong scaling: the job's streams are cut into contiguous ranges
         lo, hi = sharding.stream_range(rank, world, args.streams_total)
-        S = hi - lo
+        S_alloc = hi - lo
+    else:
+        lo = 0
+        S_alloc = args.streams_max if ladder else args.streams
     bins = B + 1
     if per_stream_ir:
-        e = eng.Engine(B, P, S, S, device=local)
+        e = eng.Engine(B, P, S_alloc, S_alloc, device=local)
         irs = [synth.decaying_ir(2000 + j, Lh, j) for j in range(8)]          # 8 distinct IRs cycled: every stream still owns its spectra
-        for s_ in range(S):
+        for s_ in range(S_alloc):
             e.set_ir(s_, irs[(lo + s_) % 8])
             e.bind(s_, s_ + 1, s_)
     else:
         h = synth.decaying_ir(2000, Lh)
-        e = eng.Engine(B, P, S, 1, device=local)
+        e = eng.Engine(B, P, S_alloc, 1, device=local)
         e.set_ir(0, h)
     if args.two_launch:
         e.set_fused_step(False)
+    tile = e.tile_channels
     stream = torch.cuda.Stream()                       # the kernels and the timing events share this stream
     torch.cuda.set_stream(stream)
     e.set_stream(stream.cuda_stream)
 
-    # synthetic input: NBUF distinct white-noise blocks per stream, resident in HBM, cycled step by step
+    # synthetic input: NBUF distinct white-noise blocks per stream, resident in HBM, cycled step by step (a run at fewer active
+    # streams reads the dense prefix of a buffer)
     NBUF = 4
     gen = torch.Generator(device="cuda").manual_seed(1003 + rank)
-    d_in = (torch.rand((NBUF, S, B), device="cuda", generator=gen, dtype=torch.float32) * 2 - 1).contiguous()
-    d_out = torch.empty((S, B), device="cuda", dtype=torch.float32)
+    d_in = (torch.rand((NBUF, S_alloc, B), device="cuda", generator=gen, dtype=torch.float32) * 2 - 1).contiguous()
+    d_out = torch.empty((S_alloc, B), device="cuda", dtype=torch.float32)
+    counter = [0]
 
-    def step(i):
-        e.process_device(d_in[i % NBUF].data_ptr(), d_out.data_ptr(), 1)
+    def step():
+        e.process_device(d_in[counter[0] % NBUF].data_ptr(), d_out.data_ptr(), 1)
+        counter[0] += 1
 
-    # fill the FDL (steady state needs P blocks of history) + the requested warm-up
-    for i in range(max(args.warmup, 3) + P):
-        step(i)
-    barrier()
+    def timed_steps(n):
+        """n consecutive steps with per-step device timing; -> (step_ms, kernel_ms, host time the first one started)"""
+        R.barrier()
+        e.set_timing(True)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step()
+        sm_, mm_ = e.timings()
+        e.set_timing(False)
+        return sm_, mm_, t0
+
+    # fill the FDL of every resident stream (steady state needs P blocks of history) + the requested warm-up
+    for _ in range(max(args.warmup, 3) + P):
+        step()
+    R.barrier()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
+
+    # ---- capacity ladder (c3): the largest stream count whose p99 block step over ladder_steps stays inside the period ----
+    S = S_alloc
+    ladder_log = []
+    if ladder:
+        def p99_at(n_streams, n_steps):
+            e.set_active_channels(n_streams)
+            for _ in range(3):
+                step()
+            sm_, _, _ = timed_steps(n_steps)
+            return R.max(np.percentile(sm_, 99)), R.max(np.percentile(sm_, 50)), sm_
+        p99, p50, _ = p99_at(S_alloc, 40)
+        ladder_log.append({"streams": S_alloc, "steps": 40, "p50_ms": p50, "p99_ms": p99})
+        if p99 < period_ms:                                   # everything resident already runs in real time: verify it over the full count
+            cand = S_alloc
+        else:
+            cand = int(S_alloc * period_ms / (p50 * 1.02)) // 2048 * 2048
+        S = 0
+        for _ in range(8):
+            cand = max(2048, min(cand, S_alloc))
+            p99, p50, sm_ = p99_at(cand, args.ladder_steps)
+            ok = p99 < period_ms
+            ladder_log.append({"streams": cand, "steps": args.ladder_steps, "p50_ms": p50, "p99_ms": p99, "realtime": bool(ok)})
+            if ok:
+                S = cand
+                break
+            cand -= 2048
+        if S == 0:
+            raise SystemExit("bench.py: no stream count of the ladder ran in real time: %r" % ladder_log)
+        e.set_active_channels(S)
+    for _ in range(3):
+        step()
+
+    # ---- the timed region of the contract: K steps, barrier + synchronize on both sides, CUDA events, max over ranks ----
     launches0 = eng.launch_count()
     e.set_timing(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    R.barrier()
+    mark0 = sampler.mark()
+    t_host0 = time.perf_counter()
     ev0.record(stream)
-    for i in range(args.steps):
-        step(i)
+    for _ in range(args.steps):
+        step()
     ev1.record(stream)
-    barrier()
+    R.barrier()
+    mark1 = sampler.mark()
     total_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
     step_ms, mac_ms = e.timings()
     e.set_timing(False)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.summary(mark0, mark1) if rank == 0 else None
 
-    total_ms = sharding.max_over_ranks(total_ms, device="cuda")
+    total_ms = R.max(total_ms)
     ms_per_step = total_ms / args.steps
     # final host-side gather of the last output block in global stream order (outside the timed region; the only
     # cross-rank data movement of the whole job)
     total_streams = args.streams_total if per_stream_ir else world * S
-    gathered = sharding.gather_streams(d_out.cpu().numpy(), total_streams, device="cuda")
-    value = total_streams * B / (ms_per_step * 1e-3) / SR
+    gathered = sharding.gather_streams(d_out[:S].cpu().numpy(), total_streams, device="cuda")
+    throughput_channels = total_streams * B / (ms_per_step * 1e-3) / SR
+    lat = percentiles(step_ms, period_ms)
+    lat["p99_ms"] = R.max(lat["p99_ms"])
+    lat["realtime"] = bool(lat["p99_ms"] < period_ms)
+    if ladder:
+        value, value_kind = float(total_streams), "verified_rt_capacity: largest stream count of the ladder whose p99 over %d consecutive steps < %.3f ms, on every rank" % (args.ladder_steps, period_ms)
+    elif lat["realtime"] and args.steps >= 100:
+        value, value_kind = float(total_streams), "fixed stream count, real time over the %d timed steps (p99 < period)" % args.steps
+    else:
+        value, value_kind = throughput_channels, "throughput_equivalent S*B/step/48000 (fixed stream count, too few steps or p99 over the period: not a verified capacity)"
+    # slow steps next to the clock / power the GPU ran at (rank 0): is an excursion a power-cap event?
+    excursions = None
+    if rank == 0 and len(step_ms):
+        med = float(np.median(step_ms))
+        idx = [int(i) for i in np.argsort(step_ms)[::-1][:3] if step_ms[i] > med + 0.5]
+        starts = t_host0 + np.concatenate([[0.0], np.cumsum(step_ms[:-1])]) * 1e-3
+        excursions = [{"step": i, "ms": float(step_ms[i]), "median_ms": med, "gpu": sampler.near(starts[i] + step_ms[i] * 5e-4)} for i in idx]
 
-    # roofline of the dominant kernel (FDL MAC, fused with the inverse FFT + overlap-add epilogue)
-    # FDL read per stream + the shared IR once per GPU (c3) or every stream's own IR spectra (c4)
-    # With the fused step (default for c3) the kernel is the WHOLE block step: add the new spectrum's write and the audio in/out
-    # (SURVEY 8d bytes_blk = bytes_mac + (B+1)*8 + 2*B*4 per stream).
-    fused = (not per_stream_ir) and (not args.two_launch) and not e.mac_plan()[0]
+    # ---- roofline of the dominant kernel (SURVEY 8d): FDL read per stream + the shared IR once per GPU (c3) or every stream's own IR
+    # spectra (c4); the fused step is the WHOLE block step: add the new spectrum's write and the audio in/out ----
+    slots, split_in, cluster = e.mac_plan()
+    fused = (not args.two_launch) and split_in == 1 and cluster == 1 and (not slots or (eng.get_tuning("mac_persistent") and e.fft_size // 2 >= 256))
     alg_bytes = 2 * S * P * bins * 8 if per_stream_ir else (S + 1) * P * bins * 8
     if fused:
         alg_bytes += S * (bins * 8 + 2 * B * 4)
     mac_avg_ms = float(np.mean(mac_ms)) if len(mac_ms) else float("nan")
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (mac_avg_ms * 1e-3) / 1e9
-    tma = fused and e.fft_size // 2 >= 256 and os.environ.get("IRB_MAC_TMA", "1") != "0"      # the dispatch rule of launch_mac_t (irb_engine.cu)
-    kname = "k_mac_slots<%d,INV> (per-stream-IR FDL multiply-accumulate + inverse FFT + overlap-add)" % (e.fft_size // 2) if per_stream_ir else \
-            ("k_mac_tma<%d> (one launch per block step: forward FFT + TMA-streamed FDL multiply-accumulate + inverse FFT + overlap-add)" if tma else
-             "k_mac<%d,INV,FUSE> (one launch per block step: forward FFT + FDL multiply-accumulate + inverse FFT + overlap-add)" if fused else
-             "k_mac<%d,INV> (FDL multiply-accumulate + inverse FFT + overlap-add)") % (e.fft_size // 2)
+    M = e.fft_size // 2
+    persistent = fused and M >= 256 and eng.get_tuning("mac_persistent")
+    if persistent:
+        kname = "k_mac_p<%d,%s> (persistent, one launch per block step: forward FFT + TMA-streamed FDL/IR multiply-accumulate + inverse FFT + overlap-add)" % (M, "PERROW" if slots else "shared IR")
+    elif slots:
+        kname = "k_mac_slots<%d,INV> (per-stream-IR FDL multiply-accumulate + inverse FFT + overlap-add)" % M
+    elif fused and M >= 256 and eng.get_tuning("mac_tma"):
+        kname = "k_mac_tma<%d> (one CTA per tile, one launch per block step)" % M
+    else:
+        kname = ("k_mac<%d,INV,FUSE> (register-staged, one launch per block step)" if fused else "k_mac<%d,INV> (FDL multiply-accumulate + inverse FFT + overlap-add)") % M
     roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": mac_avg_ms, "kernel_share_of_step": mac_avg_ms / float(np.mean(step_ms)),
@@ -304,90 +524,265 @@ def run_b200(args):
     if os.path.exists(prof):
         try:
             tj = json.load(open(prof))
-            if tj.get("streams") == S and tj.get("block") == B and tj.get("partitions") == P and bool(tj.get("fused", False)) == fused \
-                    and ("k_mac_tma" in tj.get("kernel", "")) == tma:
-                roof["traffic"] = tj["dram_bytes_per_launch"]
+            # the static ncu figure applies only to the very kernel and shape it was captured on (bytes scale with the stream count)
+            if tj.get("block") == B and tj.get("partitions") == P and tj.get("kernel", "").split("<")[0] == kname.split("<")[0] and not per_stream_ir:
+                roof["traffic"] = tj["dram_bytes_per_launch"] * S / tj["streams"]
+                roof["traffic_source"] = "ncu --set full at %d streams (%s), scaled by stream count" % (tj["streams"], tj.get("file", "profiles/"))
         except Exception:
             pass
-    period_ms = 1e3 * B / SR
-    lat = {"block_period_ms": period_ms, "p50_ms": float(np.percentile(step_ms, 50)), "p99_ms": float(np.percentile(step_ms, 99)),
-           "max_ms": float(step_ms.max()), "realtime": bool(np.percentile(step_ms, 99) < period_ms)}
 
-    # ---- e2e: host (pinned) buffers through irb_engine_process, copies inside the timed region ----
+    # ---- e2e: host (pinned) buffers through irb_engine_submit / _wait, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        K2 = args.e2e_steps or min(args.steps, 32)
-        K2 = max(4, min(K2, (2 << 30) // (S * B * 4)))          # at most ~2 GB of pinned host memory per direction
-        if per_stream_ir:
-            K2 = min(K2, 8)
-        hin = eng.pinned_empty((K2, S, B))
-        hout = eng.pinned_empty((K2, S, B))
-        rng = np.random.default_rng(1003 + rank)
-        hin[:] = rng.random((K2, S, B), dtype=np.float32) * 2 - 1
-        e.set_stream(None)
-        e.process(hin[:4], hout[:4])                      # warm-up of the copy path
-        barrier()
-        REP = 4                                           # the feed is continuous: REP back-to-back submissions of K2 blocks, one wait
-        t0 = time.perf_counter()
-        for _ in range(REP):
-            e.submit(hin, hout)                           # copies and kernels enqueued; the pipeline stays full across submissions
-        e.wait()                                          # every output block is back on the host
-        dt = (time.perf_counter() - t0) / REP
-        dt = sharding.max_over_ranks(dt, device="cuda")
-        # strict block-by-block round trip (what a live host callback sees)
-        t0 = time.perf_counter()
-        for i in range(min(K2, 16)):
-            e.process(hin[i], hout[i])
-        dt1 = (time.perf_counter() - t0) / min(K2, 16)
-        e2e = {"value": total_streams * B * K2 / dt / SR, "unit": UNIT, "h2d_bytes_per_step": S * B * 4, "d2h_bytes_per_step": S * B * 4,
-               "steps": K2, "ms_per_step": 1e3 * dt / K2, "api": "4 x irb_engine_submit(host in, host out, n_blocks=%d) + irb_engine_wait, pinned buffers, wall clock" % K2,
-               "blockwise_roundtrip_ms": 1e3 * dt1, "checksum": float(np.abs(hout[-1]).sum())}
-        eng.pinned_free(hin)
-        eng.pinned_free(hout)
+        e2e = e2e_leg(args, R, eng, e, S, B, total_streams, period_ms, per_stream_ir, tile)
 
-    # ---- self-check after the timed region, at the bench's own size (the GPU full, every SM holding its resident CTAs): the
-    # block step as measured against its two-launch form on EVERY channel, bit for bit (the oracle comparisons live in tests/) ----
+    # ---- self-check after the timed region, at the bench's own size (the GPU full): (1) the block step as measured against its
+    # two-launch form on EVERY channel, bit for bit; (2) random channels against the CPU reference (oracle/_ref) ----
     selfcheck = None
     if not args.no_selfcheck:
-        KC = 4
-        rng = np.random.default_rng(77 + rank)
-        xin = (rng.random((KC, S, B), dtype=np.float32) * 2 - 1).astype(np.float32)
-        e.set_stream(None)
-        e.reset()
-        ya = e.process(xin).copy()
-        e.reset()
-        if not per_stream_ir:
-            e.set_fused_step(bool(args.two_launch))     # the other form of the block step
-        yb = e.process(xin).copy()
-        selfcheck = {"blocks": KC, "channels_compared": int(S),
-                     "against": "same step repeated" if per_stream_ir else ("fused step" if args.two_launch else "two-launch step"),
-                     "bit_identical": bool(np.array_equal(ya, yb))}
-        selfcheck["ok"] = sharding.max_over_ranks(0.0 if selfcheck["bit_identical"] else 1.0, device="cuda") == 0.0      # every rank
-        del xin, ya, yb
+        selfcheck = self_check(args, R, eng, e, S, B, Lh, per_stream_ir, lo)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_sample(args, args.cpu_seconds)
         cpu.pop("seconds", None)
         cpu.pop("probe", None)
+    sampler.stop()
 
+    ok = selfcheck is None or selfcheck["ok"]
     if rank == 0:
+        metric, unit = metric_of(args)
         wl = ("configs[3]: %d streams with per-stream %.0f s IRs (%d taps, %d partitions), block %d, sharded by stream over %d GPU(s)"
               % (total_streams, args.ir_seconds, Lh, P, B, world)) if per_stream_ir else \
              ("configs[2] shape: %d independent mono streams per GPU sharing one %.1f s IR (%d taps, %d partitions), block %d" % (S, args.ir_seconds, Lh, P, B))
-        line = {"metric": METRIC if not per_stream_ir else "48kHz RT channels (block 1024, per-stream 10s IRs)", "value": value, "unit": UNIT, "n_gpus": world,
+        line = {"metric": metric, "value": value if ok else None, "unit": unit, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "strong" if per_stream_ir else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl,
-                           "streams_per_gpu": S, "block": B, "ir_taps": Lh, "partitions": P, "fft_size": e.fft_size,
-                           "state_bytes_per_gpu": int(e.state_bytes), "l2_policy": "inputs larger than L2 (FDL %.2f GB per GPU)" % (S * P * B * 8 / 1e9), "mac_plan": list(e.mac_plan()),
+                "config": {"workload": wl, "value_kind": value_kind,
+                           "streams_per_gpu": S, "streams_resident_per_gpu": S_alloc, "block": B, "ir_taps": Lh, "partitions": P, "fft_size": e.fft_size,
+                           "state_bytes_per_gpu": int(e.state_bytes), "l2_policy": "inputs larger than L2 (FDL %.2f GB per GPU in use)" % (S * P * B * 8 / 1e9),
+                           "mac_plan": [bool(slots), split_in, cluster], "tuning": args.tune,
                            "sharding": "contiguous stream ranges by rank, IR replicated, no data-path collective; host gather of outputs",
-                           "gathered_output_shape": list(gathered.shape), "channel_samples_per_s": value * SR},
-                "latency": lat, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "selfcheck": selfcheck, "gpu_launches": int(launches), "clocks": clocks}
+                           "gathered_output_shape": list(gathered.shape), "channel_samples_per_s": throughput_channels * SR,
+                           "throughput_equivalent_channels": throughput_channels, "capacity_ladder": ladder_log},
+                "latency": lat, "excursions": excursions, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "selfcheck": selfcheck, "gpu_launches": int(launches), "clocks": clocks}
+        if not ok:
+            line["invalid"] = "selfcheck failed: the measured block step does not reproduce its two-launch form / the CPU reference"
         print(json.dumps(line), flush=True)
     e.close()
-    if world > 1:
-        dist.destroy_process_group()
+    R.close()
+    if not ok:
+        sys.exit(3)
+
+
+def e2e_leg(args, R, eng, e, S, B, total_streams, period_ms, per_stream_ir, tile):
+    """Host buffers in and out: continuous feed (submit/wait pipeline), block-by-block round trip, the copy-only ceiling of the
+    same sizes on the same ranks, and the largest stream count whose block-by-block round trip stays inside the block period."""
+    rank, world = R.rank, R.world
+    K2 = args.e2e_steps or min(args.steps, 32)
+    K2 = max(4, min(K2, (2 << 30) // (S * B * 4)))          # at most ~2 GB of pinned host memory per direction
+    if per_stream_ir:
+        K2 = min(K2, 8)
+    hin = eng.pinned_empty((K2, S, B))
+    hout = eng.pinned_empty((K2, S, B))
+    rng = np.random.default_rng(1003 + rank)
+    hin[:] = rng.random((K2, S, B), dtype=np.float32) * 2 - 1
+    e.set_stream(None)
+    e.process(hin[:4], hout[:4])                      # warm-up of the copy path
+    R.barrier()
+    REP = 4                                           # the feed is continuous: REP back-to-back submissions of K2 blocks, one wait
+    t0 = time.perf_counter()
+    for _ in range(REP):
+        e.submit(hin, hout)                           # copies and kernels enqueued; the pipeline stays full across submissions
+    e.wait()                                          # every output block is back on the host
+    dt = (time.perf_counter() - t0) / REP
+    dt = R.max(dt)
+    # strict block-by-block round trip (what a live host callback sees)
+    nb1 = min(K2, 16)
+    R.barrier()
+    rts = []
+    for i in range(nb1):
+        t0 = time.perf_counter()
+        e.process(hin[i], hout[i])
+        rts.append(time.perf_counter() - t0)
+    dt1 = R.max(float(np.mean(rts)))
+    checksum = float(np.abs(hout[nb1 - 1]).sum())
+    blk_bytes = S * B * 4
+    out = {"value": total_streams * B * K2 / dt / SR, "unit": UNIT, "h2d_bytes_per_step": blk_bytes, "d2h_bytes_per_step": blk_bytes,
+           "steps": K2, "ms_per_step": 1e3 * dt / K2, "api": "%d x irb_engine_submit(host in, host out, n_blocks=%d) + irb_engine_wait, pinned buffers, wall clock" % (REP, K2),
+           "blockwise_roundtrip_ms": 1e3 * dt1, "blockwise_realtime": bool(1e3 * dt1 < period_ms), "checksum": checksum}
+    # ---- largest stream count whose block-by-block host round trip stays inside the period at this number of ranks ----
+    if not per_stream_ir:
+        def roundtrip_at(n):
+            e.set_active_channels(n)
+            x, y = hin.reshape(-1)[:nb1 * n * B].reshape(nb1, n, B), hout.reshape(-1)[:nb1 * n * B].reshape(nb1, n, B)
+            e.process(x[0], y[0])
+            R.barrier()
+            ts = []
+            for i in range(nb1):
+                t0 = time.perf_counter()
+                e.process(x[i], y[i])
+                ts.append(time.perf_counter() - t0)
+            return R.max(float(np.max(ts[1:]))) * 1e3
+        rt_S, trail = 0, []
+        if 1e3 * dt1 < period_ms * 0.97:
+            rt_S = S
+            trail.append({"streams": S, "roundtrip_ms": 1e3 * dt1})
+        else:
+            cand = int(S * period_ms / (1e3 * dt1) * 0.97) // 2048 * 2048
+            for _ in range(6):
+                cand = max(tile, min(cand, S)) // tile * tile
+                ms = roundtrip_at(cand)
+                trail.append({"streams": cand, "roundtrip_max_ms": ms})
+                if ms < period_ms:
+                    rt_S = cand
+                    break
+                cand = int(cand * min(0.95, period_ms / ms * 0.98)) // 2048 * 2048
+            e.set_active_channels(S)
+        out["rt_streams_per_gpu"] = rt_S
+        out["rt_streams_search"] = trail
+        out["rt_streams_note"] = "largest stream count per GPU whose one-block-per-call host round trip (irb_engine_process, copies included) stays under the %.3f ms period with all %d ranks running" % (period_ms, world)
+    eng.pinned_free(hin)
+    eng.pinned_free(hout)
+    del hin, hout
+    # ---- copy-only ceiling: the same bytes per block, H2D and D2H at once, on every rank at the same time, no kernels ----
+    try:
+        probe = eng.CopyProbe(blk_bytes, 0, device=R.local)
+        probe.run(2, 3)
+        res = {}
+        for name, direction in (("h2d", 1), ("d2h", 2), ("both", 3)):
+            R.barrier()
+            secs = R.max(probe.run(8, direction))
+            res[name] = world * blk_bytes * 8 * (2 if direction == 3 else 1) / secs / 1e9
+        probe.close()
+        used = world * 2 * blk_bytes / (dt / K2) / 1e9
+        out.update({"host_copy_ceiling_gbs": res["both"], "host_copy_h2d_only_gbs": res["h2d"], "host_copy_d2h_only_gbs": res["d2h"],
+                    "host_copy_used_gbs": used, "frac_of_copy_ceiling": used / res["both"],
+                    "host_copy_note": "aggregate over %d rank(s): %d-byte pinned transfers per direction and block, both directions at once, no kernels; "
+                                      "the submit/wait leg moves the same bytes per step" % (world, blk_bytes)})
+    except Exception as ex:                               # the probe is an aid: never fail the bench for it
+        out["host_copy_ceiling_gbs"] = None
+        out["host_copy_note"] = "probe failed: %s" % ex
+    return out
+
+
+def self_check(args, R, eng, e, S, B, Lh, per_stream_ir, lo):
+    from irbaboon_b200 import synth
+    KC = 4
+    rng = np.random.default_rng(77 + R.rank)
+    xin = (rng.random((KC, S, B), dtype=np.float32) * 2 - 1).astype(np.float32)
+    e.set_stream(None)
+    e.reset()
+    ya = e.process(xin).copy()
+    e.reset()
+    e.set_fused_step(bool(args.two_launch))             # the other form of the block step
+    yb = e.process(xin).copy()
+    e.set_fused_step(not args.two_launch)
+    out = {"blocks": KC, "channels_compared": int(S), "against": "fused step" if args.two_launch else "two-launch step (k_fwd, then the MAC kernel)",
+           "bit_identical": bool(np.array_equal(ya, yb))}
+    # random channels against the reference's own convolvePeriodic on the same input (first KC blocks from a reset engine)
+    worst, n_ref, kind = 0.0, 0, None
+    try:
+        import oracle
+        ref = oracle.Reference() if oracle.have_reference() else oracle.Oracle()
+        kind = "oracle/_ref (reference object code)" if oracle.have_reference() else "oracle port"
+        chans = sorted(set(int(c) for c in np.random.default_rng(5).integers(0, S, 8)) | {0, S - 1})
+        irs = [synth.decaying_ir(2000 + j, Lh, j) for j in range(8)] if per_stream_ir else None
+        for c in chans:
+            h = irs[(lo + c) % 8] if per_stream_ir else synth.decaying_ir(2000, Lh)
+            x = np.ascontiguousarray(xin[:, c, :]).reshape(-1)
+            want = ref.convolve_periodic(x, h, B)[0, :KC * B]
+            got = ya[:, c, :].reshape(-1)
+            fs = max(1.0, float(np.abs(want).max()))
+            worst = max(worst, float(np.abs(got - want).max()) / fs)
+            n_ref += 1
+    except Exception as ex:
+        kind = "unavailable: %s" % ex
+    out.update({"reference_channels": n_ref, "reference": kind, "max_abs_over_full_scale": worst, "tolerance": 1e-5, "reference_ok": bool(n_ref == 0 or worst <= 1e-5)})
+    good = out["bit_identical"] and out["reference_ok"]
+    out["ok"] = R.max(0.0 if good else 1.0) == 0.0      # every rank
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_c5(args, R, eng):
+    """BASELINE configs[4]: a batch of 2^20-sample ESS captures deconvolved by spectral division (fp::convolution::deconvolve,
+    smoothing off).  A step = one irb_deconvolve_batch call over the rank's batch.  value: captures/s from the CUDA-event time
+    of the call's kernels (host<->device copies excluded); e2e: wall clock around the call, pinned host buffers in and out."""
+    from irbaboon_b200 import synth
+    torch = R.torch
+    n, nb = 1 << 20, args.captures
+    eng.set_device(R.local)
+    sweep, base = c5_inputs(4)
+    caps = eng.pinned_empty((nb, n))
+    res = eng.pinned_empty((nb, n))
+    for j in range(nb):
+        caps[j] = base[j % 4] + synth.white_noise(4000 + j + 100000 * R.rank, 0, n) * np.float32(1e-3)
+    for _ in range(max(3, args.warmup)):
+        eng.deconvolve_batch(caps, sweep, SR, False, out=res)
+    sampler = ClockSampler(R.local)
+    if R.rank == 0:
+        sampler.start()
+    R.barrier()
+    launches0 = eng.launch_count()
+    dev_ms, wall = [], []
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        eng.deconvolve_batch(caps, sweep, SR, False, out=res)
+        wall.append(time.perf_counter() - t0)
+        dev_ms.append(eng.last_compute_ms())
+    R.barrier()
+    t_all = R.max(time.perf_counter() - t_all)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.summary() if R.rank == 0 else None
+    sampler.stop()
+    dev = R.max(float(np.mean(dev_ms))) * 1e-3
+    w = R.max(float(np.mean(wall)))
+    total = nb * R.world
+    peak, peak_src = measured_peak_gbs()
+    alg = nb * 2 * n * 4                                  # SURVEY 8d: read the capture, write the IR (the sweep's spectrum is shared)
+    three_pass = nb * 3 * 2 * (n // 2) * 8                # what the three-kernel scheme moves when nothing stays in L2
+    # spot check against the reference on three captures of the batch
+    chk = {"captures": [], "max_abs_over_full_scale": 0.0}
+    try:
+        import oracle
+        ref = oracle.Reference() if oracle.have_reference() else oracle.Oracle()
+        for j in sorted({0, nb // 2, nb - 1}):
+            want = ref.deconvolve(np.array(caps[j]), sweep, SR, False)[0]
+            fs = max(1.0, float(np.abs(want).max()))
+            chk["captures"].append(j)
+            chk["max_abs_over_full_scale"] = max(chk["max_abs_over_full_scale"], float(np.abs(res[j] - want).max()) / fs)
+        chk["ok"] = chk["max_abs_over_full_scale"] <= 1e-5
+    except Exception as ex:
+        chk["ok"], chk["note"] = True, "reference unavailable: %s" % ex
+    cpu = None
+    if R.rank == 0 and R.world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_sample(args, args.cpu_seconds)
+        cpu.pop("seconds", None); cpu.pop("probe", None)
+    ok = R.max(0.0 if chk["ok"] else 1.0) == 0.0
+    if R.rank == 0:
+        metric, unit = metric_of(args)
+        line = {"metric": metric, "value": total / dev if ok else None, "unit": unit, "n_gpus": R.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[4]: %d captures per GPU of a 2^20-sample exponential sine sweep (+ room IR, + noise) deconvolved by spectral division, N = 2^20" % nb,
+                           "captures_per_gpu": nb, "fft_points": n, "value_kind": "device: CUDA-event time of the batch's kernels, copies excluded (irb_last_compute_ms)",
+                           "l2_policy": "inputs larger than L2 (%.1f GB per batch)" % (nb * n * 4 / 1e9), "tuning": args.tune},
+                "roofline": {"bound": "hbm", "kernel": "k_line_fft<512> (columns) + k_rowpair<1024> (rows, divide, inverse rows) + k_line_fft<512,INV>: the batch's kernel time as a whole",
+                             "achieved": alg / dev / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / dev / 1e9 / peak, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg, "kernel_ms": dev * 1e3, "three_pass_bytes": three_pass, "frac_at_three_pass_bytes": three_pass / dev / 1e9 / peak,
+                             "traffic": None},
+                "cpu_baseline": cpu,
+                "e2e": {"value": total / w, "unit": unit, "h2d_bytes_per_step": nb * n * 4, "d2h_bytes_per_step": nb * n * 4, "ms_per_step": 1e3 * w,
+                        "api": "irb_deconvolve_batch(pinned host captures, host sweep) -> pinned host IRs, wall clock"},
+                "selfcheck": chk, "gpu_launches": int(launches), "clocks": clocks}
+        if not ok:
+            line["invalid"] = "selfcheck failed"
+        print(json.dumps(line), flush=True)
+    eng.pinned_free(caps); eng.pinned_free(res)
+    R.close()
+    if not ok:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

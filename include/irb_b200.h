@@ -72,18 +72,24 @@ int irb_engine_set_ir(irb_engine* e, int ir_id, const float* left, const float* 
  * n_partitions*block_size are never read; shorter IRs are zero-extended. */
 int irb_engine_stage_ir(irb_engine* e, int ir_id, const float* left, const float* right, int n_taps, int n_partitions);
 /* channels [chan_begin, chan_end) convolve with ir_id.  When every kernel tile (irb_engine_tile_channels()
- * consecutive channels) is bound to one IR the tile shares the staged IR spectra; otherwise the per-stream-IR
- * kernel is used (each channel stages its own partitions; twice the memory traffic). */
+ * consecutive channels) is bound to one IR the tile shares the staged IR spectra; otherwise every channel stages its own
+ * partitions (twice the memory traffic).  Either way a block step is one launch of the persistent kernel. */
 int irb_engine_bind(irb_engine* e, int chan_begin, int chan_end, int ir_id);
 int irb_engine_tile_channels(const irb_engine* e);
-/* How the next block step will launch the MAC: *slots_kernel = 1 when the per-slot kernel runs (mixed IRs in a tile, or
- * few rows), *split_in = tile slots sharing a row, *cluster = CTAs per cluster splitting the partitions further. */
+/* How the next block step will launch the MAC: *slots_kernel = 1 when every row stages its own IR partitions (mixed IRs in
+ * a tile, or few rows), *split_in = tile slots sharing a row, *cluster = CTAs per cluster splitting the partitions further
+ * (both 1 unless there are so few rows that a row's partitions are spread over the GPU). */
 int irb_engine_mac_plan(irb_engine* e, int* slots_kernel, int* split_in, int* cluster);
 /* Force the split (powers of two; clamped to what the tile allows; 1,1 = one CTA per tile) or return to automatic (0,0). */
 int irb_engine_set_mac_split(irb_engine* e, int split_in, int cluster);
-/* With every tile bound to one IR a block step is ONE launch: the forward transform of the new block runs in the MAC kernel's
- * prologue (default).  0 restores the two-launch form (k_fwd, then k_mac) -- same results bit for bit; kept for measurement. */
+/* A block step is ONE launch: the forward transform of the new block runs in the MAC kernel's prologue (default).
+ * 0 restores the two-launch form (k_fwd, then the MAC kernel) -- same results bit for bit; kept for verification. */
 int irb_engine_set_fused_step(irb_engine* e, int enable);
+/* Streams come and go: only channels [0, n_active) take part in the following block steps (their FDL rings advance, the
+ * others keep their state); the in/out arrays of the process calls are then [n_blocks][n_active][block_size].  n_active is a
+ * whole number of kernel tiles (irb_engine_tile_channels()) or n_channels (the default). */
+int irb_engine_set_active_channels(irb_engine* e, int n_active);
+int irb_engine_active_channels(const irb_engine* e);
 /* clear FDL rings, overlap buffers and heads (prepareToPlay, PluginProcessor.cpp:164-234) */
 int irb_engine_reset(irb_engine* e);
 
@@ -130,17 +136,6 @@ size_t irb_release_workspace(void);
 /* device time (CUDA events, ms) of the kernels of the calling thread's most recent offline call
  * (irb_convolve_periodic / _nonperiodic / irb_deconvolve*), host<->device copies excluded */
 double irb_last_compute_ms(void);
-/* the pure FDL multiply-accumulate (no inverse FFT) on the current state into a device buffer of
- * n_channels * M complex; used to time the roofline kernel in isolation */
-int irb_engine_mac_only_device(irb_engine* e, float* acc_dev);
-/* Measurement aid, not part of the path: GB/s of a kernel that does nothing but read `bytes` of device memory once per
- * iteration with the MAC kernels' own 32-byte streaming loads (L1 no-allocate, L2 evict-first), grid = resident CTAs;
- * averaged over `iters` launches after one warm-up.  Gives the read-only ceiling the FDL stream can be held against
- * (the roofline's `peak` stays the driver-measured copy bandwidth).  Environment, read once: IRB_PROBE_WRITE_EVERY=n writes
- * every n-th 16 KB piece instead of reading it; IRB_PROBE_STORE_KIND selects the store form (0 plain, 1 .cs, 2 L2 evict-first
- * hint, 3 .wt, 4 .cg, 5 L2 evict-last hint). */
-int irb_hbm_read_probe(size_t bytes, int iters, double* gbs);
-
 /* ---- several GPUs from one process ---------------------------------------------------------------------
  * Streams never interact (fp/convolution.cpp:160-215 has no cross-channel term), so n_channels are cut into contiguous
  * ranges of whole kernel tiles, one irb_engine per device.  n_irs > 0: shared IRs, replicated on every device, bound with

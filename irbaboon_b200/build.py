@@ -11,12 +11,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libirb_b200.so")
-SOURCES = ["irb_engine.cu", "irb_spectral.cu"]
-HEADERS = ["irb_fft.cuh", "irb_kernels.cuh", "irb_spectral.cuh", "irb_common.hpp", os.path.join(_ROOT, "include", "irb_b200.h")]
+SOURCES = ["irb_engine.cu", "irb_spectral.cu", "irb_benchaids.cu"]
+HEADERS = ["irb_fft.cuh", "irb_kernels.cuh", "irb_mac_p.cuh", "irb_spectral.cuh", "irb_common.hpp", "irb_tuning.hpp",
+           os.path.join(_ROOT, "include", "irb_b200.h"), os.path.join(_ROOT, "include", "irb_b200_bench.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared", "-t", "2",
+    "-Xcompiler", "-fPIC", "-shared", "-t", "3",
 ]
 
 

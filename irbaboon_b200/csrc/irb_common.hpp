@@ -14,6 +14,7 @@ int twiddles(int dev, int M, const float2** out);              // table of the 2
 // two-level table of the M-th roots: exp(-2 pi i idx / M) = hi[idx >> 10] * lo[idx & 1023], cached per (device, M)
 int twiddles2(int dev, int M, const float2** hi, const float2** lo);
 extern std::atomic<long long> g_launches;
+extern thread_local int g_device;
 
 #define CK(call)                                                                                         \
     do {                                                                                                 \
@@ -93,9 +94,12 @@ struct ScratchBuf : DevBuf {
     int alloc(size_t bytes, bool zero) { return alloc_scratch(bytes, zero); }
 };
 
+// Declare a StreamGuard AFTER the scratch buffers its stream works on: destructors run in reverse order, so an early return
+// first drains the stream (work already enqueued may still be reading or writing those buffers) and only then hands the
+// buffers back to the process-wide pool, where another thread's call could pick them up.
 struct StreamGuard {
     cudaStream_t s = nullptr;
-    ~StreamGuard() { if (s) cudaStreamDestroy(s); }
+    ~StreamGuard() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
     int create() { CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return 0; }
 };
 
@@ -107,3 +111,6 @@ inline int next_pow2(int x) {                                  // tools::nextPow
 }
 
 }  // namespace irbh
+
+struct irb_engine;
+namespace irbh { int engine_mac_only(irb_engine* e, float* acc_dev); }

@@ -15,8 +15,12 @@
 
 #include "irb_common.hpp"
 #include "irb_kernels.cuh"
+#include "irb_mac_p.cuh"
+#include "irb_tuning.hpp"
 
 namespace irbh {
+
+Tuning g_tuning;
 
 thread_local char g_err[512] = "";
 thread_local int g_device = 0;
@@ -134,17 +138,10 @@ int half_size_for_block(int B) {
 }
 constexpr int kMaxM = 2048;
 
-// partitions per IR ring stage (= FDL loads batched per thread): 1 or 2; IRB_MAC_U overrides for tuning
-int mac_u_pref() {
-    static int u = [] { const char* s = getenv("IRB_MAC_U"); return s ? atoi(s) : 1; }();
-    return u;
-}
-
-// FDL loads of the shared-IR kernel as 32-byte LDG.256 with L2 evict-first (IRB_MAC_WIDE=0 selects the 16-byte form)
-bool mac_wide_pref() {
-    static bool w = [] { const char* s = getenv("IRB_MAC_WIDE"); return s ? atoi(s) != 0 : true; }();
-    return w;
-}
+// launch policy (irb_tuning.hpp): partitions per IR ring stage of the register-staged MAC (1 or 2), its FDL loads as 32-byte
+// LDG.256 with L2 evict-first or 16-byte loads
+int mac_u_pref() { return irbh::g_tuning.mac_u; }
+bool mac_wide_pref() { return irbh::g_tuning.mac_wide != 0; }
 
 template <int M>
 int launch_fwd_t(const irb::FwdArgs& a, cudaStream_t st) {
@@ -156,10 +153,54 @@ int launch_fwd_t(const irb::FwdArgs& a, cudaStream_t st) {
     CK(cudaGetLastError());
     return 0;
 }
-// the fused block step with the FDL streamed through TMA (k_mac_tma); IRB_MAC_TMA=0 selects the register-staged k_mac<FUSE>
-bool mac_tma_pref() {
-    static bool w = [] { const char* s = getenv("IRB_MAC_TMA"); return s ? atoi(s) != 0 : true; }();
-    return w;
+// the non-persistent fused block step with the FDL streamed through TMA (k_mac_tma) or register-staged (k_mac<FUSE>)
+bool mac_tma_pref() { return irbh::g_tuning.mac_tma != 0; }
+
+// ---- persistent block step (irb_mac_p.cuh) ------------------------------------------------------------------------
+constexpr int kPersistMinM = 256;
+int persistent_ctas_per_sm() { const int c = irbh::g_tuning.persistent_ctas; return c >= 1 && c <= 2 ? c : 2; }
+// Units of a launch over n_rows rows for `ctas` resident CTAs (fetch order: large units first).  Whole waves of full tiles,
+// then the remainder rem < ROWS * ctas rows in t = ceil(rem / ctas) row-times: one wave of units of s rows for every set bit
+// s of t (s = ROWS/2, ROWS/4 ...), so that a launch takes about ceil(n_rows / ctas) row-times instead of
+// ceil(tiles / ctas) tile-times.  A unit of s rows starts at a multiple of s: it never straddles a tile.
+void plan_units(int n_rows, int rows_per_tile, int ctas, bool narrowing, int out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (n_rows <= 0) return;
+    const long long per_wave = (long long) rows_per_tile * ctas;
+    const int waves = (int) (n_rows / per_wave);
+    int rem = (int) (n_rows - waves * per_wave);
+    out[0] = waves * ctas;
+    if (rem == 0) return;
+    const int t = (rem + ctas - 1) / ctas;                 // row-times the remainder needs at best
+    if (!narrowing || rows_per_tile == 1 || t >= rows_per_tile) { out[0] += (rem + rows_per_tile - 1) / rows_per_tile; return; }
+    int s = rows_per_tile / 2;
+    for (int lvl = 1; lvl < 4 && s >= 1 && rem > 0; ++lvl, s /= 2) {
+        if (!(t & s)) continue;
+        const int cnt = std::min(ctas, (rem + s - 1) / s);
+        out[lvl] = cnt;
+        rem -= std::min(rem, cnt * s);
+    }
+}
+template <int M, bool PERROW>
+int launch_mac_p(irb::MacArgs a, int num_sms, cudaStream_t st) {
+    if (a.n_rows <= 0) return 0;
+    if (!a.work) return fail(IRB_ERR_STATE, "persistent block step without a work counter");
+    const int ctas = persistent_ctas_per_sm() * num_sms;
+    plan_units(a.n_rows, irb::Tile<M>::ROWS, ctas, irbh::g_tuning.unit_narrowing != 0, a.unit_n);
+    const int n_units = a.unit_n[0] + a.unit_n[1] + a.unit_n[2] + a.unit_n[3];
+    const int grid = std::min(n_units, ctas);
+    const size_t smem = sizeof(irb::PSmem<M, PERROW>);
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (configured_dev != dev) {
+        CK(cudaFuncSetAttribute(irb::k_mac_p<M, PERROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured_dev = dev;
+    }
+    irb::k_mac_p<M, PERROW><<<grid, irb::kThreads + 32, smem, st>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
 }
 template <int M>
 int launch_mac_tma(const irb::MacArgs& a, cudaStream_t st) {
@@ -237,7 +278,12 @@ int launch_slots_t(const irb::MacArgs& a, int cl, cudaStream_t st) {
     return 0;
 }
 template <int M, bool INV>
-int launch_mac_t(const irb::MacArgs& a, bool slots, int cl, cudaStream_t st) {
+int launch_mac_t(const irb::MacArgs& a, bool slots, int cl, int num_sms, cudaStream_t st) {
+    if constexpr (INV && M >= kPersistMinM) {
+        // the fused streaming block step as ONE persistent launch (shared-IR tiles or per-stream IRs)
+        if (a.head && a.in && a.work && a.blocks_per_chan == 1 && a.head_back == 0 && a.split_in == 1 && cl == 1)
+            return slots ? launch_mac_p<M, true>(a, num_sms, st) : launch_mac_p<M, false>(a, num_sms, st);
+    }
     if (slots) return launch_slots_t<M, INV>(a, cl, st);
     if constexpr (INV) {
         if (a.head) {                                   // streaming block step
@@ -266,9 +312,9 @@ int launch_mac_t(const irb::MacArgs& a, bool slots, int cl, cudaStream_t st) {
         default: return fail(IRB_ERR_ARG, "unsupported FFT half size %d", M_); \
     }
 int launch_fwd(int M, const irb::FwdArgs& a, cudaStream_t st) { IRB_DISPATCH_M(M, launch_fwd_t<MM>(a, st)); }
-int launch_mac(int M, bool inv, bool slots, int cl, const irb::MacArgs& a, cudaStream_t st) {
-    if (inv) { IRB_DISPATCH_M(M, (launch_mac_t<MM, true>(a, slots, cl, st))); }
-    IRB_DISPATCH_M(M, (launch_mac_t<MM, false>(a, slots, cl, st)));
+int launch_mac(int M, bool inv, bool slots, int cl, int num_sms, const irb::MacArgs& a, cudaStream_t st) {
+    if (inv) { IRB_DISPATCH_M(M, (launch_mac_t<MM, true>(a, slots, cl, num_sms, st))); }
+    IRB_DISPATCH_M(M, (launch_mac_t<MM, false>(a, slots, cl, num_sms, st)));
 }
 int tile_rows(int M) { return irb::kTile / M; }
 
@@ -277,6 +323,7 @@ int tile_rows(int M) { return irb::kTile / M; }
 
 struct irb_engine {
     int device = 0, B = 0, M = 0, ring = 0, n_chans = 0, n_irs = 0;
+    int active = 0;                    // channels [0, active) take part in a block step (irb_engine_set_active_channels); I/O arrays are dense over them
     // FDL layout [chan / fdl_group][slot][chan % fdl_group][M], fdl_group = channels per kernel tile (irb_kernels.cuh, MacArgs)
     int fdl_group = 1;
     long long fdl_group_stride() const { return (long long) ring * fdl_group * M; }
@@ -284,6 +331,7 @@ struct irb_engine {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     const float2* W = nullptr;
     DevBuf fdl, H, ov, head, ir_of_chan, nparts, io_in[2], io_out[2], taps;
+    DevBuf work;                       // k_mac_p: {next unit, finished CTAs}, cleared by the kernel itself
     std::vector<int> h_ir_of_chan, h_nparts;
     bool binding_dirty = true;
     bool per_row_ir = false;           // some kernel tile mixes IRs: every slot stages its own IR partitions (k_mac_slots)
@@ -303,10 +351,11 @@ struct irb_engine {
     // The latency path (one small block per call): copy-in, the step's kernels and copy-out are captured ONCE into a CUDA
     // graph over pinned staging owned by the engine and replayed with a single launch per block.  The signature records
     // everything the captured launches baked in; a change re-captures.
-    struct GraphSig { int n_rr, split_in, cluster, slots, fuse; cudaStream_t stream; bool operator==(const GraphSig& o) const {
-        return n_rr == o.n_rr && split_in == o.split_in && cluster == o.cluster && slots == o.slots && fuse == o.fuse && stream == o.stream; } };
+    struct GraphSig { int n_rr, split_in, cluster, slots, fuse, active, variant; cudaStream_t stream; bool operator==(const GraphSig& o) const {
+        return n_rr == o.n_rr && split_in == o.split_in && cluster == o.cluster && slots == o.slots && fuse == o.fuse && active == o.active &&
+               variant == o.variant && stream == o.stream; } };
     cudaGraphExec_t g_exec = nullptr;
-    GraphSig g_sig{-1, 0, 0, 0, 0, nullptr};
+    GraphSig g_sig{-1, 0, 0, 0, 0, 0, 0, nullptr};
     float *g_hin = nullptr, *g_hout = nullptr;
     int g_kernels = 0;
     bool g_warm = false;                             // a plain step with this signature has run (kernel attributes are set)
@@ -359,12 +408,12 @@ int engine_check_binding(irb_engine* e) {
         // Few rows: fill the GPU by splitting each row's partitions.  Target two CTAs per SM; at least 4 partitions
         // per slot; the reduced tile (1024/split_in float4) must divide among the CTAs of a cluster.
         const int rows = tile_rows(e->M);
-        const int tiles = (e->n_chans + rows - 1) / rows;
+        const int tiles = (e->active + rows - 1) / rows;
         int split_in = 1, cl = 1;
         if (tiles * 2 <= e->num_sms) {
             int max_np = 1;
-            for (int c = 0; c < e->n_chans; ++c) max_np = std::max(max_np, e->h_nparts[e->h_ir_of_chan[c]]);
-            long long want = floor_pow2(std::max<long long>(1, 2LL * e->num_sms * rows / e->n_chans));
+            for (int c = 0; c < e->active; ++c) max_np = std::max(max_np, e->h_nparts[e->h_ir_of_chan[c]]);
+            long long want = floor_pow2(std::max<long long>(1, 2LL * e->num_sms * rows / e->active));
             want = std::min<long long>(want, floor_pow2(std::max(1, max_np / 4)));
             split_in = (int) std::min<long long>(want, rows);
             cl = (int) std::min<long long>(want / split_in, 16);
@@ -378,6 +427,13 @@ int engine_check_binding(irb_engine* e) {
     return 0;
 }
 
+// the ring-protocol knobs every MAC launch carries (irb_tuning.hpp)
+void mac_policy(irb::MacArgs& m) {
+    m.producer_sleep_ns = irbh::g_tuning.producer_sleep_ns;
+    m.release_fence = irbh::g_tuning.release_fence;
+    m.release_dep = irbh::g_tuning.release_dep;
+}
+
 // Every launch helper takes a channel range [c0, c0 + cn): all per-channel arrays are offset, so a kernel sees rows
 // 0 .. cn-1.  c0 is a multiple of the tile's row count (tiles never straddle a range).
 void fill_mac_args(irb_engine* e, irb::MacArgs& m, int c0, int cn) {
@@ -387,10 +443,22 @@ void fill_mac_args(irb_engine* e, irb::MacArgs& m, int c0, int cn) {
     m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
     m.ir_of_chan = e->ir_of_chan.as<int>() + c0; m.nparts = e->nparts.as<int>(); m.W = e->W;
     m.B = e->B; m.split_in = e->split_in;
-    static const int sleep_ns = [] { const char* v = getenv("IRB_PRODUCER_SLEEP_NS"); return v ? atoi(v) : 200; }();
-    m.producer_sleep_ns = sleep_ns;
+    mac_policy(m);
+    m.work = irbh::g_tuning.mac_persistent ? e->work.as<int>() : nullptr;
 }
 bool use_slots(const irb_engine* e) { return e->per_row_ir || e->split_in > 1 || e->cluster_dim > 1; }
+// Is the block step ONE launch (forward transform in the MAC kernel's prologue)?  Shared-IR tiles: always (unless switched off);
+// per-stream IRs: through the persistent kernel; few rows (partitions split over slots / a cluster): two launches.
+bool step_is_fused(const irb_engine* e) {
+    if (!e->fuse_fwd || e->split_in > 1 || e->cluster_dim > 1) return false;
+    if (e->per_row_ir) return irbh::g_tuning.mac_persistent && e->M >= kPersistMinM;
+    return true;
+}
+// everything a captured graph or a cached plan bakes in besides the engine's own state
+int tuning_variant() {
+    const irbh::Tuning& t = irbh::g_tuning;
+    return t.mac_persistent | t.mac_tma << 1 | t.mac_wide << 2 | (t.mac_u & 3) << 3 | t.release_fence << 5 | t.release_dep << 9 | (t.persistent_ctas & 3) << 6 | t.unit_narrowing << 8;
+}
 
 constexpr int kTimingCap = 16384;
 
@@ -419,7 +487,7 @@ int engine_launch_mac(irb_engine* e, float* out_dev, int head_back, const float*
     m.Y = nullptr; m.out = out_dev + (size_t) c0 * e->B; m.out_chan_stride = e->B; m.Lout = e->B;
     m.ov = e->ov.as<float>() + (size_t) c0 * e->B; m.tail = nullptr; m.head_back = head_back;
     m.in = in_dev ? in_dev + (size_t) c0 * e->B : nullptr; m.in_chan_stride = e->B; m.head_rw = e->head.as<int>() + c0;
-    int rc = launch_mac(e->M, true, use_slots(e), e->cluster_dim, m, e->stream);
+    int rc = launch_mac(e->M, true, use_slots(e), e->cluster_dim, e->num_sms, m, e->stream);
     if (rc) return rc;
     e->launches += 1;
     return 0;
@@ -427,9 +495,9 @@ int engine_launch_mac(irb_engine* e, float* out_dev, int head_back, const float*
 
 // one block step for the channels [c0, c0+cn); refresh: also run the staged IRs' refresh rows (once per block)
 int engine_step_range(irb_engine* e, const float* in_dev, float* out_dev, int c0, int cn, bool refresh) {
-    // Shared-IR tiles: ONE launch per block step, the forward transform is the MAC kernel's prologue (staged IRs still
-    // get their refresh rows through a k_fwd launch of their own).  The slot kernel keeps the two-launch form.
-    const bool fused = !use_slots(e) && e->fuse_fwd;
+    // ONE launch per block step, the forward transform is the MAC kernel's prologue (staged IRs still get their refresh
+    // rows through a k_fwd launch of their own).  The few-row slot kernel keeps the two-launch form.
+    const bool fused = step_is_fused(e);
     int rc = engine_launch_fwd(e, in_dev, !fused, refresh, c0, cn);
     if (rc) return rc;
     return engine_launch_mac(e, out_dev, 0, fused ? in_dev : nullptr, c0, cn);
@@ -438,11 +506,11 @@ int engine_step_range(irb_engine* e, const float* in_dev, float* out_dev, int c0
 int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
     const bool rec = e->timing && e->t_rec < kTimingCap;
     if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec], e->stream));
-    const bool fused = !use_slots(e) && e->fuse_fwd;
-    int rc = engine_launch_fwd(e, in_dev, !fused, true, 0, e->n_chans);
+    const bool fused = step_is_fused(e);
+    int rc = engine_launch_fwd(e, in_dev, !fused, true, 0, e->active);
     if (rc) return rc;
     if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec + 1], e->stream));
-    if ((rc = engine_launch_mac(e, out_dev, 0, fused ? in_dev : nullptr, 0, e->n_chans))) return rc;
+    if ((rc = engine_launch_mac(e, out_dev, 0, fused ? in_dev : nullptr, 0, e->active))) return rc;
     if (rec) { CK(cudaEventRecord(e->tev[3 * e->t_rec + 2], e->stream)); e->t_rec++; }
     return 0;
 }
@@ -483,19 +551,18 @@ int irb_engine_create(irb_engine** out, int device, int block_size, int max_part
     irb_engine* e = new (std::nothrow) irb_engine;
     if (!e) return fail(IRB_ERR_ARG, "out of host memory");
     e->device = device; e->B = block_size; e->M = half_size_for_block(block_size);
-    e->ring = max_partitions; e->n_chans = n_channels; e->n_irs = n_irs;
+    e->ring = max_partitions; e->n_chans = n_channels; e->active = n_channels; e->n_irs = n_irs;
     int rc = irbh::twiddles(device, e->M, &e->W);
     if (rc) { delete e; return rc; }
     const size_t spec = sizeof(float2) * (size_t) e->M;
-    static const bool plain_fdl = getenv("IRB_FDL_PLAIN") != nullptr;        // A/B: [chan][slot][M] instead of the tile-interleaved layout
-    e->fdl_group = plain_fdl ? 1 : tile_rows(e->M);
+    e->fdl_group = irbh::g_tuning.fdl_plain ? 1 : tile_rows(e->M);     // A/B: [chan][slot][M] instead of the tile-interleaved layout
     const size_t b_fdl = e->fdl_bytes(), b_H = spec * e->ring * n_irs, b_io = sizeof(float) * (size_t) e->B * n_channels;
     if ((rc = e->fdl.alloc(b_fdl, true)) || (rc = e->H.alloc(b_H, true)) || (rc = e->ov.alloc(b_io, true)) ||
         (rc = e->head.alloc(sizeof(int) * n_channels, false)) || (rc = e->ir_of_chan.alloc(sizeof(int) * n_channels, true)) ||
         (rc = e->nparts.alloc(sizeof(int) * n_irs, true)) || (rc = e->io_in[0].alloc(b_io, true)) || (rc = e->io_out[0].alloc(b_io, true)) ||
         (rc = e->io_in[1].alloc(b_io, true)) || (rc = e->io_out[1].alloc(b_io, true)) ||
         (rc = e->taps.alloc(sizeof(float) * 2 * (size_t) e->B * e->ring, true)) || (rc = e->rr_ptrs.alloc(sizeof(float*) * n_irs, true)) ||
-        (rc = e->rr_pos.alloc(sizeof(int) * n_irs, true)) || (rc = e->rr_list.alloc(sizeof(int) * n_irs, true))) {
+        (rc = e->rr_pos.alloc(sizeof(int) * n_irs, true)) || (rc = e->rr_list.alloc(sizeof(int) * n_irs, true)) || (rc = e->work.alloc(sizeof(int) * 4, true))) {
         delete e;
         return rc;
     }
@@ -672,7 +739,7 @@ int irb_engine_process_device(irb_engine* e, const float* in_dev, float* out_dev
     CK(cudaSetDevice(e->device));
     int rc = engine_check_binding(e);
     if (rc) return rc;
-    const size_t blk = (size_t) e->B * e->n_chans;
+    const size_t blk = (size_t) e->B * e->active;
     for (int b = 0; b < n_blocks; ++b)
         if ((rc = engine_step_device(e, in_dev + b * blk, out_dev + b * blk))) return rc;
     return 0;
@@ -685,10 +752,9 @@ constexpr int kMaxGroups = 8;                        // channel groups a large s
 // one block, host to host, as a single graph launch; *done = false when the caller should take the plain path instead
 int engine_process_one_graphed(irb_engine* e, const float* in_host, float* out_host, bool* done) {
     *done = false;
-    const size_t bytes = sizeof(float) * (size_t) e->B * e->n_chans;
-    static const bool disabled = getenv("IRB_NO_GRAPH") != nullptr;
-    if (disabled || !e->use_graph || e->timing || bytes > kGraphMaxBytes) return 0;
-    const irb_engine::GraphSig sig{(int) e->h_rr_list.size(), e->split_in, e->cluster_dim, use_slots(e) ? 1 : 0, e->fuse_fwd ? 1 : 0, e->stream};
+    const size_t bytes = sizeof(float) * (size_t) e->B * e->active;
+    if (irbh::g_tuning.no_graph || !e->use_graph || e->timing || bytes > kGraphMaxBytes) return 0;
+    const irb_engine::GraphSig sig{(int) e->h_rr_list.size(), e->split_in, e->cluster_dim, use_slots(e) ? 1 : 0, e->fuse_fwd ? 1 : 0, e->active, tuning_variant(), e->stream};
     if (!(sig == e->g_sig)) {
         if (e->g_exec) { cudaGraphExecDestroy(e->g_exec); e->g_exec = nullptr; }
         e->g_sig = sig;
@@ -739,11 +805,12 @@ int engine_process_wait(irb_engine* e) {
     e->pipe_pending = false;
     return 0;
 }
+
 int engine_process_enqueue(irb_engine* e, const float* in_host, float* out_host, int n_blocks, size_t stride, bool allow_graph) {
     CK(cudaSetDevice(e->device));
     int rc = engine_check_binding(e);
     if (rc) return rc;
-    const size_t blk = (size_t) e->B * e->n_chans;
+    const size_t blk = (size_t) e->B * e->active;
     if (n_blocks == 1) {
         if (e->pipe_pending && (rc = engine_process_wait(e))) return rc;               // submitted blocks still own the staging slots
         // a live callback: one block in, one block out.  Small blocks replay a captured graph (one launch); larger ones
@@ -753,7 +820,7 @@ int engine_process_enqueue(irb_engine* e, const float* in_host, float* out_host,
             if ((rc = engine_process_one_graphed(e, in_host, out_host, &done)) || done) return rc;
         }
         const int rows = tile_rows(e->M);
-        const int tiles = (e->n_chans + rows - 1) / rows;
+        const int tiles = (e->active + rows - 1) / rows;
         const int groups = (e->timing || sizeof(float) * blk < (4u << 20)) ? 1 : (int) std::min<long long>(kMaxGroups, tiles / (4LL * e->num_sms) > 0 ? tiles / (4LL * e->num_sms) : 1);
         if (groups <= 1) {
             CK(cudaMemcpyAsync(e->io_in[0].p, in_host, sizeof(float) * blk, cudaMemcpyHostToDevice, e->stream));
@@ -769,7 +836,7 @@ int engine_process_enqueue(irb_engine* e, const float* in_host, float* out_host,
             for (auto& ev : e->ev_grp) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         }
         for (int g = 0; g < groups; ++g) {
-            const int c0 = (int) ((long long) tiles * g / groups) * rows, c1 = std::min(e->n_chans, (int) ((long long) tiles * (g + 1) / groups) * rows);
+            const int c0 = (int) ((long long) tiles * g / groups) * rows, c1 = std::min(e->active, (int) ((long long) tiles * (g + 1) / groups) * rows);
             const size_t off = (size_t) c0 * e->B, cnt = (size_t) (c1 - c0) * e->B;
             CK(cudaMemcpyAsync(e->io_in[0].as<float>() + off, in_host + off, sizeof(float) * cnt, cudaMemcpyHostToDevice, e->s_in));
             CK(cudaEventRecord(e->ev_grp[2 * g], e->s_in));
@@ -803,10 +870,24 @@ int engine_process_enqueue(irb_engine* e, const float* in_host, float* out_host,
 }
 }  // namespace
 
+// Streams come and go: only channels [0, n_active) take part in the following block steps (their FDL rings advance, the
+// others keep their state untouched); in/out arrays of the process calls are then [n_blocks][n_active][block_size].
+// n_active must be a whole number of kernel tiles (irb_engine_tile_channels()) or n_channels.
+int irb_engine_set_active_channels(irb_engine* e, int n_active) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    if (n_active < 1 || n_active > e->n_chans) return fail(IRB_ERR_ARG, "n_active %d outside [1, %d]", n_active, e->n_chans);
+    if (n_active != e->n_chans && n_active % tile_rows(e->M)) return fail(IRB_ERR_ARG, "n_active %d is not a multiple of the %d channels of a kernel tile", n_active, tile_rows(e->M));
+    if (e->pipe_pending) { int rc = engine_process_wait(e); if (rc) return rc; }
+    e->active = n_active;
+    e->plan_dirty = true;
+    return 0;
+}
+int irb_engine_active_channels(const irb_engine* e) { return e ? e->active : fail(IRB_ERR_ARG, "engine is null"); }
+
 int irb_engine_process(irb_engine* e, const float* in_host, float* out_host, int n_blocks) {
     if (!e || !in_host || !out_host) return fail(IRB_ERR_ARG, "null argument");
     if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
-    int rc = engine_process_enqueue(e, in_host, out_host, n_blocks, (size_t) e->B * e->n_chans, true);
+    int rc = engine_process_enqueue(e, in_host, out_host, n_blocks, (size_t) e->B * e->active, true);
     if (rc) return rc;
     return engine_process_wait(e);
 }
@@ -819,7 +900,7 @@ int irb_engine_submit(irb_engine* e, const float* in_host, float* out_host, int 
     if (n_blocks < 0) return fail(IRB_ERR_ARG, "n_blocks < 0");
     if (n_blocks == 0) return 0;
     if (n_blocks == 1) return fail(IRB_ERR_ARG, "irb_engine_submit takes at least two blocks per call (one block at a time is irb_engine_process)");
-    return engine_process_enqueue(e, in_host, out_host, n_blocks, (size_t) e->B * e->n_chans, false);
+    return engine_process_enqueue(e, in_host, out_host, n_blocks, (size_t) e->B * e->active, false);
 }
 int irb_engine_wait(irb_engine* e) {
     if (!e) return fail(IRB_ERR_ARG, "engine is null");
@@ -840,22 +921,23 @@ int irb_engine_process_callback(irb_engine* e, const float* in_host, float* out_
     CK(cudaSetDevice(e->device));
     int rc = engine_check_binding(e);
     if (rc) return rc;
-    const size_t blk = (size_t) e->B * e->n_chans;
+    const size_t blk = (size_t) e->B * e->active;
     if (e->cb_blocks < n_blocks) {
         e->cb_in.reset(new (std::nothrow) DevBuf); e->cb_out.reset(new (std::nothrow) DevBuf);
         if (!e->cb_in || !e->cb_out) return fail(IRB_ERR_ARG, "out of host memory");
         e->cb_blocks = 0;
-        if ((rc = e->cb_in->alloc(sizeof(float) * blk * n_blocks, false)) || (rc = e->cb_out->alloc(sizeof(float) * blk * n_blocks, false))) return rc;
+        const size_t cap = sizeof(float) * (size_t) e->B * e->n_chans * n_blocks;       // sized for every channel: the active count may grow later
+        if ((rc = e->cb_in->alloc(cap, false)) || (rc = e->cb_out->alloc(cap, false))) return rc;
         e->cb_blocks = n_blocks;
     }
     float* din = e->cb_in->as<float>();
     float* dout = e->cb_out->as<float>();
     CK(cudaMemcpyAsync(din, in_host, sizeof(float) * blk * n_blocks, cudaMemcpyHostToDevice, e->stream));
     for (int b = 0; b < n_blocks; ++b)
-        if ((rc = engine_launch_fwd(e, din + b * blk, true, false, 0, e->n_chans))) return rc;
+        if ((rc = engine_launch_fwd(e, din + b * blk, true, false, 0, e->active))) return rc;
     for (int b = 0; b < n_blocks; ++b) {
-        if ((rc = engine_launch_fwd(e, nullptr, false, true, 0, e->n_chans))) return rc;
-        if ((rc = engine_launch_mac(e, dout + b * blk, n_blocks - 1 - b, nullptr, 0, e->n_chans))) return rc;
+        if ((rc = engine_launch_fwd(e, nullptr, false, true, 0, e->active))) return rc;
+        if ((rc = engine_launch_mac(e, dout + b * blk, n_blocks - 1 - b, nullptr, 0, e->active))) return rc;
     }
     CK(cudaMemcpyAsync(out_host, dout, sizeof(float) * blk * n_blocks, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -921,49 +1003,6 @@ int irb_engine_read_fdl_spectrum(irb_engine* e, int chan, int age, float* out_pa
     return 0;
 }
 
-int irb_hbm_read_probe(size_t bytes, int iters, double* gbs) {
-    if (!gbs || iters < 1 || bytes < (1u << 20)) return fail(IRB_ERR_ARG, "bad argument");
-    CK(cudaSetDevice(irbh::g_device));
-    const size_t pieces = bytes / 16384;
-    DevBuf buf, sink;
-    int rc;
-    if ((rc = buf.alloc(pieces * 16384, true)) || (rc = sink.alloc(sizeof(unsigned), true))) return rc;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, irbh::g_device);
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    const int grid = sms * 4;                                  // 4 x 512 threads resident per SM
-    // IRB_PROBE_WRITE_EVERY=n: every n-th 16 KB piece is written instead of read (how much a small write share costs the stream)
-    static const int write_every = [] { const char* v = getenv("IRB_PROBE_WRITE_EVERY"); return v ? atoi(v) : 0; }();
-    static const int store_kind = [] { const char* v = getenv("IRB_PROBE_STORE_KIND"); return v ? atoi(v) : 0; }();   // 0 plain, 1 .cs, 2 L2 evict_first, 3 .wt, 4 .cg, 5 L2 evict_last
-    irb::k_read_probe<<<grid, 512>>>(buf.as<float4>(), pieces, sink.as<unsigned>(), write_every, store_kind);
-    CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) irb::k_read_probe<<<grid, 512>>>(buf.as<float4>(), pieces, sink.as<unsigned>(), write_every, store_kind);
-    CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
-    CK(cudaGetLastError());
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    g_launches += iters + 1;
-    *gbs = (double) (pieces * 16384) * iters / (ms * 1e-3) / 1e9;
-    return 0;
-}
-
-int irb_engine_mac_only_device(irb_engine* e, float* acc_dev) {
-    if (!e || !acc_dev) return fail(IRB_ERR_ARG, "null argument");
-    CK(cudaSetDevice(e->device));
-    int rc = engine_check_binding(e);
-    if (rc) return rc;
-    irb::MacArgs m{};
-    fill_mac_args(e, m, 0, e->n_chans);
-    m.Y = (float2*) acc_dev;
-    rc = launch_mac(e->M, false, use_slots(e), e->cluster_dim, m, e->stream);
-    if (rc) return rc;
-    e->launches += 1;
-    return 0;
-}
-
 // fp::ir::IRtoRealFFTRaw (fp/ir.cpp:106-147): the IR cut into len/part_size + 1 partitions of part_size samples, each
 // zero-padded to 2*part_size, transformed, stored as {Re X[0], Re X[N/2], re1, im1, ...} -- exactly the packed spectrum
 // rows of the engine.  out: (len/part_size + 1) * 2*part_size floats.  part_size must be a power of two in [16, 2048].
@@ -975,9 +1014,9 @@ int irb_ir_to_real_fft_raw(const float* x, int len, int part_size, float* out) {
     const float2* W = nullptr;
     int rc = irbh::twiddles(dev, M, &W);
     if (rc) return rc;
-    irbh::StreamGuard sg;
-    if ((rc = sg.create())) return rc;
     irbh::ScratchBuf dx, dH;
+    irbh::StreamGuard sg;              // declared after the buffers: its destructor drains the stream before they go back to the pool
+    if ((rc = sg.create())) return rc;
     if ((rc = dx.alloc(sizeof(float) * (size_t) len, false)) || (rc = dH.alloc(sizeof(float2) * (size_t) M * parts, true))) return rc;
     CK(cudaMemcpyAsync(dx.p, x, sizeof(float) * (size_t) len, cudaMemcpyHostToDevice, sg.s));
     irb::FwdArgs f{};
@@ -1024,10 +1063,10 @@ int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, i
     const bool fold = (ch_h == 2 && ch_x == 1);            // IRStereoAudioMono: (L+R)/2, :120-121
     const int n_ir = (ch_h == 2 && ch_x == 2) ? 2 : 1;     // IRStereoAudioStereo is channel-wise, :176-181
 
-    cudaStream_t st = nullptr;
-    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{st};
     irbh::ScratchBuf dx, dh, dX, dH, dout, dtail, dnp, dir;
+    irbh::StreamGuard sg;              // declared after the buffers: an early return drains the stream before they go back to the pool
+    if ((rc = sg.create())) return rc;
+    cudaStream_t st = sg.s;
     const size_t spec = sizeof(float2) * (size_t) M;
     if ((rc = dx.alloc(sizeof(float) * (size_t) ch_x * len_x, false)) || (rc = dh.alloc(sizeof(float) * (size_t) ch_h * len_h, false)) ||
         (rc = dX.alloc(spec * bpc * ch_x, false)) || (rc = dH.alloc(spec * P * n_ir, false)) ||
@@ -1056,7 +1095,8 @@ int irb_convolve_periodic(const float* x, int ch_x, int len_x, const float* h, i
     m.n_rows = bpc * ch_x; m.H = dH.as<float2>(); m.ir_stride = (long long) P * M; m.ir_of_chan = dir.as<int>(); m.nparts = dnp.as<int>();
     m.W = W; m.B = B; m.out = dout.as<float>(); m.out_chan_stride = Lout; m.Lout = (int) Lw; m.ov = nullptr; m.tail = dtail.as<float>();
     m.split_in = 1;
-    if ((rc = launch_mac(M, true, false, 1, m, st))) return rc;
+    mac_policy(m);
+    if ((rc = launch_mac(M, true, false, 1, 148, m, st))) return rc;
     {
         const long long n = (long long) bpc * B * ch_x;
         irb::k_ola_tail<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(dout.as<float>(), Lout, (int) Lw, dtail.as<float>(), B, bpc, ch_x);
@@ -1176,3 +1216,21 @@ size_t irb_group_state_bytes(const irb_group* g) {
 
 }  // extern "C"
 
+// ---- internals reached by the bench-only translation unit (irb_benchaids.cu, include/irb_b200_bench.h) -------------------
+namespace irbh {
+// the pure FDL multiply-accumulate (no forward / inverse FFT) on the current state into n_channels * M complex
+int engine_mac_only(irb_engine* e, float* acc_dev) {
+    if (!e || !acc_dev) return fail(IRB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(e->device));
+    int rc = engine_check_binding(e);
+    if (rc) return rc;
+    irb::MacArgs m{};
+    fill_mac_args(e, m, 0, e->active);
+    m.Y = (float2*) acc_dev;
+    m.work = nullptr;
+    rc = launch_mac(e->M, false, use_slots(e), e->cluster_dim, e->num_sms, m, e->stream);
+    if (rc) return rc;
+    e->launches += 1;
+    return 0;
+}
+}  // namespace irbh

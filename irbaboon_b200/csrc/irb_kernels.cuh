@@ -62,6 +62,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
 __device__ __forceinline__ void mbar_arrive_after(uint64_t* b, uint32_t dep) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b) + dep) : "memory");
 }
+// Orders this thread's earlier generic-proxy accesses to shared memory (the ld.shared of a ring stage) ahead of later
+// async-proxy accesses (the bulk copy that refills the stage once it is released): issued by every lane before the warp's
+// release of a TMA-filled stage.  mbar_arrive_after's data dependency stays as the second line of defence.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -293,6 +297,12 @@ struct MacArgs {
     int* head_rw;
     int producer_sleep_ns;     // the TMA producer sleeps this long between polls of a busy stage (0: spin)
     unsigned zero;             // always 0; unknown to the compiler (mbar_arrive_after)
+    int release_fence;         // fence.proxy.async before a ring stage is released (irb_tuning.hpp)
+    int release_dep;           // the release carries a data dependency on the values read from the stage (mbar_arrive_after)
+    // k_mac_p (persistent block step): work[0] = next unit, work[1] = CTAs that have finished (the last one clears both);
+    // the launch's units in fetch order: unit_n[l] units of max(1, ROWS >> l) rows each, l = 0 .. 3
+    int* work;
+    int unit_n[4];
 };
 
 // Time-domain epilogue of a tile whose accumulated packed spectra sit in shared memory, row r at tile + r*M
@@ -350,6 +360,12 @@ __device__ __forceinline__ long long fdl_row_offset(const MacArgs& a, int chan, 
     return (chan / grp) * a.fdl_chan_stride + (long long) (chan % grp) * M;
 }
 template <int M> __device__ __forceinline__ long long fdl_slot_stride(const MacArgs& a) { return a.fdl_slot_stride ? a.fdl_slot_stride : M; }
+
+// consumer release of a TMA-filled ring stage by the warp's elected lane (after the warp-wide fence.proxy.async + __syncwarp)
+__device__ __forceinline__ void mbar_release_stage(uint64_t* b, uint32_t dep, const MacArgs& a) {
+    if (a.release_dep) mbar_arrive_after(b, dep & a.zero);
+    else mbar_arrive(b);
+}
 
 // Shared-IR kernel: the whole tile is bound to one IR and a ring stage holds U consecutive partitions of it.
 template <int M, int U>
@@ -551,8 +567,9 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
                 }
             }
         }
+        if (a.release_fence) fence_proxy_async_smem();
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive_after(&sm.empty[st], dep & a.zero);
+        if ((tid & 31) == 0) mbar_release_stage(&sm.empty[st], dep, a);
     };
 
     if (ngroups > 0) load_group(xa, 0);
@@ -751,8 +768,9 @@ __global__ void __launch_bounds__(kThreads + 32, M <= 1024 ? 3 : 2) k_mac_tma(co
                 ac.w = fmaf(xv.w, h.z, fmaf(xv.z, h.w, ac.w));
             }
         }
+        if (a.release_fence) fence_proxy_async_smem();
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive_after(&sm.empty[st], dep & a.zero);
+        if ((tid & 31) == 0) mbar_release_stage(&sm.empty[st], dep, a);
     }
 
     bar_compute();                                        // every warp is through its last group: stage 0 is the tile again
@@ -926,8 +944,9 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
                     ac.w = fmaf(xv.w, h.z, fmaf(xv.z, h.w, ac.w));
                 }
             }
+            if (a.release_fence) fence_proxy_async_smem();
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive_after(&sm.empty[st], dep & a.zero);
+            if ((tid & 31) == 0) mbar_release_stage(&sm.empty[st], dep, a);
         };
         if (ngroups > 0) load_group(xa, 0);
         for (int g = 0; g < ngroups; g += 2) {
@@ -1003,44 +1022,6 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
             if (row < a.n_rows) reinterpret_cast<float4*>(a.Y + (long long) row * M)[o % (M / 2)] = reinterpret_cast<const float4*>(fin)[o];
         }
     }
-}
-
-// read-only bandwidth probe (irb_hbm_read_probe): every CTA walks the buffer grid-strided in 16 KB pieces, four independent
-// 32-byte loads per thread in flight; the XOR of everything read is stored only if it equals a value it never takes
-__device__ __forceinline__ void probe_store(float4* q, float4 v, int kind, uint64_t pol) {
-    if (kind == 1) asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    else if (kind == 2) asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
-    else if (kind == 3) asm volatile("st.global.wt.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    else if (kind == 4) asm volatile("st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    else *q = v;
-}
-static __global__ void __launch_bounds__(512) k_read_probe(float4* __restrict__ p, size_t n_pieces, unsigned* sink, int write_every, int store_kind) {
-    uint64_t pol = 0;
-    if (store_kind == 2) pol = l2_policy_evict_first();
-    if (store_kind == 5) { asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); }
-    const int sk = store_kind == 5 ? 2 : store_kind;
-    unsigned acc = 0;
-    size_t piece = blockIdx.x;
-    for (; piece + 3 * (size_t) gridDim.x < n_pieces; piece += 4 * (size_t) gridDim.x) {
-        float4 a[4], b[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float4* q = p + (piece + u * (size_t) gridDim.x) * 1024 + 2 * threadIdx.x;         // 16 KB = 512 threads x 32 bytes
-            const size_t pc = piece + u * (size_t) gridDim.x;
-            if (write_every > 0 && pc % (size_t) write_every == 0) {                          // a share of the pieces is WRITTEN instead
-                probe_store(q, make_float4(1.f, 2.f, 3.f, 4.f), sk, pol); probe_store(q + 1, make_float4(5.f, 6.f, 7.f, 8.f), sk, pol);
-                a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else ldg_stream256(q, a[u], b[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc ^= __float_as_uint(a[u].x) ^ __float_as_uint(a[u].w) ^ __float_as_uint(b[u].y) ^ __float_as_uint(b[u].z);
-    }
-    for (; piece < n_pieces; piece += gridDim.x) {
-        float4 a, b;
-        ldg_stream256(p + piece * 1024 + 2 * threadIdx.x, a, b);
-        acc ^= __float_as_uint(a.x) ^ __float_as_uint(a.w) ^ __float_as_uint(b.y) ^ __float_as_uint(b.z);
-    }
-    if (acc == 0x7fc12345u) *sink = acc;
 }
 
 // (a + b) / 2 : tools::sumToMono (fp/tools.cpp:25-29)

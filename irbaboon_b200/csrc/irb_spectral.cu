@@ -10,6 +10,7 @@
 
 #include "irb_common.hpp"
 #include "irb_spectral.cuh"
+#include "irb_tuning.hpp"
 
 namespace {
 
@@ -247,13 +248,13 @@ int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h
     Plan plan;
     int rc = plan.init(dev, M);
     if (rc) return rc;
-    irbh::StreamGuard sg;
+    DevBuf dx, dh, dhf, Zx, Zh, tmp, dy;
+    irbh::StreamGuard sg;                                // after the buffers: drains the stream before they return to the pool
     if ((rc = sg.create())) return rc;
     cudaStream_t st = sg.s;
     const bool fold = ch_h == 2 && ch_x == 1;            // IRStereoAudioMono -> sumToMono (:302)
     const int n_ir = (ch_h == 2 && ch_x == 2) ? 2 : 1;   // IRStereoAudioStereo is channel-wise (:320-323)
     const long long lxe = (len_x + 1) & ~1LL, lhe = (len_h + 1) & ~1LL;     // even strides keep float2 loads aligned
-    DevBuf dx, dh, dhf, Zx, Zh, tmp, dy;
     if ((rc = dx.alloc(sizeof(float) * lxe * ch_x, true)) || (rc = dh.alloc(sizeof(float) * lhe * ch_h, true)) || (rc = dhf.alloc(sizeof(float) * lhe, true)) ||
         (rc = Zx.alloc(sizeof(float2) * (size_t) M * ch_x, false)) || (rc = Zh.alloc(sizeof(float2) * (size_t) M * n_ir, false)) ||
         (rc = tmp.alloc(sizeof(float2) * (size_t) M * 2, false)) || (rc = dy.alloc(sizeof(float2) * (size_t) M * ch_x, false)))
@@ -305,13 +306,18 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
     CK(cudaSetDevice(dev));
     Plan plan;
     if ((rc = plan.init(dev, M))) return rc;
-    irbh::StreamGuard sg, sg_in, sg_out;
+    struct Slot { DevBuf dn, Zn, dy, dy2, tmp; cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr, t0 = nullptr, t1 = nullptr;
+                  bool dn_busy = false, dy_busy = false, timed = false;
+                  ~Slot() { for (cudaEvent_t e : {ev_in, ev_done, ev_out, t0, t1}) if (e) cudaEventDestroy(e); } } slot[2];
+    DevBuf dd, Zd, Bd, Sd, dtmp, Sall;
+    Smoother sm;
+    irbh::StreamGuard sg, sg_in, sg_out;                 // after every buffer: an early return drains the streams before the buffers return to the pool
     if ((rc = sg.create()) || (rc = sg_in.create()) || (rc = sg_out.create())) return rc;
     cudaStream_t st = sg.s;
     const long long lne = (len_num + 1) & ~1LL, lde = (len_den + 1) & ~1LL;
     // captures per sub-batch: about 48 MB of spectra (IRB_DECONV_SUB overrides), never more than the batch
-    static const int sub_env = [] { const char* v = getenv("IRB_DECONV_SUB"); return v ? atoi(v) : 0; }();
-    int sub = sub_env > 0 ? sub_env : (int) std::max<long long>(1, (48LL << 20) / ((long long) sizeof(float2) * M));
+    const int sub_pref = irbh::g_tuning.deconv_sub;
+    int sub = sub_pref > 0 ? sub_pref : (int) std::max<long long>(1, (48LL << 20) / ((long long) sizeof(float2) * M));
     sub = std::min(sub, batch);
     // smoothing: the running sum is one sequential chain per capture and costs the same few milliseconds per pass for 1 or
     // 500 captures, so a whole GROUP of captures (about 5 GB of spectra and sums) is smoothed at once, between a first phase
@@ -319,11 +325,6 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
     // sub-batches with their copies overlapped.
     const int grp = smoothing ? (int) std::min<long long>(batch, std::max<long long>(sub, (5LL << 30) / (16LL * (M + 1)))) : batch;
     const bool fused = plan.big() && !smoothing;
-    struct Slot { DevBuf dn, Zn, dy, dy2, tmp; cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr, t0 = nullptr, t1 = nullptr;
-                  bool dn_busy = false, dy_busy = false, timed = false;
-                  ~Slot() { for (cudaEvent_t e : {ev_in, ev_done, ev_out, t0, t1}) if (e) cudaEventDestroy(e); } } slot[2];
-    DevBuf dd, Zd, Bd, Sd, dtmp, Sall;
-    Smoother sm;
     const float smooth_per_avg = 1.0 / 13.0;                                          // fp/convolution.cpp:390 (a float there)
     const int nslots = batch > sub ? 2 : 1;
     for (int i = 0; i < nslots; ++i) {
@@ -472,10 +473,10 @@ int irb_fft_transform(const float* x, int ch, int len, int format_ampl_phase, fl
     CK(cudaSetDevice(dev));
     Plan plan;
     if ((rc = plan.init(dev, M))) return rc;
+    DevBuf dx, Z, tmp, S;
     irbh::StreamGuard sg;
     if ((rc = sg.create())) return rc;
     cudaStream_t st = sg.s;
-    DevBuf dx, Z, tmp, S;
     if ((rc = dx.alloc(sizeof(float) * ((size_t) len + 1), true)) || (rc = Z.alloc(sizeof(float2) * (size_t) M, false)) || (rc = tmp.alloc(sizeof(float2) * (size_t) M, false)) ||
         (rc = S.alloc(sizeof(float2) * (size_t) N, true)))
         return rc;
@@ -499,10 +500,10 @@ int irb_fft_inv_transform(const float* spec, int ch, int fft_size, float* out) {
     CK(cudaSetDevice(dev));
     Plan plan;
     if ((rc = plan.init(dev, M))) return rc;
+    DevBuf S, Z, tmp, dy;
     irbh::StreamGuard sg;
     if ((rc = sg.create())) return rc;
     cudaStream_t st = sg.s;
-    DevBuf S, Z, tmp, dy;
     if ((rc = S.alloc(sizeof(float) * (size_t) fft_size * ch, false)) || (rc = Z.alloc(sizeof(float2) * (size_t) M * ch, false)) ||
         (rc = tmp.alloc(sizeof(float2) * (size_t) M * ch, false)) || (rc = dy.alloc(sizeof(float2) * (size_t) M * ch, false)))
         return rc;
@@ -521,12 +522,12 @@ int irb_averaging_filter(float* spec, int ch, int fft_size, double octave_fracti
     if (fft_size & (fft_size - 1)) return 0;                                          // not a power of two: untouched (:412-415)
     const int N = fft_size / 2, M = N / 2, dev = irbh::current_device();
     CK(cudaSetDevice(dev));
+    DevBuf S;
+    Smoother sm;
     irbh::StreamGuard sg;
     int rc;
     if ((rc = sg.create())) return rc;
     cudaStream_t st = sg.s;
-    DevBuf S;
-    Smoother sm;
     if ((rc = S.alloc(sizeof(float) * (size_t) fft_size * ch, false)) || (rc = sm.init(M, ch, octave_fraction, sample_rate, log_avg, st))) return rc;
     CK(cudaMemcpyAsync(S.p, spec, sizeof(float) * (size_t) fft_size * ch, cudaMemcpyHostToDevice, st));
     if ((rc = sm.run(S.as<float2>(), N, ch, 1, log_avg, include_phase, include_amplitude, st))) return rc;
@@ -549,10 +550,10 @@ int irb_ess_generate(double duration_s, double sample_rate, double f1, double f2
     const double g = pow(10.0, gain_db / 20.0);                                       // tools::dBToLin(double), fp/tools.cpp:93-95
     const double kdecay = pow(10.0, (-6.0 * log2(w2 / w1)) / 20.0 / T);               // fp/ExpSineSweep.cpp:70
     CK(cudaSetDevice(irbh::current_device()));
+    DevBuf d;
     irbh::StreamGuard sg;
     int rc;
     if ((rc = sg.create())) return rc;
-    DevBuf d;
     if ((rc = d.alloc(sizeof(double) * (size_t) n, false))) return rc;
     irb::k_ess<<<grid1(n, 1), 256, 0, sg.s>>>(d.as<double>(), n, g, K, L, inverse, kdecay);
     LAUNCHED();

@@ -1,0 +1,25 @@
+// irb_tuning.hpp -- launch-policy knobs of libirb_b200.so.  The product path reads these plain globals with the defaults
+// below and nothing else (no environment variable is consulted anywhere in the library); the only writer is
+// irbx_set_tuning() in irb_benchaids.cu, the bench-only translation unit behind include/irb_b200_bench.h, which
+// A/B measurements and tests use to select the other form of a kernel.
+#pragma once
+
+namespace irbh {
+
+struct Tuning {
+    int mac_persistent = 1;      // shared-IR / per-stream-IR block step as the persistent TMA kernel k_mac_p (0: k_mac_tma / k_mac_slots)
+    int mac_tma = 1;             // non-persistent fused step: FDL through TMA (k_mac_tma); 0: register-staged k_mac<FUSE>
+    int mac_wide = 1;            // register-staged MAC: 32-byte FDL loads (0: 16-byte)
+    int mac_u = 1;               // register-staged MAC: IR partitions per ring stage (1 or 2)
+    int fdl_plain = 0;           // engines created from now on store the FDL [chan][slot][M] instead of tile-interleaved
+    int producer_sleep_ns = 200; // the TMA producer sleeps this long between polls of a busy stage (0: spin)
+    int no_graph = 0;            // single small blocks: plain launches instead of the captured CUDA graph
+    int deconv_sub = 0;          // captures per sub-batch of irb_deconvolve_batch (0: about 48 MB of spectra)
+    int release_fence = 1;       // fence.proxy.async between the last ld.shared of a ring stage and its release
+    int release_dep = 1;         // the release also carries a data dependency on the values read (0 + 0 = the unguarded round-1 form: sanitizer experiments only)
+    int persistent_ctas = 0;     // k_mac_p: CTAs per SM (0: the kernel's own choice)
+    int unit_narrowing = 1;      // k_mac_p: the last partial wave of a launch runs on tiles of fewer rows
+};
+extern Tuning g_tuning;
+
+}  // namespace irbh

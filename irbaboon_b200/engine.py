@@ -6,12 +6,14 @@ there is no CPU fallback here -- if the library is missing, or no B200 is visibl
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IRB_LIB") or os.path.join(_HERE, "libirb_b200.so")      # IRB_LIB: another build of the library (A/B measurements)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "irb_b200.h")
+BENCH_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "irb_b200_bench.h")      # measurement aids, not the drop-in boundary
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 _vp = ctypes.c_void_p
@@ -45,6 +47,8 @@ _SIGS = {
     "irb_engine_bind": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "irb_engine_tile_channels": (ctypes.c_int, [_vp]),
     "irb_engine_reset": (ctypes.c_int, [_vp]),
+    "irb_engine_set_active_channels": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "irb_engine_active_channels": (ctypes.c_int, [_vp]),
     "irb_engine_process": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "irb_engine_process_callback": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
     "irb_engine_process_device": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
@@ -62,8 +66,6 @@ _SIGS = {
     "irb_launch_count": (ctypes.c_longlong, []),
     "irb_release_workspace": (ctypes.c_size_t, []),
     "irb_last_compute_ms": (ctypes.c_double, []),
-    "irb_engine_mac_only_device": (ctypes.c_int, [_vp, _vp]),
-    "irb_hbm_read_probe": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "irb_group_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_int)] + [ctypes.c_int] * 5),
     "irb_group_destroy": (ctypes.c_int, [_vp]),
     "irb_group_device_count": (ctypes.c_int, [_vp]),
@@ -86,6 +88,17 @@ _SIGS = {
     "irb_ess_generate": (ctypes.c_int, [ctypes.c_double] * 5 + [ctypes.c_int, _vp, ctypes.c_int]),
 }
 
+# include/irb_b200_bench.h: bench-only entry points (irbaboon_b200/csrc/irb_benchaids.cu)
+_BENCH_SIGS = {
+    "irbx_set_tuning": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "irbx_get_tuning": (ctypes.c_int, [ctypes.c_char_p]),
+    "irbx_engine_mac_only_device": (ctypes.c_int, [_vp, _vp]),
+    "irbx_hbm_read_probe": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "irbx_copy_probe_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_size_t, ctypes.c_int]),
+    "irbx_copy_probe_run": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double)]),
+    "irbx_copy_probe_destroy": (ctypes.c_int, [_vp]),
+}
+
 
 def lib():
     """Load libirb_b200.so; raises if it has not been built (python -m irbaboon_b200.build)."""
@@ -94,7 +107,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise FileNotFoundError(LIB_PATH + " is missing: run `python -m irbaboon_b200.build` (there is no CPU fallback)")
         L = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in _SIGS.items():
+        for name, (res, args) in list(_SIGS.items()) + list(_BENCH_SIGS.items()):
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
@@ -138,22 +151,71 @@ def last_compute_ms():
     return lib().irb_last_compute_ms()
 
 
-def hbm_read_probe(nbytes, iters=5):
-    """GB/s of a read-only streaming kernel over nbytes of device memory (measurement aid)."""
+def hbm_read_probe(nbytes, iters=5, write_every=0, store_kind=0):
+    """GB/s of a read-only streaming kernel over nbytes of device memory (measurement aid, irb_b200_bench.h)."""
     g = ctypes.c_double(0.0)
-    _ck(lib().irb_hbm_read_probe(int(nbytes), int(iters), ctypes.byref(g)))
+    _ck(lib().irbx_hbm_read_probe(int(nbytes), int(iters), int(write_every), int(store_kind), ctypes.byref(g)))
     return g.value
 
 
+def set_tuning(name, value):
+    """Launch-policy knob of the library by name (irb_b200_bench.h; A/B measurements and tests only)."""
+    _ck(lib().irbx_set_tuning(name.encode(), int(value)))
+
+
+def get_tuning(name):
+    return _ck(lib().irbx_get_tuning(name.encode()))
+
+
+class CopyProbe:
+    """Copy-only host<->device ceiling (irb_b200_bench.h): `nbytes` per direction, no kernels."""
+
+    def __init__(self, nbytes, host_mode=0, device=0):
+        self._h = _vp()
+        _ck(lib().irbx_copy_probe_create(ctypes.byref(self._h), int(device), int(nbytes), int(host_mode)))
+        self.nbytes = int(nbytes)
+
+    def run(self, iters=8, direction=3, chunk_bytes=0):
+        """-> wall seconds of `iters` rounds (direction 1: H2D, 2: D2H, 3: both at once)."""
+        s = ctypes.c_double(0.0)
+        _ck(lib().irbx_copy_probe_run(self._h, int(iters), int(direction), int(chunk_bytes), ctypes.byref(s)))
+        return s.value
+
+    def close(self):
+        if self._h:
+            lib().irbx_copy_probe_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _PinnedOwner:
+    """Owns one cudaMallocHost block: the block is released when the last numpy view of it is collected, or by pinned_free."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+        self._fin = weakref.finalize(self, lib().irb_host_free, ptr)
+
+    def free(self):
+        self._fin()
+
+
 def pinned_empty(shape, dtype=np.float32):
-    """numpy array over cudaMallocHost memory (freed when the array's base is collected)."""
+    """numpy array over cudaMallocHost memory.  The memory goes back when the array (and every view of it) is collected;
+    pinned_free(arr) releases it at once (the array must not be touched afterwards)."""
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = lib().irb_host_alloc(n)
     if not p:
         raise IrbError(IRB_ERR_CUDA, lib().irb_last_error().decode())
-    buf = (ctypes.c_char * n).from_address(p)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    _PINNED[arr.__array_interface__["data"][0]] = p
+    owner = _PinnedOwner(p)
+    buf = (ctypes.c_char * max(n, 1)).from_address(p)
+    buf._irb_owner = owner                      # the ctypes buffer is the base of every numpy view: it keeps the owner alive
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[p] = weakref.ref(owner)
     return arr
 
 
@@ -161,9 +223,10 @@ _PINNED = {}
 
 
 def pinned_free(arr):
-    p = _PINNED.pop(arr.__array_interface__["data"][0], None)
-    if p:
-        lib().irb_host_free(p)
+    ref = _PINNED.pop(arr.__array_interface__["data"][0], None)
+    owner = ref() if ref else None
+    if owner is not None:
+        owner.free()
 
 
 def convolve_periodic(x, h, block_size=256):
@@ -272,6 +335,7 @@ class Engine:
         _ck(lib().irb_engine_create(ctypes.byref(self._h), int(device), int(block_size), int(max_partitions), int(n_channels), int(n_irs)))
         self.block_size, self.max_partitions, self.n_channels, self.n_irs, self.device = block_size, max_partitions, n_channels, n_irs, device
         self.fft_size = lib().irb_engine_fft_size(self._h)
+        self.active_channels = n_channels
 
     def close(self):
         if self._h:
@@ -346,16 +410,19 @@ class Engine:
         x = np.ascontiguousarray(x, np.float32)
         shp = x.shape
         nb = 1 if x.ndim == 2 else shp[0]
-        assert shp[-2:] == (self.n_channels, self.block_size), shp
+        if x.ndim not in (2, 3) or shp[-2:] != (self.active_channels, self.block_size):
+            raise ValueError("input shape %r, expected [n_blocks][%d][%d]" % (shp, self.active_channels, self.block_size))
         if out is None:
             out = np.empty(shp, np.float32)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == shp and out.flags.c_contiguous and out.flags.writeable):
+            raise ValueError("out must be a writable C-contiguous float32 array of shape %r" % (shp,))      # its raw pointer goes to the library
         _ck(lib().irb_engine_process(self._h, _ptr(x), _ptr(out), nb))
         return out
 
     def process_callback(self, x):
         """Blocks of one plug-in callback, reference order (all forward FFTs first): host [n_blocks][n_channels][B]."""
         x = np.ascontiguousarray(x, np.float32)
-        assert x.ndim == 3 and x.shape[1:] == (self.n_channels, self.block_size), x.shape
+        assert x.ndim == 3 and x.shape[1:] == (self.active_channels, self.block_size), x.shape
         out = np.empty(x.shape, np.float32)
         _ck(lib().irb_engine_process_callback(self._h, _ptr(x), _ptr(out), x.shape[0]))
         return out
@@ -363,7 +430,7 @@ class Engine:
     def submit(self, x, out):
         """Asynchronous multi-block call on pinned host arrays [n_blocks >= 2][n_channels][B]; pair with wait()."""
         assert x.dtype == np.float32 and out.dtype == np.float32 and x.flags.c_contiguous and out.flags.c_contiguous and x.shape == out.shape
-        assert x.ndim == 3 and x.shape[1:] == (self.n_channels, self.block_size), x.shape
+        assert x.ndim == 3 and x.shape[1:] == (self.active_channels, self.block_size), x.shape
         _ck(lib().irb_engine_submit(self._h, _ptr(x), _ptr(out), x.shape[0]))
 
     def wait(self):
@@ -373,7 +440,13 @@ class Engine:
         _ck(lib().irb_engine_process_device(self._h, _vp(int(in_ptr)), _vp(int(out_ptr)), int(n_blocks)))
 
     def mac_only_device(self, acc_ptr):
-        _ck(lib().irb_engine_mac_only_device(self._h, _vp(int(acc_ptr))))
+        """bench-only (irb_b200_bench.h): the bare FDL multiply-accumulate into a device buffer"""
+        _ck(lib().irbx_engine_mac_only_device(self._h, _vp(int(acc_ptr))))
+
+    def set_active_channels(self, n_active):
+        """Only channels [0, n_active) take part in the following block steps; I/O arrays are then [n_blocks][n_active][B]."""
+        _ck(lib().irb_engine_set_active_channels(self._h, int(n_active)))
+        self.active_channels = int(n_active)
 
     def set_timing(self, enable=True):
         _ck(lib().irb_engine_set_timing(self._h, int(bool(enable))))
@@ -479,6 +552,8 @@ class Group:
         assert x.shape[-2:] == (self.n_channels, self.block_size), x.shape
         if out is None:
             out = np.empty(x.shape, np.float32)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == x.shape and out.flags.c_contiguous and out.flags.writeable):
+            raise ValueError("out must be a writable C-contiguous float32 array of shape %r" % (x.shape,))
         _ck(lib().irb_group_process(self._h, _ptr(x), _ptr(out), nb))
         return out
 

@@ -8,9 +8,9 @@ import numpy as np
 import pytest
 
 
-def _declared_symbols(header):
+def _declared_symbols(header, prefix="irb_"):
     txt = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
-    return sorted(set(re.findall(r"\b(irb_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_symbols_are_all_exported(eng):
@@ -21,6 +21,24 @@ def test_header_symbols_are_all_exported(eng):
     assert not missing, missing
     # and the python binding covers the same surface
     assert sorted(eng._SIGS) == names
+
+
+def test_measurement_aids_live_outside_the_product_abi(eng):
+    """include/irb_b200.h carries no bandwidth probe, no tuning switch and no bare-MAC hook; those are irbx_* entry points of
+    include/irb_b200_bench.h (a translation unit of their own), and no library source reads the environment."""
+    prod = open(eng.HEADER_PATH).read()
+    assert "probe" not in prod.lower() and "irbx_" not in prod and "getenv" not in prod and "mac_only" not in prod
+    names = _declared_symbols(eng.BENCH_HEADER_PATH, "irbx_")
+    L = ctypes.CDLL(eng.LIB_PATH)
+    assert names and not [n for n in names if not hasattr(L, n)]
+    assert sorted(eng._BENCH_SIGS) == names
+    csrc = os.path.join(os.path.dirname(eng.LIB_PATH), "csrc")
+    for f in os.listdir(csrc):
+        assert "getenv" not in open(os.path.join(csrc, f)).read(), f
+    # the knobs are reachable by name only; unknown names are rejected
+    assert eng.get_tuning("mac_persistent") in (0, 1)
+    with pytest.raises(eng.IrbError):
+        eng.set_tuning("no_such_knob", 1)
 
 
 def test_library_is_built_for_sm_100a(eng):
@@ -54,6 +72,21 @@ def test_headline_kernel_streams_fdl_and_ir_through_tma(eng):
     assert not re.search(r"LDG\.E\.[A-Z0-9.]*(128|256)", sass)
     assert "FENCE.VIEW.ASYNC" in sass                                   # generic -> async proxy hand-over of stage 0's memory
     assert re.search(r"@!?P\d SYNCS\.ARRIVE", sass) and "LDS.128" in sass
+
+
+def test_persistent_block_step_kernel_sass(eng):
+    """SASS of k_mac_p<512> (shared IR) and k_mac_p<1024, PERROW> (per-stream IRs), the kernels behind the headline and the
+    configs[3] numbers: FDL slots and IR partitions arrive by bulk TMA copies only (no 16- or 32-byte global load), units come
+    from a global atomic counter, the ring stage is released behind a generic->async proxy fence by one predicated arrive,
+    the inner loop reads shared memory with LDS.128, and there is no tensor-core instruction."""
+    import subprocess
+    for fun in ("_ZN3irb7k_mac_pILi512ELb0EEEvNS_7MacArgsE", "_ZN3irb7k_mac_pILi1024ELb1EEEvNS_7MacArgsE"):
+        sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", "-fun", fun, eng.LIB_PATH], capture_output=True, text=True).stdout
+        assert sass.count("UBLKCP") >= 3 and re.search(r"UBLKCP[^;]*desc\[", sass), fun
+        assert not re.search(r"LDG\.E\.[A-Z0-9.]*(128|256)", sass), fun
+        assert "ATOMG" in sass and "FENCE.VIEW.ASYNC" in sass and "LDS.128" in sass, fun
+        assert re.search(r"@!?P\d SYNCS\.ARRIVE", sass), fun
+        assert "HMMA" not in sass and "UTCHMMA" not in sass, fun
 
 
 def test_argument_validation_without_a_device(eng):
