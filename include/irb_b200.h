@@ -176,6 +176,10 @@ int irb_deconvolve(const float* num, int len_num, const float* den, int len_den,
                    float* out);
 int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase,
                          int include_amplitude, float* out);
+/* _batch with DEVICE-resident captures nums_dev[batch][len_num] and results out_dev[batch][N] (den: host or device memory):
+ * the batched capture when the recordings already live in HBM.  No staging copies for large plain divisions. */
+int irb_deconvolve_batch_device(const float* nums_dev, int batch, int len_num, const float* den, int len_den, double sample_rate, int smoothing,
+                                int include_phase, int include_amplitude, float* out_dev);
 /* fp::ir::invertFilter (fp/ir.hpp:20, fp/ir.cpp:13-18); out[nextPowerOfTwo(len)] */
 int irb_invert_filter(const float* x, int len, int sample_rate, float* out);
 /* fp::convolution::averagingFilter (fp/convolution.hpp:44, fp/convolution.cpp:406-546), in place on an interleaved

@@ -332,6 +332,18 @@ struct irb_engine {
     const float2* W = nullptr;
     DevBuf fdl, H, ov, head, ir_of_chan, nparts, io_in[2], io_out[2], taps;
     DevBuf work;                       // k_mac_p: {next unit, finished CTAs}, cleared by the kernel itself
+    int h_reps = 1;                    // identical copies of the IR spectra H (MacArgs::h_reps): [rep][ir][partition][M]
+    long long h_rep_stride() const { return (long long) n_irs * ring * M; }
+    // clear / replicate the spectra of one IR across the copies (copy 0 is the one every writer fills)
+    int ir_clear_all(int ir, cudaStream_t st) {
+        for (int r = 0; r < h_reps; ++r) CK(cudaMemsetAsync(H.as<float2>() + r * h_rep_stride() + (size_t) ir * ring * M, 0, sizeof(float2) * (size_t) M * ring, st));
+        return 0;
+    }
+    int ir_replicate(int ir, cudaStream_t st) {
+        const float2* src = H.as<float2>() + (size_t) ir * ring * M;
+        for (int r = 1; r < h_reps; ++r) CK(cudaMemcpyAsync(H.as<float2>() + r * h_rep_stride() + (size_t) ir * ring * M, src, sizeof(float2) * (size_t) M * ring, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
     std::vector<int> h_ir_of_chan, h_nparts;
     bool binding_dirty = true;
     bool per_row_ir = false;           // some kernel tile mixes IRs: every slot stages its own IR partitions (k_mac_slots)
@@ -441,6 +453,7 @@ void fill_mac_args(irb_engine* e, irb::MacArgs& m, int c0, int cn) {
     m.fdl_group = e->fdl_group; m.fdl_slot_stride = (long long) e->fdl_group * e->M;
     m.head = e->head.as<int>() + c0; m.ring = e->ring; m.blocks_per_chan = 1; m.n_rows = cn;
     m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
+    m.h_reps = e->h_reps; m.h_rep_stride = e->h_rep_stride(); m.stagger_ns = irbh::g_tuning.stagger_ns;
     m.ir_of_chan = e->ir_of_chan.as<int>() + c0; m.nparts = e->nparts.as<int>(); m.W = e->W;
     m.B = e->B; m.split_in = e->split_in;
     mac_policy(m);
@@ -474,6 +487,7 @@ int engine_launch_fwd(irb_engine* e, const float* in_dev, bool audio, bool refre
     // one IR partition of every staged IR is re-transformed per block, in the same launch
     f.n_rr = refresh ? (int) e->h_rr_list.size() : 0; f.rr_list = e->rr_list.as<int>(); f.rr_taps = e->rr_ptrs.as<const float*>();
     f.rr_pos = e->rr_pos.as<int>(); f.nparts = e->nparts.as<int>(); f.H = e->H.as<float2>(); f.ir_stride = (long long) e->ring * e->M;
+    f.h_reps = e->h_reps; f.h_rep_stride = e->h_rep_stride();
     if (f.n_rows == 0 && f.n_rr == 0) return 0;
     int rc = launch_fwd(e->M, f, e->stream);
     if (rc) return rc;
@@ -556,7 +570,13 @@ int irb_engine_create(irb_engine** out, int device, int block_size, int max_part
     if (rc) { delete e; return rc; }
     const size_t spec = sizeof(float2) * (size_t) e->M;
     e->fdl_group = irbh::g_tuning.fdl_plain ? 1 : tile_rows(e->M);     // A/B: [chan][slot][M] instead of the tile-interleaved layout
-    const size_t b_fdl = e->fdl_bytes(), b_H = spec * e->ring * n_irs, b_io = sizeof(float) * (size_t) e->B * n_channels;
+    // shared IR spectra in several identical copies (MacArgs::h_reps): as many as fit 24 MB, at most 32; one when the IRs are many
+    {
+        const size_t one = spec * e->ring * n_irs;
+        const int pref = irbh::g_tuning.ir_replicas;
+        e->h_reps = pref > 0 ? std::min(pref, 64) : (int) std::max<size_t>(1, std::min<size_t>(32, (24u << 20) / one));
+    }
+    const size_t b_fdl = e->fdl_bytes(), b_H = spec * e->ring * n_irs * e->h_reps, b_io = sizeof(float) * (size_t) e->B * n_channels;
     if ((rc = e->fdl.alloc(b_fdl, true)) || (rc = e->H.alloc(b_H, true)) || (rc = e->ov.alloc(b_io, true)) ||
         (rc = e->head.alloc(sizeof(int) * n_channels, false)) || (rc = e->ir_of_chan.alloc(sizeof(int) * n_channels, true)) ||
         (rc = e->nparts.alloc(sizeof(int) * n_irs, true)) || (rc = e->io_in[0].alloc(b_io, true)) || (rc = e->io_out[0].alloc(b_io, true)) ||
@@ -604,14 +624,13 @@ int irb_engine_set_stream(irb_engine* e, void* cuda_stream) {
 int irb_engine_reset(irb_engine* e) {
     if (!e) return fail(IRB_ERR_ARG, "engine is null");
     CK(cudaSetDevice(e->device));
-    const size_t spec = sizeof(float2) * (size_t) e->M;
     CK(cudaMemsetAsync(e->fdl.p, 0, e->fdl_bytes(), e->stream));
     CK(cudaMemsetAsync(e->ov.p, 0, sizeof(float) * (size_t) e->B * e->n_chans, e->stream));
     std::vector<int> h(e->n_chans, e->ring - 1);     // first block lands in slot 0
     CK(cudaMemcpyAsync(e->head.p, h.data(), sizeof(int) * e->n_chans, cudaMemcpyHostToDevice, e->stream));
     // staged IRs start over like irFftBufferArray.clearAndResize in prepareToPlay (PluginProcessor.cpp:226): spectra
     // cleared, write position 0; their partitions come back one per block
-    for (int ir : e->h_rr_list) CK(cudaMemsetAsync(e->H.as<float2>() + (size_t) ir * e->ring * e->M, 0, spec * e->ring, e->stream));
+    for (int ir : e->h_rr_list) { int rc = e->ir_clear_all(ir, e->stream); if (rc) return rc; }
     CK(cudaMemsetAsync(e->rr_pos.p, 0, sizeof(int) * e->n_irs, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return 0;
@@ -627,15 +646,15 @@ int irb_engine_set_ir(irb_engine* e, int ir_id, const float* left, const float* 
     float* dr = dl + (size_t) e->B * e->ring;
     CK(cudaMemcpyAsync(dl, left, sizeof(float) * n_taps, cudaMemcpyHostToDevice, e->stream));
     if (right) CK(cudaMemcpyAsync(dr, right, sizeof(float) * n_taps, cudaMemcpyHostToDevice, e->stream));
-    const size_t spec = sizeof(float2) * (size_t) e->M;
     float2* Hd = e->H.as<float2>() + (size_t) ir_id * e->ring * e->M;
-    CK(cudaMemsetAsync(Hd, 0, spec * e->ring, e->stream));
+    int rc = e->ir_clear_all(ir_id, e->stream);
+    if (rc) return rc;
     irb::FwdArgs f{};
     f.src = dl; f.src2 = right ? dr : nullptr; f.src_chan_stride = 0; f.L = n_taps; f.B = e->B;
     f.blocks_per_chan = P; f.n_rows = P; f.dst = Hd; f.dst_chan_stride = 0; f.head = nullptr; f.ring = e->ring; f.W = e->W;
-    int rc = launch_fwd(e->M, f, e->stream);
-    if (rc) return rc;
+    if ((rc = launch_fwd(e->M, f, e->stream))) return rc;
     e->launches += 1;
+    if ((rc = e->ir_replicate(ir_id, e->stream))) return rc;
     if (e->rr_buf[ir_id]) {            // a staged (round-robin) IR: the refresh must keep producing these taps
         float* rb = e->rr_buf[ir_id]->as<float>();
         CK(cudaMemsetAsync(rb, 0, sizeof(float) * (size_t) e->B * e->ring, e->stream));
@@ -691,7 +710,7 @@ int irb_engine_stage_ir(irb_engine* e, int ir_id, const float* left, const float
     }
     if (P != e->h_nparts[ir_id]) {
         if (e->h_nparts[ir_id] == 0)               // nothing was ever loaded for this IR: its partitions fade in from cleared spectra
-            CK(cudaMemsetAsync(e->H.as<float2>() + (size_t) ir_id * e->ring * e->M, 0, sizeof(float2) * (size_t) e->M * e->ring, e->stream));
+            { int rc2 = e->ir_clear_all(ir_id, e->stream); if (rc2) return rc2; }
         CK(cudaMemsetAsync(e->rr_pos.as<int>() + ir_id, 0, sizeof(int), e->stream));
         e->h_nparts[ir_id] = P;
         CK(cudaMemcpyAsync(e->nparts.as<int>() + ir_id, &e->h_nparts[ir_id], sizeof(int), cudaMemcpyHostToDevice, e->stream));

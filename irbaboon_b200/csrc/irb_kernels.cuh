@@ -157,14 +157,16 @@ struct FwdArgs {
     const int* nparts;
     float2* H;
     long long ir_stride;       // float2 units
+    int h_reps;                // refresh rows write every copy of the IR spectra (MacArgs::h_reps)
+    long long h_rep_stride;
 };
 
 struct FwdRow {                // what one row of k_fwd reads and writes
-    const float* p; const float* q; int len; float2* d; bool live;
+    const float* p; const float* q; int len; float2* d; bool live; int reps;
 };
 template <int ROWS, int M>
 __device__ __forceinline__ FwdRow fwd_row(const FwdArgs& a, int main_tiles, int tile, int r) {
-    FwdRow w{nullptr, nullptr, 0, nullptr, false};
+    FwdRow w{nullptr, nullptr, 0, nullptr, false, 1};
     if (tile < main_tiles) {
         const int row = tile * ROWS + r;
         if (row >= a.n_rows) return w;
@@ -185,6 +187,7 @@ __device__ __forceinline__ FwdRow fwd_row(const FwdArgs& a, int main_tiles, int 
         w.len = a.B;
         w.p = a.rr_taps[ir] + (long long) p * a.B;
         w.d = a.H + ir * a.ir_stride + (long long) p * M;
+        w.reps = a.h_reps > 1 ? a.h_reps : 1;
     }
     w.live = true;
     return w;
@@ -236,7 +239,8 @@ __global__ void __launch_bounds__(kThreads) k_fwd(const FwdArgs a) {
                 const int k = 2 * (c0 + vv * T::TPR);
                 const float2 x0 = real_split(z[k], z[(M - k) & (M - 1)], root<false>(a.W, k), k);
                 const float2 x1 = real_split(z[k + 1], z[M - k - 1], root<false>(a.W, k + 1), k + 1);
-                *reinterpret_cast<float4*>(w.d + k) = make_float4(x0.x, x0.y, x1.x, x1.y);
+                for (int rep = 0; rep < w.reps; ++rep)
+                    *reinterpret_cast<float4*>(w.d + rep * a.h_rep_stride + k) = make_float4(x0.x, x0.y, x1.x, x1.y);
             }
         }
     }
@@ -303,7 +307,17 @@ struct MacArgs {
     // the launch's units in fetch order: unit_n[l] units of max(1, ROWS >> l) rows each, l = 0 .. 3
     int* work;
     int unit_n[4];
+    // Shared IRs are kept in h_reps identical copies h_rep_stride float2 apart; CTA b streams copy b % h_reps.  CTAs of one
+    // launch move through the partitions in lockstep, so without the copies every CTA would ask the same few L2 lines for
+    // the same 4 KB partition at the same moment.
+    int h_reps;
+    long long h_rep_stride;
+    int stagger_ns;            // k_mac_p: CTA starts are spread over this many nanoseconds
 };
+// the copy of the shared IR spectra this CTA streams
+__device__ __forceinline__ const float2* ir_replica(const MacArgs& a) {
+    return a.h_reps > 1 ? a.H + (long long) (blockIdx.x % (unsigned) a.h_reps) * a.h_rep_stride : a.H;
+}
 
 // Time-domain epilogue of a tile whose accumulated packed spectra sit in shared memory, row r at tile + r*M
 // (r < rows_in_tile): packed merge -> inverse M-point FFT -> x 1/N -> overlap-add -> output block
@@ -407,7 +421,7 @@ __global__ void __launch_bounds__(kThreads + 32, U == 1 ? 3 : 2) k_mac(const Mac
     if (tid >= kThreads) {
         // ===== TMA producer warp: stream the IR partition spectra through the ring =====
         if (tid == kThreads) {
-            const float2* hsrc = a.H + ir * a.ir_stride;
+            const float2* hsrc = ir_replica(a) + ir * a.ir_stride;
             for (int g = 0; g < ngroups; ++g) {
                 const int st = g % kStages;
                 if (g >= kStages) mbar_wait_relaxed(&sm.empty[st], ((g / kStages) - 1) & 1, a.producer_sleep_ns);
@@ -661,7 +675,7 @@ __global__ void __launch_bounds__(kThreads + 32, M <= 1024 ? 3 : 2) k_mac_tma(co
     if (tid >= kThreads) {
         // ===== TMA producer =====
         if (tid == kThreads) {
-            const float2* hsrc = a.H + ir * a.ir_stride;
+            const float2* hsrc = ir_replica(a) + ir * a.ir_stride;
             const long long sstride = fdl_slot_stride<M>(a);
             int nlive = 0;
             bool uni = a.fdl_group == T::ROWS;

@@ -70,6 +70,15 @@ __global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
             const long long sstride = fdl_slot_stride<M>(a);
             const uint32_t hb = M * sizeof(float2);
             const uint64_t pol = l2_policy_evict_first();
+            const float2* Hsh = ir_replica(a);            // this CTA's copy of the shared IR spectra
+            if (a.stagger_ns > 0) {
+                // CTAs of a launch run in lockstep (equal work, fair shares of the memory system): spreading their starts
+                // spreads where in the partition sequence they are, for the whole launch
+                unsigned long long t0, t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                const unsigned long long wait = (unsigned long long) a.stagger_ns * (blockIdx.x % 64u) / 64u;
+                do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < wait);
+            }
             int st = 0;
             unsigned round = 0;                           // laps of the ring completed by the producer
             for (unsigned ui = 0;; ++ui) {
@@ -119,7 +128,7 @@ __global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
                         for (int r = 0; r < T::ROWS; ++r) if (g < npr[r]) bytes += hb + (g > 0 ? hb : 0u);
                     }
                     mbar_expect_tx(&sm.full[st], bytes);
-                    if (!PERROW) tma_bulk_g2s(S.h, a.H + ir0 * a.ir_stride + (long long) g * M, hb, &sm.full[st]);
+                    if (!PERROW) tma_bulk_g2s(S.h, Hsh + ir0 * a.ir_stride + (long long) g * M, hb, &sm.full[st]);
                     else {
 #pragma unroll
                         for (int r = 0; r < T::ROWS; ++r)

@@ -296,8 +296,8 @@ int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h
 // out: [batch][N], N = nextPowerOfTwo(max(len_num, len_den))
 // The batch runs in sub-batches through a three-stage pipeline (upload i+1 | kernels i | download i-1) over
 // double-buffered device memory; a sub-batch is small enough for its intermediate spectra to stay in the L2.
-int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase,
-                         int include_amplitude, float* out) {
+static int deconvolve_batch_staged(const float* nums, int batch, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase,
+                                   int include_amplitude, float* out) {
     if (!nums || !den || !out) return fail(IRB_ERR_ARG, "null argument");
     if (batch < 1 || len_num < 1 || len_den < 1) return fail(IRB_ERR_ARG, "empty input");
     int N = 0, rc;
@@ -344,7 +344,7 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
         return rc;
     irbh::set_last_compute_ms(0.0);
     // the denominator's spectrum, once
-    CK(cudaMemcpyAsync(dd.p, den, sizeof(float) * len_den, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dd.p, den, sizeof(float) * len_den, cudaMemcpyDefault, st));
     if (fused) {
         if ((rc = plan.cols_fwd(dd.p, lde / 2, len_den, Zd.as<float2>(), 1, st)) || (rc = plan.rows_to_split_spectrum(Zd.as<float2>(), Bd.as<float2>(), 1, true, st))) return rc;
     } else {
@@ -370,7 +370,7 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
     // upload of a sub-batch into q.dn (after the kernels that last read it), and the compute stream waiting for it
     auto upload = [&](Slot& q, int b0, int nb) -> int {
         if (q.dn_busy) CK(cudaStreamWaitEvent(sg_in.s, q.ev_done, 0));
-        CK(cudaMemcpy2DAsync(q.dn.p, sizeof(float) * lne, nums + (size_t) b0 * len_num, sizeof(float) * len_num, sizeof(float) * len_num, nb, cudaMemcpyHostToDevice, sg_in.s));
+        CK(cudaMemcpy2DAsync(q.dn.p, sizeof(float) * lne, nums + (size_t) b0 * len_num, sizeof(float) * len_num, sizeof(float) * len_num, nb, cudaMemcpyDefault, sg_in.s));
         CK(cudaEventRecord(q.ev_in, sg_in.s));
         CK(cudaStreamWaitEvent(st, q.ev_in, 0));
         return 0;
@@ -386,7 +386,7 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
         CK(cudaEventRecord(q.t1, st));
         CK(cudaEventRecord(q.ev_done, st));
         CK(cudaStreamWaitEvent(sg_out.s, q.ev_done, 0));
-        CK(cudaMemcpyAsync(out + (size_t) b0 * N, res, sizeof(float) * (size_t) N * nb, cudaMemcpyDeviceToHost, sg_out.s));
+        CK(cudaMemcpyAsync(out + (size_t) b0 * N, res, sizeof(float) * (size_t) N * nb, cudaMemcpyDefault, sg_out.s));
         CK(cudaEventRecord(q.ev_out, sg_out.s));
         q.dy_busy = true;
         return 0;
@@ -448,6 +448,69 @@ int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float*
     CK(cudaStreamSynchronize(st));
     for (int i = 0; i < nslots; ++i) if ((rc = collect(slot[i]))) return rc;
     irbh::set_last_compute_ms(total_ms);
+    return 0;
+}
+
+int irb_deconvolve_batch(const float* nums, int batch, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase,
+                         int include_amplitude, float* out) {
+    return deconvolve_batch_staged(nums, batch, len_num, den, len_den, sample_rate, smoothing, include_phase, include_amplitude, out);
+}
+
+// The same with DEVICE-resident captures and results (den: host or device).  Large plain divisions (no smoothing, phase kept, an
+// even capture length) run with no staging at all: every sub-batch's column pass reads the captures where they lie, the
+// inverse column pass writes the impulse responses where they belong, and consecutive sub-batches alternate between compute
+// streams so that one sub-batch's row kernels fill the SMs another one's column pass leaves idle.  Everything else goes
+// through the staged pipeline above with device-to-device copies.  irb_last_compute_ms() is the device time of the whole call.
+int irb_deconvolve_batch_device(const float* nums_dev, int batch, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase,
+                                int include_amplitude, float* out_dev) {
+    if (!nums_dev || !den || !out_dev) return fail(IRB_ERR_ARG, "null argument");
+    if (batch < 1 || len_num < 1 || len_den < 1) return fail(IRB_ERR_ARG, "empty input");
+    int N = 0, rc;
+    if ((rc = fft_size_for(len_num > len_den ? len_num : len_den, &N))) return rc;
+    const int M = N / 2, dev = irbh::current_device();
+    CK(cudaSetDevice(dev));
+    Plan plan;
+    if ((rc = plan.init(dev, M))) return rc;
+    if (!(plan.big() && !smoothing && include_phase && len_num % 2 == 0))
+        return deconvolve_batch_staged(nums_dev, batch, len_num, den, len_den, sample_rate, smoothing, include_phase, include_amplitude, out_dev);
+    constexpr int kStreams = 3;
+    const int sub_pref = irbh::g_tuning.deconv_sub;
+    int sub = sub_pref > 0 ? sub_pref : (int) std::max<long long>(1, (32LL << 20) / ((long long) sizeof(float2) * M));      // about 32 MB of spectra per sub-batch
+    sub = std::min(sub, batch);
+    const int ncs = std::max(1, std::min(std::min(kStreams, irbh::g_tuning.deconv_streams > 0 ? irbh::g_tuning.deconv_streams : 2), (batch + sub - 1) / sub));
+    const long long lde = (len_den + 1) & ~1LL;
+    DevBuf Zn[kStreams], dd, Zd, Bd;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, ev_den = nullptr, ev_end[kStreams] = {nullptr, nullptr, nullptr};
+    struct EvGuard { cudaEvent_t *a, *b, *c, *d; ~EvGuard() { for (cudaEvent_t* e : {a, b, c}) if (*e) cudaEventDestroy(*e); for (int i = 0; i < kStreams; ++i) if (d[i]) cudaEventDestroy(d[i]); } } evg{&e0, &e1, &ev_den, ev_end};
+    irbh::StreamGuard cs[kStreams];                      // after the buffers and events: drained first on an early return
+    for (int i = 0; i < ncs; ++i) {
+        if ((rc = cs[i].create()) || (rc = Zn[i].alloc(sizeof(float2) * (size_t) M * sub, false))) return rc;
+        CK(cudaEventCreateWithFlags(&ev_end[i], cudaEventDisableTiming));
+    }
+    if ((rc = dd.alloc(sizeof(float) * lde, true)) || (rc = Zd.alloc(sizeof(float2) * (size_t) M, false)) || (rc = Bd.alloc(sizeof(float2) * (size_t) M, false))) return rc;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreateWithFlags(&ev_den, cudaEventDisableTiming));
+    cudaStream_t st = cs[0].s;
+    CK(cudaMemcpyAsync(dd.p, den, sizeof(float) * len_den, cudaMemcpyDefault, st));
+    CK(cudaEventRecord(e0, st));
+    // the denominator's reciprocal spectrum in row layout, once
+    if ((rc = plan.cols_fwd(dd.p, lde / 2, len_den, Zd.as<float2>(), 1, st)) || (rc = plan.rows_to_split_spectrum(Zd.as<float2>(), Bd.as<float2>(), 1, true, st))) return rc;
+    CK(cudaEventRecord(ev_den, st));
+    for (int i = 1; i < ncs; ++i) CK(cudaStreamWaitEvent(cs[i].s, ev_den, 0));
+    int it = 0;
+    for (int b0 = 0; b0 < batch; b0 += sub, ++it) {
+        const int k = it % ncs, nb = std::min(sub, batch - b0);
+        cudaStream_t s = cs[k].s;
+        if ((rc = plan.cols_fwd(nums_dev + (size_t) b0 * len_num, len_num / 2, len_num, Zn[k].as<float2>(), nb, s)) ||
+            (rc = plan.rows_binop(Zn[k].as<float2>(), Bd.as<float2>(), 0, nb, s)) ||
+            (rc = plan.cols_inv(Zn[k].as<float2>(), reinterpret_cast<float2*>(out_dev + (size_t) b0 * N), M, nb, 1.0f / (float) N, s)))
+            return rc;
+    }
+    for (int i = 1; i < ncs; ++i) { CK(cudaEventRecord(ev_end[i], cs[i].s)); CK(cudaStreamWaitEvent(st, ev_end[i], 0)); }
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    irbh::set_last_compute_ms((double) ms);
     return 0;
 }
 

@@ -44,10 +44,17 @@ template <int L, bool INV>
 static __global__ void __launch_bounds__(kThreads, L >= 1024 ? 2 : 4) k_line_fft(const LineArgs a) {
     using T = LineTile<L>;
     extern __shared__ __align__(16) float2 s_lines[];
+    __shared__ float2 s_step[T::C][kPts];                 // inter-pass twiddle: root(line * TPF * j), the same for every thread of a line
     const int tid = threadIdx.x;
     const int line0 = blockIdx.x * T::C;
     const long long ib = (long long) blockIdx.y * a.in_batch_stride, ob = (long long) blockIdx.y * a.out_batch_stride;
     const bool in_contig = a.in_elem_stride == 1, out_contig = a.out_elem_stride == 1;
+    if (a.tw_M > 0) {
+        for (int i = tid; i < T::C * kPts; i += kThreads) {
+            const int c = i / kPts, j = i % kPts;
+            s_step[c][j] = root_big(a.tw_hi, a.tw_lo, ((long long) (line0 + c) * T::TPF * j) & (a.tw_M - 1));
+        }
+    }
 
     // all of a thread's loads are issued before the first shared-memory store: PER x 8 bytes in flight per thread
     constexpr int PER = T::C * L / kThreads;
@@ -96,8 +103,8 @@ static __global__ void __launch_bounds__(kThreads, L >= 1024 ? 2 : 4) k_line_fft
                 const int k = t + j * T::TPF;
                 if (a.tw_M > 0) {
                     // root(line*k), k = t + j*TPF, as root(line*t) * root(line*TPF*j): the second factor is the same for
-                    // the whole line, so a warp reads one table line instead of 32 scattered ones
-                    const float2 w = cmul(tw_base, root_big(a.tw_hi, a.tw_lo, ((long long) line * T::TPF * j) & (a.tw_M - 1)));
+                    // the whole line and was looked up once per CTA (a broadcast read of shared memory here)
+                    const float2 w = cmul(tw_base, s_step[c][j]);
                     v[j] = cmul(v[j], INV ? cconj(w) : w);
                 }
                 srow[k] = v[j];              // each thread rewrites exactly the elements it gathered last
@@ -220,6 +227,20 @@ struct PairArgs {
     const float2 *Nhi, *Nlo;     // two-level table of the 2M-th roots (split / merge)
     const float2 *Mhi, *Mlo;     // two-level table of the M-th roots (inverse inter-pass twiddle)
 };
+// exp(-2 pi i j / 16), j = 0 .. 7 (correctly rounded)
+__device__ __forceinline__ float2 root16(int j) {
+    constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    switch (j) {
+        case 0: return make_float2(1.f, 0.f);
+        case 1: return make_float2(c1, -s1);
+        case 2: return make_float2(h, -h);
+        case 3: return make_float2(s1, -c1);
+        case 4: return make_float2(0.f, -1.f);
+        case 5: return make_float2(-s1, -c1);
+        case 6: return make_float2(-h, -h);
+        default: return make_float2(-c1, -s1);
+    }
+}
 // Z'[k] of the bin pair (k, M-k): split both bins of the real signal's spectrum, multiply by B, merge back.
 // Division is multiplication by the reciprocal spectrum that k_split_rows prepares once for the whole batch.
 __device__ __forceinline__ float2 pair_op(float2 zk, float2 zm, float2 bk, float2 bm, float2 w) {
@@ -235,6 +256,7 @@ template <int L>
 static __global__ void __launch_bounds__(kThreads, 4) k_rowpair(const PairArgs a) {
     using T = PairTile<L>;
     extern __shared__ __align__(16) float2 s_lines[];
+    __shared__ float2 s_step[2 * T::NP][kPts];            // inverse inter-pass twiddle steps root_M(row * TPF * j), one set per line
     const int tid = threadIdx.x, M1 = a.M1;
     const long long M = (long long) M1 * L;
     float2* Z = a.Z + blockIdx.y * a.z_batch_stride;
@@ -252,6 +274,10 @@ static __global__ void __launch_bounds__(kThreads, 4) k_rowpair(const PairArgs a
     float2 v[kPts];
 #pragma unroll
     for (int j = 0; j < kPts; ++j) v[j] = live ? zrow[t + j * T::TPF] : make_float2(0.f, 0.f);
+    if (t < kPts && line < 2 * T::NP) s_step[line][t] = root_big(a.Mhi, a.Mlo, ((long long) row * T::TPF * t) & (M - 1));
+    // split / merge root of this thread's bins k = row + M1*(t + j*TPF): exp(-2 pi i k / 2M) = root_2M(row + M1*t) * exp(-2 pi i j / 16)
+    // (M1 * TPF / 2M = 1/16), one table read and the sixteenth roots of unity as constants
+    const float2 n_base = root_big(a.Nhi, a.Nlo, row + (long long) M1 * t);
     fft_run<L, false>(v, t, srow, a.W);                                   // forward row transform: v[j] = Z[row + M1*(t + j*TPF)]
     bar_compute();
 #pragma unroll
@@ -270,7 +296,7 @@ static __global__ void __launch_bounds__(kThreads, 4) k_rowpair(const PairArgs a
                 const float2 q0 = bin_mul(a0, bb0), qM = bin_mul(aM, bbM);
                 v[j] = make_float2(q0.x + qM.x, q0.x - qM.x);
             } else {
-                v[j] = pair_op(v[j], spart[pk2], __ldg(Bq + (long long) row * L + k2), __ldg(Bq + (long long) prow * L + pk2), root_big(a.Nhi, a.Nlo, k));
+                v[j] = pair_op(v[j], spart[pk2], __ldg(Bq + (long long) row * L + k2), __ldg(Bq + (long long) prow * L + pk2), cmul(n_base, root16(j)));
             }
         }
     }
@@ -280,7 +306,7 @@ static __global__ void __launch_bounds__(kThreads, 4) k_rowpair(const PairArgs a
         const float2 tw_base = root_big(a.Mhi, a.Mlo, ((long long) row * t) & (M - 1));
 #pragma unroll
         for (int j = 0; j < kPts; ++j) {
-            const float2 w = cmul(tw_base, root_big(a.Mhi, a.Mlo, ((long long) row * T::TPF * j) & (M - 1)));
+            const float2 w = cmul(tw_base, s_step[line][j]);             // written before the first barrier of the forward transform
             zrow[t + j * T::TPF] = cmul(v[j], cconj(w));
         }
     }

@@ -15,9 +15,12 @@ struct Tuning {
     int producer_sleep_ns = 200; // the TMA producer sleeps this long between polls of a busy stage (0: spin)
     int no_graph = 0;            // single small blocks: plain launches instead of the captured CUDA graph
     int deconv_sub = 0;          // captures per sub-batch of irb_deconvolve_batch (0: about 48 MB of spectra)
+    int deconv_streams = 0;      // irb_deconvolve_batch_device: compute streams the sub-batches alternate between (0: two)
     int release_fence = 1;       // fence.proxy.async between the last ld.shared of a ring stage and its release
     int release_dep = 1;         // the release also carries a data dependency on the values read (0 + 0 = the unguarded round-1 form: sanitizer experiments only)
     int persistent_ctas = 0;     // k_mac_p: CTAs per SM (0: the kernel's own choice)
+    int ir_replicas = 0;         // copies of the shared IR spectra an engine created from now on keeps (0: as many as fit 24 MB, at most 32)
+    int stagger_ns = 0;          // k_mac_p: CTA starts spread over this many nanoseconds
     int unit_narrowing = 1;      // k_mac_p: the last partial wave of a launch runs on tiles of fewer rows
 };
 extern Tuning g_tuning;

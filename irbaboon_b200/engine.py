@@ -80,6 +80,7 @@ _SIGS = {
     "irb_convolve_nonperiodic": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_deconvolve": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_deconvolve_batch": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    "irb_deconvolve_batch_device": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_invert_filter": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     "irb_averaging_filter": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "irb_fft_transform": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
@@ -281,6 +282,13 @@ def deconvolve_batch(nums, den, sample_rate=48000.0, smoothing=False, include_ph
     _ck(lib().irb_deconvolve_batch(_ptr(nums), nums.shape[0], nums.shape[1], _ptr(den), len(den), float(sample_rate), int(smoothing), int(include_phase),
                                    int(include_amplitude), _ptr(out)))
     return out
+
+
+def deconvolve_batch_device(nums_ptr, batch, len_num, den, out_ptr, sample_rate=48000.0, smoothing=False, include_phase=True, include_amplitude=True):
+    """irb_deconvolve_batch_device: captures and results are raw DEVICE pointers ([batch][len_num] / [batch][N] float32)."""
+    den = np.ascontiguousarray(den, np.float32).reshape(-1)
+    _ck(lib().irb_deconvolve_batch_device(_vp(int(nums_ptr)), int(batch), int(len_num), _ptr(den), len(den), float(sample_rate), int(smoothing), int(include_phase),
+                                          int(include_amplitude), _vp(int(out_ptr))))
 
 
 def invert_filter(x, sample_rate=48000):

@@ -566,11 +566,24 @@ bool writeWav(const std::string& path, const AudioBuffer<float>& buffer, int sam
     put32(out, (uint32_t) (sampleRate * ch * bytes)); put16(out, (uint32_t) (ch * bytes)); put16(out, (uint32_t) bitsPerSample);
     out.insert(out.end(), {'d', 'a', 't', 'a'});
     put32(out, dataBytes);
+    // Sample quantisation = what juce::AudioFormatWriter does for an integer WAV (JUCE 6.0.1, the version the reference pins;
+    // JUCE is not vendored by the reference, so this restates two of its functions):
+    //   1. AudioFormatWriter::convertFloatsToInts (juce_audio_formats/format/juce_AudioFormatWriter.cpp): every float goes to a
+    //      LEFT-JUSTIFIED 32-bit integer in double arithmetic:  samp <= -1.0 -> INT_MIN;  samp >= 1.0 -> INT_MAX;
+    //      otherwise roundToInt (INT_MAX * samp), round-half-to-even (a NaN fails both comparisons and its conversion is
+    //      undefined there; here it becomes 0);
+    //   2. WavAudioFormatWriter::write converts Int32 -> Int24 / Int16 with AudioData::Int24::setAsInt32LE =
+    //      littleEndian24BitToChars (value >> 8) and Int16::setAsInt32LE = (value >> 16): an ARITHMETIC shift, i.e. the top
+    //      bits of the 32-bit value, rounding toward minus infinity (no dither).
+    // So +1.0 -> 0x7fffff, -1.0 -> -0x800000, and anything of magnitude below 2^-32 (every denormal) -> 0.
     for (int i = 0; i < n; ++i)
         for (int c = 0; c < ch; ++c) {
-            double v = (double) buffer.getSample(c, i);
-            v = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);
-            const int32_t q = (int32_t) std::lrint(v * 2147483647.0);           // 32-bit fixed point, then the top `bits` bits
+            const double samp = (double) buffer.getSample(c, i);
+            int32_t q;
+            if (samp <= -1.0) q = INT32_MIN;
+            else if (samp >= 1.0) q = INT32_MAX;
+            else if (samp != samp) q = 0;
+            else q = (int32_t) std::lrint(2147483647.0 * samp);
             const uint32_t u = (uint32_t) (q >> (32 - bitsPerSample));
             for (int b = 0; b < bytes; ++b) out.push_back((u >> (8 * b)) & 0xff);
         }

@@ -59,6 +59,44 @@ def test_wav_writer_is_standard_pcm(fac, tmp_path, bits, ch, n):
     assert np.abs(back - np.clip(x, -1, 1)).max() <= 2.0 ** -(bits - 1)
 
 
+def _juce_quantise(x32, bits):
+    """The JUCE 6 integer-WAV sample rule restated in plain Python (no numpy arithmetic, no C++): double product, round half to
+    even, saturation at the 32-bit limits, then an arithmetic right shift to the file's word length
+    (AudioFormatWriter::convertFloatsToInts, AudioData::Int24::setAsInt32LE / Int16::setAsInt32LE)."""
+    samp = float(x32)                       # the float32 value, exactly, as a Python (IEEE double) float
+    if samp <= -1.0:
+        q = -(1 << 31)
+    elif samp >= 1.0:
+        q = (1 << 31) - 1
+    else:
+        q = round(2147483647.0 * samp)      # Python's round(): half to even, on the same IEEE double product
+    return q >> (32 - bits)                 # Python's >> on a negative int is arithmetic (floor)
+
+
+@pytest.mark.parametrize("bits", [16, 24])
+def test_wav_quantisation_matches_the_juce_rule_on_edge_vectors(fac, tmp_path, bits):
+    """Fixed vectors, bit for bit: full scale, one ulp inside and outside it, the smallest normal and denormal floats, signed
+    zeros, values on both sides of a quantisation step, and the step's exact half-way points."""
+    f = np.float32
+    one = f(1.0)
+    step = 2.0 ** -(bits - 1)
+    vec = [f(0.0), f(-0.0), one, -one, np.nextafter(one, f(0)), np.nextafter(-one, f(0)), np.nextafter(one, f(2)), np.nextafter(-one, f(-2)), f(1.5), f(-1.5),
+           f(3.4e38), f(-3.4e38), np.finfo(f).tiny, -np.finfo(f).tiny, f(1e-45), f(-1e-45), f(2.0 ** -31), f(-2.0 ** -31), f(2.0 ** -32), f(-2.0 ** -33),
+           f(step), f(-step), f(step / 2), f(-step / 2), np.nextafter(f(step / 2), f(1)), np.nextafter(f(-step / 2), f(-1)), f(1.5 * step), f(-1.5 * step),
+           f(2.5 * step), f(-2.5 * step), f(0.5), f(-0.5), f(0.25) + f(step / 2), f(1.0 / 3.0), f(-2.0 / 3.0), f(0.999), f(-0.999), f(12345 * step), f(-12345 * step - step / 4)]
+    x = np.array(vec, dtype=np.float32).reshape(1, -1)
+    n = x.shape[1]
+    path = str(tmp_path / "edge.wav")
+    assert fac.fac_write_wav(path.encode(), _fp(x), 1, n, 48000, bits) == 0
+    raw = open(path, "rb").read()[44:44 + n * (bits // 8)]
+    got = [int.from_bytes(raw[i * (bits // 8):(i + 1) * (bits // 8)], "little", signed=True) for i in range(n)]
+    want = [_juce_quantise(v, bits) for v in x[0]]
+    assert got == want, [(float(v), g, w) for v, g, w in zip(x[0], got, want) if g != w]
+    top = (1 << (bits - 1)) - 1
+    assert got[2] == top and got[3] == -top - 1 and got[6] == top and got[7] == -top - 1          # +-1.0 and beyond: the extreme codes
+    assert got[0] == 0 and got[1] == 0 and got[12] == 0 and got[14] == 0                           # zeros, FLT_MIN, a positive denormal
+    
+
 def test_wav_reader_takes_float_and_32_bit_files_and_rejects_garbage(fac, tmp_path):
     import struct
     x = synth.white_noise(5, 0, 300).reshape(1, 300)
@@ -139,7 +177,13 @@ def test_capture_to_filter_chain_matches_the_reference_functions(fac, orc, ref):
     assert fac.fac_create_ir_filt(_fp(irs[0]), n, _fp(irs[1]), n, sr, 1, 1, _fp(filt)) == n
     want_f = orc.deconvolve(irs[0], irs[1], sr, True, True, True)                      # same inputs: isolates this step
     e, l2 = parity(filt[None, :], want_f)
-    assert e <= 5e-5 and l2 <= 5e-4, (e, l2)
+    # Dividing one measured IR's spectrum by another's and smoothing the quotient is ill-conditioned (both are noise where the
+    # sweep has no energy): the REFERENCE's own output moves by 1e-4 .. 1e-3 relative L2 when its inputs change by one float32
+    # ulp.  The bound is therefore the reference's response to exactly that perturbation (seeded), not a fixed number.
+    rng = np.random.default_rng(0)
+    pert = [(v * (1 + 1.2e-7 * rng.choice([-1.0, 1.0], n))).astype(np.float32) for v in irs]
+    ce, cl2 = parity(orc.deconvolve(pert[0], pert[1], sr, True, True, True), want_f)
+    assert e <= max(5e-5, 2 * ce) and l2 <= max(5e-4, 2 * cl2), (e, l2, ce, cl2)
     got = np.zeros(2048, np.float32)
     assert fac.fac_chop_and_normalize(_fp(filt), n, 2048, ctypes.c_float(-60.0), 50, _fp(got)) == 2048
     chopped = ref.ir_chop(filt, 2048, -60.0, 50)[0]
