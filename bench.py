@@ -643,6 +643,22 @@ def e2e_leg(args, R, eng, e, S, B, total_streams, period_ms, per_stream_ir, tile
         out["rt_streams_per_gpu"] = rt_S
         out["rt_streams_search"] = trail
         out["rt_streams_note"] = "largest stream count per GPU whose one-block-per-call host round trip (irb_engine_process, copies included) stays under the %.3f ms period with all %d ranks running" % (period_ms, world)
+    # ---- the same continuous feed with the INPUT in write-combined pinned memory (the host only writes it) ----
+    try:
+        hwc = eng.pinned_empty((K2, S, B), write_combined=True)
+        hwc[:] = hin
+        e.process(hwc[:4], hout[:4])
+        R.barrier()
+        t0 = time.perf_counter()
+        for _ in range(REP):
+            e.submit(hwc, hout)
+        e.wait()
+        dtw = R.max((time.perf_counter() - t0) / REP)
+        out["write_combined_input"] = {"value": total_streams * B * K2 / dtw / SR, "ms_per_step": 1e3 * dtw / K2}
+        eng.pinned_free(hwc)
+        del hwc
+    except Exception as ex:
+        out["write_combined_input"] = {"error": str(ex)}
     eng.pinned_free(hin)
     eng.pinned_free(hout)
     del hin, hout
@@ -763,6 +779,8 @@ def run_c5(args, R, eng):
             fs = max(1.0, float(np.abs(want).max()))
             chk["captures"].append(j)
             chk["max_abs_over_full_scale"] = max(chk["max_abs_over_full_scale"], float(np.abs(res[j] - want).max()) / fs)
+            chk["relative_l2"] = max(chk.get("relative_l2", 0.0), float(np.linalg.norm(np.asarray(res[j], np.float64) - want) / np.linalg.norm(want)))
+        chk["note"] = "relative L2 is reported, not gated: dividing by a sweep spectrum that falls to 2e-4 of its peak puts the reference itself 2e-5 from the float64 result (tests/test_gpu_fullsize.py calibrates the bound)"
         chk["ok"] = chk["max_abs_over_full_scale"] <= 1e-5 and same_bits
     except Exception as ex:
         chk["ok"], chk["note"] = same_bits, "reference unavailable: %s" % ex

@@ -44,6 +44,9 @@ int irb_max_block_size(void);                /* largest processBlockSize the blo
 
 /* pinned host buffers for the engine's host-side entry points (plain malloc'ed memory also works, slower) */
 void* irb_host_alloc(size_t bytes);
+/* the same, write-combined: for buffers the host only WRITES, front to back (audio input).  The device's reads then skip the
+ * CPU cache snoop, which matters when several GPUs pull from one host; reading such memory from the CPU is very slow. */
+void* irb_host_alloc_write_combined(size_t bytes);
 void irb_host_free(void* p);
 
 /* ---- streaming engine -----------------------------------------------------------------------------

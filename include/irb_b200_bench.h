@@ -16,7 +16,7 @@ extern "C" {
 #endif
 
 /* Launch-policy knobs (irbaboon_b200/csrc/irb_tuning.hpp) by name: "mac_persistent", "mac_tma", "mac_wide", "mac_u",
- * "fdl_plain", "producer_sleep_ns", "no_graph", "deconv_sub", "deconv_streams", "release_fence", "release_dep", "persistent_ctas", "unit_narrowing", "ir_replicas", "stagger_ns".
+ * "fdl_plain", "producer_sleep_ns", "no_graph", "deconv_sub", "deconv_streams", "release_fence", "release_dep", "persistent_ctas", "unit_narrowing", "ir_replicas", "stagger_ns", "ring_stages".
  * The library itself never reads the environment; the defaults are compiled in.  _get returns the value (or IRB_ERR_ARG). */
 int irbx_set_tuning(const char* name, int value);
 int irbx_get_tuning(const char* name);

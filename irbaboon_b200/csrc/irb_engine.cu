@@ -195,6 +195,11 @@ int launch_mac_p(irb::MacArgs a, int num_sms, cudaStream_t st) {
     CK(cudaGetDevice(&dev));
     if (configured_dev != dev) {
         CK(cudaFuncSetAttribute(irb::k_mac_p<M, PERROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        CK(cudaFuncSetAttribute(irb::k_mac_p<M, PERROW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        // two CTAs per SM is what the kernel is built for (ring depth, register budget): refuse to run silently at half of it
+        int resident = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, irb::k_mac_p<M, PERROW>, irb::kThreads + 32, smem));
+        if (resident < 2) return fail(IRB_ERR_CUDA, "k_mac_p<%d>: only %d CTA per SM fits (registers / shared memory), 2 expected", M, resident);
         configured_dev = dev;
     }
     irb::k_mac_p<M, PERROW><<<grid, irb::kThreads + 32, smem, st>>>(a);
@@ -453,7 +458,7 @@ void fill_mac_args(irb_engine* e, irb::MacArgs& m, int c0, int cn) {
     m.fdl_group = e->fdl_group; m.fdl_slot_stride = (long long) e->fdl_group * e->M;
     m.head = e->head.as<int>() + c0; m.ring = e->ring; m.blocks_per_chan = 1; m.n_rows = cn;
     m.H = e->H.as<float2>(); m.ir_stride = (long long) e->ring * e->M;
-    m.h_reps = e->h_reps; m.h_rep_stride = e->h_rep_stride(); m.stagger_ns = irbh::g_tuning.stagger_ns;
+    m.h_reps = e->h_reps; m.h_rep_stride = e->h_rep_stride(); m.stagger_ns = irbh::g_tuning.stagger_ns; m.ring_stages = irbh::g_tuning.ring_stages;
     m.ir_of_chan = e->ir_of_chan.as<int>() + c0; m.nparts = e->nparts.as<int>(); m.W = e->W;
     m.B = e->B; m.split_in = e->split_in;
     mac_policy(m);
@@ -549,6 +554,11 @@ int irb_max_block_size(void) { return kMaxM; }
 void* irb_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); fail(IRB_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void* irb_host_alloc_write_combined(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocWriteCombined) != cudaSuccess) { cudaGetLastError(); fail(IRB_ERR_CUDA, "cudaHostAlloc(%zu, write-combined) failed", bytes); return nullptr; }
     return p;
 }
 void irb_host_free(void* p) { if (p) cudaFreeHost(p); }

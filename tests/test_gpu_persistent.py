@@ -92,7 +92,7 @@ def test_per_stream_irs_persistent_equals_slot_kernel_and_oracle(eng, orc, B, C,
     y_two, l2, _ = _run(eng, B, ring, C, x, irs, bind=lambda c: (c * 5 + c // 3) % 8, fused=False)      # k_fwd + k_mac_slots
     assert l2 == 2 * nb and np.array_equal(y, y_two)
     y_old, l3, _ = _run(eng, B, ring, C, x, irs, bind=lambda c: (c * 5 + c // 3) % 8, tune=[("mac_persistent", 0)])
-    assert l3 == 2 * nb and np.array_equal(y, y_old)
+    assert l3 == (2 * nb if B < 2048 else nb) and np.array_equal(y, y_old)     # (one-row tiles never mix IRs: the tile kernel, fused)
     for c in (0, 1, 2, 3, C // 2, C - 1):
         hc = irs[(c * 5 + c // 3) % 8]
         want = orc.convolve_periodic(np.ascontiguousarray(x[:, c, :]).reshape(-1), hc, B)[0, :nb * B]
