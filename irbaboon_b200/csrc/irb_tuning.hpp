@@ -19,10 +19,10 @@ struct Tuning {
     int release_fence = 1;       // fence.proxy.async between the last ld.shared of a ring stage and its release
     int release_dep = 1;         // the release also carries a data dependency on the values read (0 + 0 = the unguarded round-1 form: sanitizer experiments only)
     int persistent_ctas = 0;     // k_mac_p: CTAs per SM (0: the kernel's own choice)
-    int ir_replicas = 0;         // copies of the shared IR spectra an engine created from now on keeps (0: as many as fit 24 MB, at most 32)
+    int ir_replicas = 1;         // copies of the shared IR spectra an engine created from now on keeps (0: as many as fit 24 MB, at most 32); measured: no effect
     int ring_stages = 0;         // k_mac_p: ring stages in use (0: all the kernel has; measurement of the in-flight depth)
     int stagger_ns = 0;          // k_mac_p: CTA starts spread over this many nanoseconds
-    int unit_narrowing = 1;      // k_mac_p: the last partial wave of a launch runs on tiles of fewer rows
+    int unit_narrowing = 0;      // k_mac_p: run the last partial wave of a launch on tiles of fewer rows (measured slower: a narrow unit has less in flight)
 };
 extern Tuning g_tuning;
 

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True)
 def _default_tuning(eng):
     yield
-    for k, v in (("mac_persistent", 1), ("unit_narrowing", 1), ("release_fence", 1), ("persistent_ctas", 0), ("mac_tma", 1)):
+    for k, v in (("mac_persistent", 1), ("unit_narrowing", 0), ("release_fence", 1), ("persistent_ctas", 0), ("mac_tma", 1)):
         eng.set_tuning(k, v)
 
 
@@ -40,7 +40,7 @@ def _run(eng, B, ring, C, x, irs, bind=None, fused=True, tune=()):
             return y, e.launches - l0, e.mac_plan()
     finally:
         for k, _ in tune:
-            eng.set_tuning(k, {"mac_persistent": 1, "unit_narrowing": 1, "release_fence": 1, "persistent_ctas": 0, "mac_tma": 1}[k])
+            eng.set_tuning(k, {"mac_persistent": 1, "unit_narrowing": 0, "release_fence": 1, "persistent_ctas": 0, "mac_tma": 1}[k])
 
 
 # stream counts chosen against 2 x 148 resident CTAs so that the last wave runs on half / quarter / single-row units,
@@ -60,7 +60,7 @@ def test_persistent_step_equals_every_other_form_and_the_oracle(eng, orc, B, C, 
     x = _blocks(C, nb, B)
     y, launches, plan = _run(eng, B, P, C, x, [h])
     assert plan == (False, 1, 1) and launches == nb                       # one launch per block step
-    y_plain, _, _ = _run(eng, B, P, C, x, [h], tune=[("unit_narrowing", 0)])
+    y_plain, _, _ = _run(eng, B, P, C, x, [h], tune=[("unit_narrowing", 1)])             # last partial wave on units of fewer rows
     y_tile, _, _ = _run(eng, B, P, C, x, [h], tune=[("mac_persistent", 0)])             # k_mac_tma, one CTA per tile
     y_two, l2, _ = _run(eng, B, P, C, x, [h], fused=False)                               # k_fwd + k_mac
     assert l2 == 2 * nb
