@@ -15,7 +15,7 @@
 extern "C" {
 #endif
 
-/* Launch-policy knobs (irbaboon_b200/csrc/irb_tuning.hpp) by name: "mac_persistent", "mac_tma", "mac_wide", "mac_u",
+/* Launch-policy knobs (irbaboon_b200/csrc/irb_tuning.hpp) by name: "mac_persistent", "fuse_split", "mac_tma", "mac_wide", "mac_u",
  * "fdl_plain", "producer_sleep_ns", "no_graph", "deconv_sub", "deconv_streams", "release_fence", "release_dep", "persistent_ctas", "unit_narrowing", "ir_replicas", "stagger_ns", "ring_stages".
  * The library itself never reads the environment; the defaults are compiled in.  _get returns the value (or IRB_ERR_ARG). */
 int irbx_set_tuning(const char* name, int value);
@@ -24,6 +24,10 @@ int irbx_get_tuning(const char* name);
 /* The pure FDL multiply-accumulate of the engine's current state (no forward / inverse FFT) into a device buffer of
  * n_channels * M complex: times the roofline kernel's inner loop in isolation. */
 int irbx_engine_mac_only_device(irb_engine* e, float* acc_dev);
+/* Phase time stamps of the latency-path kernel (k_mac_slots): with a device array of 64 x 16 uint64 set, thread 0 of CTA b < 64
+ * stores at [16 b + phase] the %globaltimer (ns) at kernel start, after the set-up, after the forward transform, after the partition loop, before and after
+ * each cluster barrier and at the end.  NULL switches it off (the default). */
+int irbx_engine_set_stamps(irb_engine* e, unsigned long long* stamps_dev);
 
 /* GB/s of a kernel that does nothing but read `bytes` of device memory once per iteration with 32-byte streaming loads
  * (L1 no-allocate, L2 evict-first), grid = resident CTAs; averaged over `iters` launches after one warm-up: the read-only

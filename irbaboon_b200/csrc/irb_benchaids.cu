@@ -58,7 +58,7 @@ using irbh::fail;
 int* tuning_field(const char* name) {
     irbh::Tuning& t = irbh::g_tuning;
     struct { const char* n; int* p; } tab[] = {
-        {"mac_persistent", &t.mac_persistent}, {"mac_tma", &t.mac_tma}, {"mac_wide", &t.mac_wide}, {"mac_u", &t.mac_u}, {"fdl_plain", &t.fdl_plain},
+        {"mac_persistent", &t.mac_persistent}, {"fuse_split", &t.fuse_split}, {"mac_tma", &t.mac_tma}, {"mac_wide", &t.mac_wide}, {"mac_u", &t.mac_u}, {"fdl_plain", &t.fdl_plain},
         {"producer_sleep_ns", &t.producer_sleep_ns}, {"no_graph", &t.no_graph}, {"deconv_sub", &t.deconv_sub}, {"deconv_streams", &t.deconv_streams}, {"release_fence", &t.release_fence}, {"release_dep", &t.release_dep},
         {"persistent_ctas", &t.persistent_ctas}, {"unit_narrowing", &t.unit_narrowing}, {"ir_replicas", &t.ir_replicas}, {"stagger_ns", &t.stagger_ns}, {"ring_stages", &t.ring_stages}};
     if (name) for (auto& e : tab) if (!strcmp(e.n, name)) return e.p;
@@ -88,6 +88,7 @@ int irbx_get_tuning(const char* name) {
 }
 
 int irbx_engine_mac_only_device(irb_engine* e, float* acc_dev) { return irbh::engine_mac_only(e, acc_dev); }
+int irbx_engine_set_stamps(irb_engine* e, unsigned long long* stamps_dev) { return irbh::engine_set_stamps(e, stamps_dev); }
 
 int irbx_hbm_read_probe(size_t bytes, int iters, int write_every, int store_kind, double* gbs) {
     if (!gbs || iters < 1 || bytes < (1u << 20)) return fail(IRB_ERR_ARG, "bad argument");

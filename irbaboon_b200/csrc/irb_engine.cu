@@ -337,6 +337,7 @@ struct irb_engine {
     const float2* W = nullptr;
     DevBuf fdl, H, ov, head, ir_of_chan, nparts, io_in[2], io_out[2], taps;
     DevBuf work;                       // k_mac_p: {next unit, finished CTAs}, cleared by the kernel itself
+    unsigned long long* stamps = nullptr;   // measurement only (irbx_engine_set_stamps): phase time stamps of the latency-path kernel
     int h_reps = 1;                    // identical copies of the IR spectra H (MacArgs::h_reps): [rep][ir][partition][M]
     long long h_rep_stride() const { return (long long) n_irs * ring * M; }
     // clear / replicate the spectra of one IR across the copies (copy 0 is the one every writer fills)
@@ -462,20 +463,22 @@ void fill_mac_args(irb_engine* e, irb::MacArgs& m, int c0, int cn) {
     m.ir_of_chan = e->ir_of_chan.as<int>() + c0; m.nparts = e->nparts.as<int>(); m.W = e->W;
     m.B = e->B; m.split_in = e->split_in;
     mac_policy(m);
+    m.stamps = e->stamps;
     m.work = irbh::g_tuning.mac_persistent ? e->work.as<int>() : nullptr;
 }
 bool use_slots(const irb_engine* e) { return e->per_row_ir || e->split_in > 1 || e->cluster_dim > 1; }
 // Is the block step ONE launch (forward transform in the MAC kernel's prologue)?  Shared-IR tiles: always (unless switched off);
-// per-stream IRs: through the persistent kernel; few rows (partitions split over slots / a cluster): two launches.
+// per-stream IRs: through the persistent kernel; few rows (partitions split over slots / a cluster): in the cluster kernel.
 bool step_is_fused(const irb_engine* e) {
-    if (!e->fuse_fwd || e->split_in > 1 || e->cluster_dim > 1) return false;
+    if (!e->fuse_fwd) return false;
+    if (e->split_in > 1 || e->cluster_dim > 1) return irbh::g_tuning.fuse_split != 0;      // the cluster kernel's rank 0 transforms the new blocks itself
     if (e->per_row_ir) return irbh::g_tuning.mac_persistent && e->M >= kPersistMinM;
     return true;
 }
 // everything a captured graph or a cached plan bakes in besides the engine's own state
 int tuning_variant() {
     const irbh::Tuning& t = irbh::g_tuning;
-    return t.mac_persistent | t.mac_tma << 1 | t.mac_wide << 2 | (t.mac_u & 3) << 3 | t.release_fence << 5 | t.release_dep << 9 | (t.persistent_ctas & 3) << 6 | t.unit_narrowing << 8;
+    return t.mac_persistent | t.mac_tma << 1 | t.mac_wide << 2 | (t.mac_u & 3) << 3 | t.release_fence << 5 | t.release_dep << 9 | t.fuse_split << 10 | (t.persistent_ctas & 3) << 6 | t.unit_narrowing << 8;
 }
 
 constexpr int kTimingCap = 16384;
@@ -515,7 +518,7 @@ int engine_launch_mac(irb_engine* e, float* out_dev, int head_back, const float*
 // one block step for the channels [c0, c0+cn); refresh: also run the staged IRs' refresh rows (once per block)
 int engine_step_range(irb_engine* e, const float* in_dev, float* out_dev, int c0, int cn, bool refresh) {
     // ONE launch per block step, the forward transform is the MAC kernel's prologue (staged IRs still get their refresh
-    // rows through a k_fwd launch of their own).  The few-row slot kernel keeps the two-launch form.
+    // rows through a k_fwd launch of their own).  The few-row cluster kernel transforms the new blocks on its rank 0.
     const bool fused = step_is_fused(e);
     int rc = engine_launch_fwd(e, in_dev, !fused, refresh, c0, cn);
     if (rc) return rc;
@@ -1247,6 +1250,12 @@ size_t irb_group_state_bytes(const irb_group* g) {
 
 // ---- internals reached by the bench-only translation unit (irb_benchaids.cu, include/irb_b200_bench.h) -------------------
 namespace irbh {
+int engine_set_stamps(irb_engine* e, unsigned long long* dev) {
+    if (!e) return fail(IRB_ERR_ARG, "engine is null");
+    e->stamps = dev;
+    e->g_sig.n_rr = -1;                // a captured graph baked the old pointer in: re-capture
+    return 0;
+}
 // the pure FDL multiply-accumulate (no forward / inverse FFT) on the current state into n_channels * M complex
 int engine_mac_only(irb_engine* e, float* acc_dev) {
     if (!e || !acc_dev) return fail(IRB_ERR_ARG, "null argument");

@@ -18,8 +18,9 @@
 //               partitions streamed by TMA into a 3-stage shared-memory ring, inverse FFT, overlap-add
 //   k_mac       the same loop with the FDL staged through registers (coalesced 16- / 32-byte loads): offline form, two-launch
 //               streaming form, small FFT sizes; with FUSE also k_fwd's work (the A/B partner of k_mac_tma)
-//   k_mac_slots the same loop when a tile's rows do not share an IR (per-stream IRs) or when there are so few rows that
-//               each row's partitions are split over tile slots and the CTAs of a thread-block cluster
+//   k_mac_slots the same loop when there are so few rows that each row's partitions are split over tile slots and the CTAs of a
+//               thread-block cluster (the latency path; with the fused step cluster rank 0 runs the forward transform itself)
+//   k_mac_p     (irb_mac_p.cuh) the persistent block step: shared-IR tiles and per-stream IRs, one launch per step
 //   k_ola_tail  fp/convolution.cpp:210-213 for the offline (all blocks at once) formulation
 #pragma once
 #include <cuda_runtime.h>
@@ -314,6 +315,7 @@ struct MacArgs {
     long long h_rep_stride;
     int stagger_ns;            // k_mac_p: CTA starts are spread over this many nanoseconds
     int ring_stages;           // k_mac_p: use only this many of the ring's stages (0: all; measurement)
+    unsigned long long* stamps;  // measurement (irbx_engine_set_stamps): thread 0 of CTA b < 64 stores %globaltimer at stamps[16 b + phase] in k_mac_slots
 };
 // the copy of the shared IR spectra this CTA streams
 __device__ __forceinline__ const float2* ir_replica(const MacArgs& a) {
@@ -375,6 +377,11 @@ __device__ __forceinline__ long long fdl_row_offset(const MacArgs& a, int chan, 
     return (chan / grp) * a.fdl_chan_stride + (long long) (chan % grp) * M;
 }
 template <int M> __device__ __forceinline__ long long fdl_slot_stride(const MacArgs& a) { return a.fdl_slot_stride ? a.fdl_slot_stride : M; }
+
+// phase time stamp of the latency path (measurement aid: a null pointer in every product launch)
+__device__ __forceinline__ void stamp(const MacArgs& a, int i) {
+    if (a.stamps && blockIdx.x < 64 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.stamps[blockIdx.x * 16 + i] = t; }
+}
 
 // consumer release of a TMA-filled ring stage by the warp's elected lane (after the warp-wide fence.proxy.async + __syncwarp)
 __device__ __forceinline__ void mbar_release_stage(uint64_t* b, uint32_t dep, const MacArgs& a) {
@@ -809,12 +816,16 @@ __global__ void __launch_bounds__(kThreads + 32, M <= 1024 ? 3 : 2) k_mac_tma(co
 // Otherwise the partial sums of a row are added in ascending q (i.e. ascending partition order between ranges)
 // through distributed shared memory: every CTA of the cluster reduces 1/cluster_size of the tile and writes it
 // into rank 0, which runs the inverse-FFT epilogue.  Streaming only (head != nullptr).
+constexpr int kSlotStages = 8;           // IR ring stages of the slot kernel: a short partition range is staged all at once
+constexpr int kSlotDepth = 4;            // FDL load groups a thread keeps in flight (registers)
 template <int M>
 struct SlotSmem {
-    float2 spec[kTile];                                  // partial sums, slot-major
-    float2 h[kStages][kTile / M][M];                     // IR ring: one partition per slot and stage; reused as the reduced tile
-    uint64_t full[kStages], empty[kStages];
+    float2 spec[kTile];                                  // fused step: the forward transform's tile; then the partial sums, slot-major
+    float2 h[kSlotStages][kTile / M][M];                 // IR ring: one partition per slot and stage; reused as the reduced tile
+    float2 xnew[kTile];                                  // fused step, cluster rank 0: packed spectra of the rows' new blocks (partition 0's operand)
+    uint64_t full[kSlotStages], empty[kSlotStages];
     int pbeg[kTile / M], pcnt[kTile / M], ngroups;
+    int hd[kTile / M];                                   // head of every slot's row as the kernel found it
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -837,7 +848,7 @@ __device__ __forceinline__ void dsmem_st4(uint32_t addr, float4 v) {
 }
 
 template <int M, bool INV, bool WIDE = true>
-__global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a) {
+__global__ void __launch_bounds__(kThreads + 32, 1) k_mac_slots(const MacArgs a) {
     using T = Tile<M>;
     using L = MacLayout<M, WIDE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -847,9 +858,10 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
     const int split_in = a.split_in, nsplit = split_in * CL;
     const int rpt = T::ROWS / split_in;                   // rows per tile
     const int row0 = (blockIdx.x / CL) * rpt;
+    stamp(a, 0);
 
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], kThreads / 32); }
+        for (int i = 0; i < kSlotStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], kThreads / 32); }
         mbar_fence_init();
         sm.ngroups = 0;
     }
@@ -858,56 +870,128 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
     if (tid < T::ROWS) {
         const int row = row0 + tid / split_in;
         int pb = 0, pc = 0;
+        int hd = 0;
         if (row < a.n_rows) {
             const int chan = row / a.blocks_per_chan;
             const int nv = a.nparts[a.ir_of_chan ? a.ir_of_chan[chan] : 0];
-            const int per = (nv + nsplit - 1) / nsplit;
-            pb = (crank * split_in + tid % split_in) * per;
-            pc = nv - pb;
-            pc = pc < 0 ? 0 : (pc > per ? per : pc);
+            hd = a.head[chan];
+            if (a.in != nullptr && CL > 1) {
+                // Fused step on a cluster: rank 0 also runs the forward transform, so it takes partition 0 alone (its operand is the
+                // transform's result); the other ranks share partitions 1 .. nv-1.  Ranges stay in ascending order of (rank, slot).
+                if (crank == 0) { pb = 0; pc = (tid % split_in == 0 && nv > 0) ? 1 : 0; }
+                else {
+                    const int nsl = (CL - 1) * split_in, per = (nv - 1 + nsl - 1) / nsl;
+                    pb = 1 + ((crank - 1) * split_in + tid % split_in) * per;
+                    pc = nv - pb;
+                    pc = pc < 0 ? 0 : (pc > per ? per : pc);
+                }
+            } else {
+                const int per = (nv + nsplit - 1) / nsplit;
+                pb = (crank * split_in + tid % split_in) * per;
+                pc = nv - pb;
+                pc = pc < 0 ? 0 : (pc > per ? per : pc);
+            }
         }
-        sm.pbeg[tid] = pb; sm.pcnt[tid] = pc;
+        sm.pbeg[tid] = pb; sm.pcnt[tid] = pc; sm.hd[tid] = hd;
         if (pc > 0) atomicMax(&sm.ngroups, pc);
     }
     __syncthreads();
     const int ngroups = sm.ngroups;
+    stamp(a, 1);
 
     if (tid >= kThreads) {
         // ===== TMA producer warp: one bulk copy per (slot, step); lanes split the slots of the tile =====
+        // Everything a copy's address depends on is fetched BEFORE the loop: with the IR index loaded inside it every ring step
+        // started one L2 latency after the previous one (phase stamps: 0.4 - 0.55 us per partition, whatever the loads did).
         const int lane = tid - kThreads;
+        constexpr int SPL = (T::ROWS + 31) / 32;           // slots per lane
+        const float2* hsrc[SPL];
+        int pcn[SPL];
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+            const int r = lane + 32 * j;
+            pcn[j] = r < T::ROWS ? sm.pcnt[r] : 0;
+            hsrc[j] = a.H;
+            if (pcn[j] > 0) {
+                const int chan = (row0 + r / split_in) / a.blocks_per_chan;
+                const int irr = a.ir_of_chan ? a.ir_of_chan[chan] : 0;
+                hsrc[j] = a.H + irr * a.ir_stride + (long long) sm.pbeg[r] * M;
+            }
+        }
         for (int g = 0; g < ngroups; ++g) {
-            const int st = g % kStages;
-            if (g >= kStages) mbar_wait_relaxed(&sm.empty[st], ((g / kStages) - 1) & 1, a.producer_sleep_ns);
+            const int st = g % kSlotStages;
+            if (g >= kSlotStages) mbar_wait_relaxed(&sm.empty[st], ((g / kSlotStages) - 1) & 1, a.producer_sleep_ns);
             uint32_t total = 0;
-            for (int r = lane; r < T::ROWS; r += 32) if (g < sm.pcnt[r]) total += M * sizeof(float2);
+#pragma unroll
+            for (int j = 0; j < SPL; ++j) if (g < pcn[j]) total += M * sizeof(float2);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
             if (lane == 0) mbar_expect_tx(&sm.full[st], total);
             __syncwarp();
-            for (int r = lane; r < T::ROWS; r += 32) {
-                if (g < sm.pcnt[r]) {
-                    const int chan = (row0 + r / split_in) / a.blocks_per_chan;
-                    const int irr = a.ir_of_chan ? a.ir_of_chan[chan] : 0;
-                    tma_bulk_g2s(&sm.h[st][r][0], a.H + irr * a.ir_stride + (long long) (sm.pbeg[r] + g) * M, M * sizeof(float2), &sm.full[st]);
-                }
-            }
+#pragma unroll
+            for (int j = 0; j < SPL; ++j)
+                if (g < pcn[j]) tma_bulk_g2s(&sm.h[st][lane + 32 * j][0], hsrc[j] + (long long) g * M, M * sizeof(float2), &sm.full[st]);
         }
     } else {
-        // ===== compute threads, MAC layout: thread owns V float4 of the K slots s*G + g_ =====
+        // ===== compute threads =====
+        // Fused step (a.in != nullptr): the heads still name the PREVIOUS block; the new block's spectrum goes to slot head + 1 and is
+        // partition 0's operand.  Cluster rank 0 owns partition 0 of every row of the tile, so it alone runs the forward transform
+        // (k_fwd's work for these rows), writes the spectrum to the FDL and keeps a packed copy in shared memory; the other ranks
+        // start on their partition ranges (which only meet older slots) right away.  Rank 0 advances the heads after the
+        // cluster's first barrier, when every rank has read them.
+        const bool fused = a.in != nullptr;
+        if (fused && crank == 0) {
+            const int rf = tid / T::TPF, t = tid % T::TPF;
+            const int row = row0 + rf;
+            float2 v[kPts];
+#pragma unroll
+            for (int j = 0; j < kPts; ++j) v[j] = make_float2(0.f, 0.f);
+            if (rf < rpt && row < a.n_rows) {
+                const float* p = a.in + row * a.in_chan_stride;
+#pragma unroll
+                for (int j = 0; j < kPts; ++j) {
+                    const int m = 2 * (t + j * T::TPF);
+                    if (m < a.B) v[j].x = p[m];
+                    if (m + 1 < a.B) v[j].y = p[m + 1];
+                }
+            }
+            float2* srow = sm.spec + rf * M;
+            fft_run<M, false>(v, t, srow, a.W);
+            bar_compute();
+#pragma unroll
+            for (int j = 0; j < kPts; ++j) srow[t + j * T::TPF] = v[j];
+            bar_compute();
+            for (int o = tid; o < rpt * (M / 2); o += kThreads) {
+                const int r = o / (M / 2), k = 2 * (o % (M / 2)), rw = row0 + r;
+                if (rw >= a.n_rows) continue;
+                const float2* z = sm.spec + r * M;
+                const float2 x0 = real_split(z[k], z[(M - k) & (M - 1)], root<false>(a.W, k), k);
+                const float2 x1 = real_split(z[k + 1], z[M - k - 1], root<false>(a.W, k + 1), k + 1);
+                const float4 xv = make_float4(x0.x, x0.y, x1.x, x1.y);
+                int ns = sm.hd[r * split_in] + 1; if (ns >= a.ring) ns = 0;
+                *reinterpret_cast<float4*>(const_cast<float2*>(a.fdl) + fdl_row_offset(a, rw, M) + (long long) ns * fdl_slot_stride<M>(a) + k) = xv;
+                *reinterpret_cast<float4*>(sm.xnew + r * M + k) = xv;
+            }
+            bar_compute();                                // xnew is complete; sm.spec is free for the partial sums
+        }
+        stamp(a, 2);
+        // MAC layout: thread owns V float4 of the K slots s*G + g_
         const int g_ = tid / L::TPR, c0 = tid % L::TPR;
         const float4* xptr[L::K];
         int slot[L::K], nvalid[L::K];
+        bool first[L::K];                                 // this slot's range starts at partition 0 of a fused step: operand in sm.xnew
 #pragma unroll
         for (int s = 0; s < L::K; ++s) {
             const int sl = s * L::G + g_;
             const int row = row0 + sl / split_in;
-            nvalid[s] = sm.pcnt[sl]; slot[s] = 0; xptr[s] = nullptr;
+            nvalid[s] = sm.pcnt[sl]; slot[s] = 0; xptr[s] = nullptr; first[s] = false;
             if (nvalid[s] > 0) {
                 const int chan = row / a.blocks_per_chan;
-                int hd = a.head[chan] - a.head_back - sm.pbeg[sl];      // partition p meets slot (head - p) mod ring
-                while (hd < 0) hd += a.ring;
+                int hd = (sm.hd[sl] + (fused ? 1 : 0) - a.head_back - sm.pbeg[sl]) % a.ring;      // partition p meets slot (newest - p) mod ring
+                if (hd < 0) hd += a.ring;
                 slot[s] = hd;
                 xptr[s] = reinterpret_cast<const float4*>(a.fdl + fdl_row_offset(a, chan, M) + (long long) hd * fdl_slot_stride<M>(a));
+                first[s] = fused && sm.pbeg[sl] == 0;
             }
         }
         float4 acc[L::K][L::V];
@@ -916,13 +1000,17 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
 #pragma unroll
             for (int vv = 0; vv < L::V; ++vv) acc[s][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        float4 xa[L::K][L::V], xb[L::K][L::V];
+        float4 xq[kSlotDepth][L::K][L::V];
         const long long sstep = fdl_slot_stride<M>(a) / 2;    // float4 between ring slots
         auto load_group = [&](float4 (&x)[L::K][L::V], int g) {
 #pragma unroll
             for (int s = 0; s < L::K; ++s) {
                 const bool ok = g < nvalid[s];
-                if constexpr (WIDE) {
+                if (g == 0 && first[s]) {                 // the new block's spectrum is not in global memory for this kernel to read: it sits in sm.xnew
+                    const float4* xn = reinterpret_cast<const float4*>(sm.xnew + ((s * L::G + g_) / split_in) * M);
+#pragma unroll
+                    for (int vv = 0; vv < L::V; ++vv) x[s][vv] = ok ? xn[L::f4(c0, vv)] : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else if constexpr (WIDE) {
 #pragma unroll
                     for (int vv = 0; vv < L::V; vv += 2) {
                         x[s][vv] = x[s][vv + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -939,8 +1027,8 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
             }
         };
         auto consume_group = [&](float4 (&x)[L::K][L::V], int g) {
-            const int st = g % kStages;
-            mbar_wait(&sm.full[st], (g / kStages) & 1);
+            const int st = g % kSlotStages;
+            mbar_wait(&sm.full[st], (g / kSlotStages) & 1);
             uint32_t dep = 0;                              // see mbar_arrive_after
 #pragma unroll
             for (int vv = 0; vv < L::V; ++vv) {
@@ -963,15 +1051,20 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
             __syncwarp();
             if ((tid & 31) == 0) mbar_release_stage(&sm.empty[st], dep, a);
         };
-        if (ngroups > 0) load_group(xa, 0);
-        for (int g = 0; g < ngroups; g += 2) {
-            if (g + 1 < ngroups) load_group(xb, g + 1);
-            consume_group(xa, g);
-            if (g + 1 < ngroups) {
-                if (g + 2 < ngroups) load_group(xa, g + 2);
-                consume_group(xb, g + 1);
+        // kSlotDepth groups of FDL loads stay in flight (round 1 kept one), the IR ring holds kSlotStages partitions: the 6 or 7
+        // partitions a slot has on the latency path are requested at once.
+#pragma unroll
+        for (int i = 0; i < kSlotDepth; ++i) if (i < ngroups) load_group(xq[i], i);
+        for (int g = 0; g < ngroups; g += kSlotDepth) {
+#pragma unroll
+            for (int i = 0; i < kSlotDepth; ++i) {
+                if (g + i < ngroups) {
+                    consume_group(xq[i], g + i);
+                    if (g + i + kSlotDepth < ngroups) load_group(xq[i], g + i + kSlotDepth);
+                }
             }
         }
+        stamp(a, 3);
         if (!INV && nsplit == 1) {
 #pragma unroll
             for (int s = 0; s < L::K; ++s) {
@@ -1010,7 +1103,13 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
                 part[o] = sum;
             }
         }
+        stamp(a, 4);
         cluster_sync_all();                               // every CTA's row sums are visible cluster-wide
+        stamp(a, 5);
+        if (a.in != nullptr && crank == 0 && tid < rpt && row0 + tid < a.n_rows) {      // fused step: every rank has read the old heads
+            const int hnew = sm.hd[tid * split_in] + 1;
+            a.head_rw[row0 + tid] = hnew >= a.ring ? 0 : hnew;
+        }
         if (tid < kThreads && CL > 1) {
             const int per = n4 / CL;
             const uint32_t red0 = dsmem_addr(red, 0);
@@ -1023,12 +1122,20 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
                 dsmem_st4(red0 + (uint32_t) (o * sizeof(float4)), sum);
             }
         }
+        stamp(a, 6);
         cluster_sync_all();                               // rank 0 holds the reduced tile; nobody reads remote memory any more
+        stamp(a, 7);
         if (crank != 0) return;
         fin = reinterpret_cast<float2*>(CL > 1 ? red : part);
     }
     if (tid >= kThreads) return;
-    if (nsplit == 1) bar_compute();                       // the tile is complete in shared memory
+    if (nsplit == 1) {
+        bar_compute();                                    // the tile is complete in shared memory
+        if (a.in != nullptr && tid < rpt && row0 + tid < a.n_rows) {       // fused step without a split: the heads move here
+            const int hnew = sm.hd[tid] + 1;
+            a.head_rw[row0 + tid] = hnew >= a.ring ? 0 : hnew;
+        }
+    }
     if constexpr (INV) {
         inv_epilogue<M>(a, fin, tid, row0, rpt);
     } else {
@@ -1037,6 +1144,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_slots(const MacArgs a)
             if (row < a.n_rows) reinterpret_cast<float4*>(a.Y + (long long) row * M)[o % (M / 2)] = reinterpret_cast<const float4*>(fin)[o];
         }
     }
+    stamp(a, 8);
 }
 
 // (a + b) / 2 : tools::sumToMono (fp/tools.cpp:25-29)

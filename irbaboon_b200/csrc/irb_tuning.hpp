@@ -8,6 +8,7 @@ namespace irbh {
 
 struct Tuning {
     int mac_persistent = 1;      // shared-IR / per-stream-IR block step as the persistent TMA kernel k_mac_p (0: k_mac_tma / k_mac_slots)
+    int fuse_split = 1;          // few rows (partitions split over a cluster): forward transform inside the cluster kernel (0: k_fwd launch first)
     int mac_tma = 1;             // non-persistent fused step: FDL through TMA (k_mac_tma); 0: register-staged k_mac<FUSE>
     int mac_wide = 1;            // register-staged MAC: 32-byte FDL loads (0: 16-byte)
     int mac_u = 1;               // register-staged MAC: IR partitions per ring stage (1 or 2)

@@ -95,6 +95,7 @@ _BENCH_SIGS = {
     "irbx_set_tuning": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "irbx_get_tuning": (ctypes.c_int, [ctypes.c_char_p]),
     "irbx_engine_mac_only_device": (ctypes.c_int, [_vp, _vp]),
+    "irbx_engine_set_stamps": (ctypes.c_int, [_vp, _vp]),
     "irbx_hbm_read_probe": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "irbx_copy_probe_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_size_t, ctypes.c_int]),
     "irbx_copy_probe_run": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double)]),
@@ -452,6 +453,10 @@ class Engine:
     def mac_only_device(self, acc_ptr):
         """bench-only (irb_b200_bench.h): the bare FDL multiply-accumulate into a device buffer"""
         _ck(lib().irbx_engine_mac_only_device(self._h, _vp(int(acc_ptr))))
+
+    def set_stamps(self, dev_ptr):
+        """bench-only: device array of 16 uint64 for the phase time stamps of the latency-path kernel (0 / None: off)"""
+        _ck(lib().irbx_engine_set_stamps(self._h, _vp(int(dev_ptr or 0))))
 
     def set_active_channels(self, n_active):
         """Only channels [0, n_active) take part in the following block steps; I/O arrays are then [n_blocks][n_active][B]."""

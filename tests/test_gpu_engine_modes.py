@@ -49,6 +49,40 @@ def test_split_mac_matches_oracle(eng, orc, B, Lh, C, split, cluster):
         _check(y1[c:c + 1], want)
 
 
+@pytest.mark.parametrize("B,Lh,C,split,cluster", [(256, 256 * 37 + 11, 2, 8, 16), (256, 256 * 37 + 11, 2, 2, 4), (512, 512 * 21, 5, 2, 2), (1024, 1024 * 9 + 1, 3, 2, 8),
+                                                   (2048, 2048 * 6, 2, 1, 16), (64, 64 * 50 + 3, 3, 32, 8), (16, 16 * 70, 2, 128, 8), (300, 300 * 20 + 5, 3, 4, 4), (512, 512 * 21, 5, 4, 1), (256, 256 * 3, 2, 2, 8)])
+def test_split_mac_with_fused_forward_equals_its_two_launch_form(eng, orc, B, Lh, C, split, cluster):
+    """The latency path in ONE launch: cluster rank 0 transforms the new blocks itself (partition 0's operand comes out of
+    shared memory), the heads move after the cluster's first barrier.  Bit-identical to k_fwd + the cluster kernel; ring wrap."""
+    P = -(-Lh // B)
+    nb = P + 6
+    rng = np.random.default_rng(B + C)
+    x = (rng.random((nb, C, B), dtype=np.float32) * 2 - 1).astype(np.float32)
+    h = synth.decaying_ir(2000, Lh)
+    outs = []
+    for fuse in (1, 0):
+        eng.set_tuning("fuse_split", fuse)
+        try:
+            with eng.Engine(B, P, C, 1) as e:
+                e.set_ir(0, h)
+                e.set_mac_split(split, cluster)
+                l0 = e.launches
+                outs.append(np.stack([e.process(x[k]) for k in range(nb)]))           # one block per call: plain, then graph replays
+                assert e.launches - l0 == (nb if fuse else 2 * nb)
+        finally:
+            eng.set_tuning("fuse_split", 1)
+    # on a cluster the fused form gives rank 0 partition 0 alone (it also runs the transform), so the ranges -- the blocking of
+    # the sum -- differ from the two-launch form's: equal within rounding there, bit for bit without a cluster
+    if cluster == 1:
+        assert np.array_equal(outs[0], outs[1])
+    else:
+        assert np.abs(outs[0] - outs[1]).max() <= 2e-6 * max(1.0, float(np.abs(outs[1]).max()))
+    for c in range(C):
+        want = orc.convolve_periodic(np.ascontiguousarray(x[:, c, :]).reshape(-1), h, B)[:, :nb * B]
+        _check(outs[0][:, c, :].reshape(1, -1), want)
+        _check(outs[1][:, c, :].reshape(1, -1), want)
+
+
 def test_split_is_chosen_automatically_for_few_rows_only(eng):
     with eng.Engine(256, 750, 2, 2) as e:                       # BASELINE config 2: stereo, 4 s IR, one stream
         h = synth.decaying_ir(2000, 192000)
@@ -332,7 +366,7 @@ def test_single_block_calls_replay_a_graph_with_identical_results(eng, orc):
         assert np.array_equal(one, whole)
         l0 = e.launches
         e.process(blocks[0])
-        assert e.launches - l0 == 2                                # the replayed graph holds the step's two kernels
+        assert e.launches - l0 == 1                                # the replayed graph holds the step's ONE kernel (cluster kernel, forward transform fused)
         e.reset()
         e.set_mac_split(1, 1)                                      # different plan -> different kernels -> re-capture
         one2 = np.stack([e.process(blocks[k]) for k in range(nb)])
