@@ -209,3 +209,23 @@ def test_config5_full_size_ess_capture(eng, orc):
         back = np.fft.irfft(np.fft.rfft(got[j].astype(np.float64)) * S, n)
         assert np.abs(back - caps[j]).max() <= 2e-4 * np.abs(caps[j]).max()
         assert np.abs(got[j, :48000] - irs[j]).max() <= 2e-2          # the IR is recovered up to the injected noise
+
+
+# ---- device-resident batch entry ------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,batch,smoothing,phase", [(1 << 16, 7, False, True), ((1 << 16) - 1, 5, False, True), (1 << 16, 4, True, True),
+                                                     (1 << 16, 3, True, False), (4096, 6, False, True), (1 << 18, 40, False, True)])
+def test_deconvolve_batch_device_equals_the_host_entry(eng, n, batch, smoothing, phase):
+    """irb_deconvolve_batch_device (captures and results in HBM, sub-batches alternating between compute streams; staged
+    device-to-device for small transforms, smoothing, a dropped phase or an odd capture length) against irb_deconvolve_batch."""
+    import torch
+    rng = np.random.default_rng(n + batch)
+    sweep = synth.exp_sine_sweep(n / 48000.0, 48000.0, 20.0, 20000.0).astype(np.float32)[:n]
+    caps = (rng.random((batch, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+    want = eng.deconvolve_batch(caps, sweep, 48000.0, smoothing, phase, True)
+    N = want.shape[1]
+    d_caps = torch.from_numpy(caps).cuda()
+    d_out = torch.zeros((batch, N), dtype=torch.float32, device="cuda")
+    eng.deconvolve_batch_device(d_caps.data_ptr(), batch, n, sweep, d_out.data_ptr(), 48000.0, smoothing, phase, True)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    assert eng.last_compute_ms() > 0.0
