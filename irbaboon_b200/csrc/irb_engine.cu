@@ -645,6 +645,7 @@ int irb_engine_reset(irb_engine* e) {
     // cleared, write position 0; their partitions come back one per block
     for (int ir : e->h_rr_list) { int rc = e->ir_clear_all(ir, e->stream); if (rc) return rc; }
     CK(cudaMemsetAsync(e->rr_pos.p, 0, sizeof(int) * e->n_irs, e->stream));
+    CK(cudaMemsetAsync(e->work.p, 0, sizeof(int) * 4, e->stream));          // the persistent kernel's unit counter (it clears itself; belt and braces)
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
