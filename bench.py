@@ -349,6 +349,29 @@ def percentiles(ms, period):
             "realtime": bool(np.percentile(ms, 99) < period)}
 
 
+def capacity_search(p99_at, s_alloc, period_ms, ladder_steps, quantum=2048, max_rungs=12):
+    """SURVEY 8d channels_RT: the largest stream count (a multiple of `quantum`, at most s_alloc) whose p99 block step over
+    `ladder_steps` consecutive steps stays under the block period.  p99_at(streams, steps) -> (p99_ms, p50_ms), already reduced
+    over the ranks (every rank walks the same rungs).  A 40-step probe at everything resident gives the first rung; a failed rung
+    steps one quantum down, or straight to the estimate when even the MEDIAN step is over the period (a p99 miss alone may be a
+    stray slow step).  -> (streams, trail, failed): failed = no rung held (then `streams` is the last rung tried)."""
+    log = []
+    p99, p50 = p99_at(s_alloc, 40)
+    log.append({"streams": s_alloc, "steps": 40, "p50_ms": p50, "p99_ms": p99})
+    cand = s_alloc if p99 < period_ms else int(s_alloc * period_ms / (p50 * 1.02)) // quantum * quantum
+    for _ in range(max_rungs):
+        cand = max(quantum, min(cand, s_alloc))
+        p99, p50 = p99_at(cand, ladder_steps)
+        ok = p99 < period_ms
+        log.append({"streams": cand, "steps": ladder_steps, "p50_ms": p50, "p99_ms": p99, "realtime": bool(ok)})
+        if ok:
+            return cand, log, False
+        if cand <= quantum:
+            break
+        cand = min(cand - quantum, int(cand * period_ms / (p50 * 1.02)) // quantum * quantum) if p50 >= period_ms else cand - quantum
+    return max(quantum, min(cand, s_alloc)), log, True
+
+
 def run_b200(args):
     from irbaboon_b200 import engine as eng
     for kv in args.tune:
@@ -432,29 +455,8 @@ def run_b200(args):
             for _ in range(3):
                 step()
             sm_, _, _ = timed_steps(n_steps)
-            return R.max(np.percentile(sm_, 99)), R.max(np.percentile(sm_, 50)), sm_
-        p99, p50, _ = p99_at(S_alloc, 40)
-        ladder_log.append({"streams": S_alloc, "steps": 40, "p50_ms": p50, "p99_ms": p99})
-        if p99 < period_ms:                                   # everything resident already runs in real time: verify it over the full count
-            cand = S_alloc
-        else:
-            cand = int(S_alloc * period_ms / (p50 * 1.02)) // 2048 * 2048
-        S = 0
-        for _ in range(12):
-            cand = max(2048, min(cand, S_alloc))
-            p99, p50, sm_ = p99_at(cand, args.ladder_steps)
-            ok = p99 < period_ms
-            ladder_log.append({"streams": cand, "steps": args.ladder_steps, "p50_ms": p50, "p99_ms": p99, "realtime": bool(ok)})
-            if ok:
-                S = cand
-                break
-            if cand <= 2048:
-                break
-            # one rung down; further when the MEDIAN step is already over the period (a p99 miss alone may be a stray slow step)
-            cand = min(cand - 2048, int(cand * period_ms / (p50 * 1.02)) // 2048 * 2048) if p50 >= period_ms else cand - 2048
-        ladder_failed = S == 0
-        if ladder_failed:                                    # nothing verified (a disturbed box): measure at the last rung and say so
-            S = max(2048, min(cand, S_alloc))
+            return R.max(np.percentile(sm_, 99)), R.max(np.percentile(sm_, 50))
+        S, ladder_log, ladder_failed = capacity_search(p99_at, S_alloc, period_ms, args.ladder_steps)
         e.set_active_channels(S)
     for _ in range(3):
         step()

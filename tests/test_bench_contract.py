@@ -30,3 +30,56 @@ def test_product_arm_needs_a_gpu():
         pytest.skip("a GPU is present")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
+
+
+# ---- the capacity ladder (SURVEY 8d channels_RT) as a pure function ----------------------------------------------
+def _bench_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("irb_bench", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def _fake_gpu(ms_per_stream, fixed_ms, slow_every=0, slow_ms=2.2, seed=0):
+    """p99_at of a GPU whose step time is linear in the stream count, with an isolated slow step every `slow_every` steps."""
+    import numpy as np
+    calls = []
+    rng = np.random.default_rng(seed)
+
+    def p99_at(streams, steps):
+        t = fixed_ms + ms_per_stream * streams + rng.normal(0, 0.003, steps)
+        if slow_every:
+            t[rng.integers(0, slow_every, 1)[0]::slow_every] += slow_ms
+        calls.append((streams, steps))
+        return float(np.percentile(t, 99)), float(np.percentile(t, 50))
+    return p99_at, calls
+
+
+def test_capacity_ladder_finds_the_largest_real_time_rung():
+    b = _bench_module()
+    period = 1e3 * 512 / 48000.0
+    # 7.1 TB/s-like device: 0.1105 us per stream -> 96.5 k streams fit the period exactly
+    p99_at, calls = _fake_gpu(1.105e-4, 0.0)
+    S, log, failed = b.capacity_search(p99_at, 98304, period, 300)
+    assert not failed and S % 2048 == 0 and S == 94208                       # 96 256 would need 10.64 ms + margin: the first rung below the 2 % guard
+    assert calls[0] == (98304, 40) and all(c[1] == 300 for c in calls[1:]) and log[-1]["realtime"]
+    # everything resident already runs in real time: verified at the full count, nothing above it is claimed
+    p99_at, calls = _fake_gpu(0.9e-4, 0.0)
+    S, log, failed = b.capacity_search(p99_at, 98304, period, 300)
+    assert (S, failed) == (98304, False) and calls == [(98304, 40), (98304, 300)]
+    # isolated +2.2 ms steps, four in 300: the rungs near the limit fail on p99 and the search walks down rung by rung
+    p99_at, calls = _fake_gpu(1.105e-4, 0.0, slow_every=70)
+    S, log, failed = b.capacity_search(p99_at, 98304, period, 300)
+    assert not failed and 2048 <= S <= 77824 and 1.105e-4 * S + 2.2 < period and [r["streams"] for r in log[1:]] == sorted((r["streams"] for r in log[1:]), reverse=True)
+
+
+def test_capacity_ladder_never_aborts():
+    b = _bench_module()
+    period = 1e3 * 512 / 48000.0
+    p99_at, calls = _fake_gpu(1.0e-4, 20.0)                                # a disturbed box: no stream count can be real-time
+    S, log, failed = b.capacity_search(p99_at, 98304, period, 300)
+    assert failed and S == 2048 and len(calls) <= 14                        # falls to the last rung and reports it as unverified
+    p99_at, calls = _fake_gpu(4.0e-4, 0.0)                                 # a GPU four times slower: jumps to the estimate, then verifies
+    S, log, failed = b.capacity_search(p99_at, 98304, period, 300)
+    assert not failed and 22528 <= S <= 26624 and len(calls) <= 4
