@@ -137,3 +137,52 @@ def test_full_gpu_many_laps_stays_in_lockstep_with_the_two_launch_form(eng):
     y, _, _ = _run(eng, B, P, C, x, [h])
     y_two, _, _ = _run(eng, B, P, C, x, [h], fused=False)
     assert np.array_equal(y, y_two)
+
+
+# ---- randomised shapes through the persistent kernel (enough channels that the launch plan never splits rows) ----------
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+
+@settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(B=st.sampled_from([129, 200, 256, 300, 512, 777, 1024, 1500, 2048]), tiles=st.integers(160, 700), extra=st.integers(0, 7), P=st.integers(1, 11), nb=st.integers(1, 9),
+       n_irs=st.integers(1, 4), mixed=st.booleans(), active_tiles=st.integers(0, 150), seed=st.integers(0, 1000))
+def test_persistent_step_any_shape(eng, orc, B, tiles, extra, P, nb, n_irs, mixed, active_tiles, seed):
+    """Random block sizes (not powers of two included), stream counts with a ragged last tile, IR lengths, shared IRs bound per
+    tile or mixed inside tiles (PERROW), and a change of the active channel count half way: fused == two-launch bit for bit, and
+    three random channels against the oracle."""
+    rng = np.random.default_rng(seed)
+    M = 16
+    while M < B:
+        M *= 2
+    rows = 2048 // max(M, 256) if M >= 256 else 2048 // M
+    C = tiles * rows // 4 + (extra % rows)
+    C = max(C, 2 * 148 * rows // 2 + 1)                                    # never few enough rows for the split plan
+    lens = [int(rng.integers(1, P * B + 1)) for _ in range(n_irs)]
+    irs = [synth.decaying_ir(2100 + seed + j, lens[j], j) for j in range(n_irs)]
+    bind = (lambda c: int((c * 7 + c // 3) % n_irs)) if mixed else (lambda c: int((c // rows) % n_irs))
+    x = _blocks(C, nb, B, seed)
+    A = min(C, max(rows, (C // rows - active_tiles) * rows))               # active channels for the second half (whole tiles)
+    k = nb // 2
+    outs = []
+    for fused in (True, False):
+        with eng.Engine(B, P, C, n_irs) as e:
+            for j, h in enumerate(irs):
+                e.set_ir(j, h)
+            for c in range(C):
+                e.bind(c, c + 1, bind(c))
+            e.set_fused_step(fused)
+            plan = e.mac_plan()
+            assert plan[1:] == (1, 1)
+            y = np.zeros((nb, C, B), np.float32)
+            if k:
+                y[:k] = e.process(x[:k])
+            e.set_active_channels(A)
+            if nb - k:
+                y[k:, :A] = e.process(np.ascontiguousarray(x[k:, :A]))
+            outs.append(y)
+    assert np.array_equal(outs[0], outs[1])
+    for c in [int(v) for v in rng.integers(0, A, 3)]:
+        want = orc.convolve_periodic(np.ascontiguousarray(x[:, c, :]).reshape(-1), irs[bind(c)], B)[0, :nb * B]
+        e_, l2 = parity(outs[0][:, c, :].reshape(-1), want)
+        assert e_ <= TOL and l2 <= TOL, (c, e_, l2)
