@@ -41,7 +41,10 @@ __device__ __forceinline__ float2 root_big(const float2* __restrict__ hi, const 
 }
 
 template <int L, bool INV>
-static __global__ void __launch_bounds__(kThreads, L >= 1024 ? 2 : 4) k_line_fft(const LineArgs a) {
+#ifndef IRB_LINE_CTAS
+#define IRB_LINE_CTAS 4                  // resident CTAs per SM the line kernels (L < 1024) are compiled for
+#endif
+static __global__ void __launch_bounds__(kThreads, L >= 1024 ? 2 : IRB_LINE_CTAS) k_line_fft(const LineArgs a) {
     using T = LineTile<L>;
     extern __shared__ __align__(16) float2 s_lines[];
     __shared__ float2 s_step[T::C][kPts];                 // inter-pass twiddle: root(line * TPF * j), the same for every thread of a line
@@ -253,7 +256,10 @@ __device__ __forceinline__ float2 pair_op(float2 zk, float2 zm, float2 bk, float
 // forward result, from which a thread reads the partners Z[M-k] of its own 8 bins; both owners of a pair evaluate
 // the pair, each keeping its own half, which costs arithmetic but no second exchange.
 template <int L>
-static __global__ void __launch_bounds__(kThreads, 4) k_rowpair(const PairArgs a) {
+#ifndef IRB_ROWPAIR_CTAS
+#define IRB_ROWPAIR_CTAS 4               // resident CTAs per SM the row-pair kernel is compiled for (register budget)
+#endif
+static __global__ void __launch_bounds__(kThreads, IRB_ROWPAIR_CTAS) k_rowpair(const PairArgs a) {
     using T = PairTile<L>;
     extern __shared__ __align__(16) float2 s_lines[];
     __shared__ float2 s_step[2 * T::NP][kPts];            // inverse inter-pass twiddle steps root_M(row * TPF * j), one set per line
