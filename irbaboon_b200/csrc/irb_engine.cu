@@ -780,7 +780,7 @@ int irb_engine_process_device(irb_engine* e, const float* in_dev, float* out_dev
 
 namespace {
 constexpr size_t kGraphMaxBytes = 256 << 10;         // blocks up to this size take the captured-graph path
-constexpr int kMaxGroups = 8;                        // channel groups a large single block is pipelined over
+constexpr int kMaxGroups = 16;                       // channel groups a large single block is pipelined over
 
 // one block, host to host, as a single graph launch; *done = false when the caller should take the plain path instead
 int engine_process_one_graphed(irb_engine* e, const float* in_host, float* out_host, bool* done) {

@@ -58,6 +58,14 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_p(const MacArgs a) {
     PSmem<M, PERROW>& sm = *reinterpret_cast<PSmem<M, PERROW>*>(smem_raw);
     const int tid = threadIdx.x;
     const int NSE = a.ring_stages > 0 && a.ring_stages < C::NS ? a.ring_stages : C::NS;       // ring stages in use
+    // measurement aid (null in every product launch): CTA 0 logs {globaltimer, SM cycle counter} at its start and end into a ring
+    // of 4096 launches indexed by work[2], the launch sequence number -- the SM clock a block step actually ran at
+    unsigned long long* stamp_row = nullptr;
+    if (a.stamps && blockIdx.x == 0 && tid == 0) {
+        stamp_row = a.stamps + (size_t) ((unsigned) a.work[2] % 4096u) * 4;
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        stamp_row[0] = t; stamp_row[1] = (unsigned long long) clock64();
+    }
 
     if (tid == 0) {
         for (int i = 0; i < C::NS; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], kThreads / 32); }
@@ -286,9 +294,10 @@ __global__ void __launch_bounds__(kThreads + 32, 2) k_mac_p(const MacArgs a) {
     // the last CTA to finish clears the work counter for the next launch (every CTA has stopped fetching by then)
     __syncthreads();
     if (tid == 0) {
+        if (stamp_row) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); stamp_row[2] = t; stamp_row[3] = (unsigned long long) clock64(); }
         __threadfence();
         const int done = atomicAdd(a.work + 1, 1);
-        if (done == (int) gridDim.x - 1) { a.work[0] = 0; a.work[1] = 0; __threadfence(); }
+        if (done == (int) gridDim.x - 1) { a.work[0] = 0; a.work[1] = 0; a.work[2] += 1; __threadfence(); }
     }
 }
 
