@@ -353,17 +353,22 @@ def capacity_search(p99_at, s_alloc, period_ms, ladder_steps, quantum=2048, max_
     """SURVEY 8d channels_RT: the largest stream count (a multiple of `quantum`, at most s_alloc) whose p99 block step over
     `ladder_steps` consecutive steps stays under the block period.  p99_at(streams, steps) -> (p99_ms, p50_ms), already reduced
     over the ranks (every rank walks the same rungs).  A 40-step probe at everything resident gives the first rung; a failed rung
-    steps one quantum down, or straight to the estimate when even the MEDIAN step is over the period (a p99 miss alone may be a
-    stray slow step).  -> (streams, trail, failed): failed = no rung held (then `streams` is the last rung tried)."""
+    is verified once more when only its p99 missed (a stray slow step), then steps one quantum down, or straight to the estimate
+    when even the MEDIAN step is over the period.  -> (streams, trail, failed): failed = no rung held (then `streams` is the last rung tried)."""
     log = []
     p99, p50 = p99_at(s_alloc, 40)
     log.append({"streams": s_alloc, "steps": 40, "p50_ms": p50, "p99_ms": p99})
     cand = s_alloc if p99 < period_ms else int(s_alloc * period_ms / (p50 * 1.02)) // quantum * quantum
     for _ in range(max_rungs):
         cand = max(quantum, min(cand, s_alloc))
-        p99, p50 = p99_at(cand, ladder_steps)
-        ok = p99 < period_ms
-        log.append({"streams": cand, "steps": ladder_steps, "p50_ms": p50, "p99_ms": p99, "realtime": bool(ok)})
+        for attempt in (1, 2):
+            p99, p50 = p99_at(cand, ladder_steps)
+            ok = p99 < period_ms
+            log.append({"streams": cand, "steps": ladder_steps, "attempt": attempt, "p50_ms": p50, "p99_ms": p99, "realtime": bool(ok)})
+            # Isolated slow steps (memory-side stalls, 0.4 - 0.6 % of steps) make the p99 of 300 samples noisy, the more so as every
+            # rank must pass: a rung whose MEDIAN is inside the period gets one more full verification before the search moves down.
+            if ok or p50 >= period_ms:
+                break
         if ok:
             return cand, log, False
         if cand <= quantum:

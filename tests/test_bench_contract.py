@@ -68,6 +68,14 @@ def test_capacity_ladder_finds_the_largest_real_time_rung():
     p99_at, calls = _fake_gpu(0.9e-4, 0.0)
     S, log, failed = b.capacity_search(p99_at, 98304, period, 300)
     assert (S, failed) == (98304, False) and calls == [(98304, 40), (98304, 300)]
+    # a rung that misses only on p99 is verified a second time before the search moves down (both attempts are in the trail)
+    state = {"n": 0}
+    def flaky(streams, steps):
+        state["n"] += 1
+        base = 1.105e-4 * streams
+        return (base + (2.2 if state["n"] == 2 else 0.01), base)            # the first full verification catches stray slow steps
+    S, log, failed = b.capacity_search(flaky, 98304, period, 300)
+    assert (S, failed) == (94208, False) and [(r["streams"], r.get("attempt")) for r in log] == [(98304, None), (94208, 1), (94208, 2)]
     # isolated +2.2 ms steps, four in 300: the rungs near the limit fail on p99 and the search walks down rung by rung
     p99_at, calls = _fake_gpu(1.105e-4, 0.0, slow_every=70)
     S, log, failed = b.capacity_search(p99_at, 98304, period, 300)
@@ -79,7 +87,7 @@ def test_capacity_ladder_never_aborts():
     period = 1e3 * 512 / 48000.0
     p99_at, calls = _fake_gpu(1.0e-4, 20.0)                                # a disturbed box: no stream count can be real-time
     S, log, failed = b.capacity_search(p99_at, 98304, period, 300)
-    assert failed and S == 2048 and len(calls) <= 14                        # falls to the last rung and reports it as unverified
+    assert failed and S == 2048 and len(calls) <= 26                        # falls to the last rung and reports it as unverified
     p99_at, calls = _fake_gpu(4.0e-4, 0.0)                                 # a GPU four times slower: jumps to the estimate, then verifies
     S, log, failed = b.capacity_search(p99_at, 98304, period, 300)
-    assert not failed and 22528 <= S <= 26624 and len(calls) <= 4
+    assert not failed and 22528 <= S <= 26624 and len(calls) <= 6
