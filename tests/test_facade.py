@@ -260,7 +260,7 @@ def test_facade_spectral_functions_on_gpu(fac, orc):
     fac.fac_deconvolve.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int, ctypes.c_double] + [ctypes.c_int] * 3 + [_f32p]
     y = orc.convolve_nonperiodic(x, h)[0]
     num, den = np.pad(y, (0, 4096 - len(y))), np.pad(x, (0, 1096))
-    for smoothing, tol in ((0, TOL), (1, 1e-4)):
+    for smoothing, tol in ((0, TOL), (1, TOL)):
         got = np.zeros(4096, np.float32)
         assert fac.fac_deconvolve(_fp(num), 4096, _fp(den), 4096, 48000.0, smoothing, 1, 1, _fp(got)) == 4096
         e, l2 = parity(got[None, :], orc.deconvolve(num, den, 48000.0, bool(smoothing)))
@@ -271,13 +271,13 @@ def test_facade_spectral_functions_on_gpu(fac, orc):
     inv = np.zeros(1024, np.float32)
     assert fac.fac_invert_filter(_fp(h), 900, 48000, _fp(inv)) == 1024
     e, l2 = parity(inv[None, :], orc.invert_filter(h, 48000))
-    assert e <= 2e-5 and l2 <= 1e-4
+    assert e <= TOL and l2 <= TOL
     fac.fac_averaging_filter.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double] + [ctypes.c_int] * 3
     s0 = orc.fft_transform(x)
     mine = s0.copy()
     assert fac.fac_averaging_filter(_fp(mine), 1, 8192, 1.0 / 13.0, 48000.0, 1, 1, 1) == 0
     e, l2 = parity(mine[:, :4098], orc.averaging_filter(s0, 1.0 / 13.0, 48000.0)[:, :4098])
-    assert e <= 2e-5 and l2 <= 5e-5
+    assert e <= TOL and l2 <= TOL
 
 
 @pytest.mark.gpu

@@ -12,7 +12,7 @@ import wave
 import numpy as np
 import pytest
 
-from conftest import parity
+from conftest import TOL, parity
 from irbaboon_b200 import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -171,7 +171,7 @@ def test_capture_to_filter_chain_matches_the_reference_functions(fac, orc, ref):
         assert np.array_equal(rec, cap)                                                # consolidate() restores the capture
         want = orc.deconvolve(cap, sweep, sr, True)
         e, l2 = parity(ir[None, :], want)
-        assert e <= 2e-5 and l2 <= 1e-4, (e, l2)
+        assert e <= TOL and l2 <= TOL, (e, l2)
         irs.append(ir); wants.append(want[0])
     filt = np.zeros(n, np.float32)
     assert fac.fac_create_ir_filt(_fp(irs[0]), n, _fp(irs[1]), n, sr, 1, 1, _fp(filt)) == n

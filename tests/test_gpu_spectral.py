@@ -124,19 +124,19 @@ def test_deconvolve_without_phase_is_shifted(eng, orc):
     # smoothing must be on for the phase flag to act (averagingFilter is where it is applied)
     want = orc.deconvolve(cap, sweep, 48000.0, True, False, True)
     got = eng.deconvolve(cap, sweep, 48000.0, True, False, True)
-    _check(got, want, tol=2e-5, l2tol=1e-4)
+    _check(got, want)
     assert int(np.argmax(np.abs(got[0]))) == int(np.argmax(np.abs(want[0])))
 
 
-@pytest.mark.parametrize("n", [4096, 1 << 15])
+@pytest.mark.parametrize("n", [4096, 1 << 13, 1 << 15, 1 << 16])
 def test_deconvolve_smoothed(eng, orc, n):
-    """smoothing=true (the plugin default): three 1/13-octave log-average passes whose float32 running sum is
-    order sensitive; the device executes the reference's sequential order, libm's logf/expf/atan2f/sincosf differ in
-    the last ulp between glibc and CUDA, hence the looser relative-L2 bound."""
+    """smoothing=true (the plugin default): three 1/13-octave log-average passes whose float32 running sum is order
+    sensitive; the device executes the reference's exact sequence of additions.  Within the north-star tolerance (measured
+    max-abs 1e-7, relative L2 1e-6 .. 4e-6 -- about half of what the reference itself moves by under a half-ulp input change)."""
     sweep, h, cap = _capture(orc, n, n // 8, 2)
     want = orc.deconvolve(cap, sweep, 48000.0, True)
     got = eng.deconvolve(cap, sweep, 48000.0, True)
-    _check(got, want, tol=2e-5, l2tol=1e-4)
+    _check(got, want)
 
 
 def test_deconvolve_batch_equals_singles(eng, orc):
@@ -151,7 +151,7 @@ def test_deconvolve_batch_equals_singles(eng, orc):
 
 def test_invert_filter(eng, orc):
     h = synth.decaying_ir(2005, 1000)
-    _check(eng.invert_filter(h, 48000), orc.invert_filter(h, 48000), tol=2e-5, l2tol=1e-4)
+    _check(eng.invert_filter(h, 48000), orc.invert_filter(h, 48000))
 
 
 # ---- averagingFilter ------------------------------------------------------------------------------------------
@@ -162,7 +162,7 @@ def test_averaging_filter_log(eng, orc, flags):
     want = orc.averaging_filter(spec, 1.0 / 13.0, 48000.0, True, *flags)
     got = eng.averaging_filter(spec, 1.0 / 13.0, 48000.0, True, *flags)
     k = slice(0, 4096 + 2)                                   # bins 0..N/2; the rest is untouched by both
-    _check(got[:, k], want[:, k], tol=2e-5, l2tol=5e-5)
+    _check(got[:, k], want[:, k])
     assert np.array_equal(got[:, 4098:], spec[:, 4098:]) and np.array_equal(want[:, 4098:], spec[:, 4098:])
 
 
@@ -171,7 +171,7 @@ def test_averaging_filter_linear_and_non_pow2(eng, orc):
     spec = orc.fft_transform(x)
     want = orc.averaging_filter(spec, 1.0 / 3.0, 48000.0, False)
     got = eng.averaging_filter(spec, 1.0 / 3.0, 48000.0, False)
-    _check(got[:, :1026], want[:, :1026], tol=2e-5, l2tol=5e-5)
+    _check(got[:, :1026], want[:, :1026])
     odd = np.ones((1, 1000), np.float32)
     assert np.array_equal(eng.averaging_filter(odd, 0.1, 48000.0), odd)          # untouched (fp/convolution.cpp:412-415)
 
