@@ -65,6 +65,7 @@ def parse():
                          "10 s IRs, block 1024, sharded by stream over the ranks (strong scaling).  c5: configs[4], batched ESS deconvolution")
     ap.add_argument("--streams-total", type=int, default=8192, help="c4: streams of the whole job")
     ap.add_argument("--captures", type=int, default=256, help="c5: captures per batch (per GPU)")
+    ap.add_argument("--smoothing", action="store_true", help="c5: with the plug-in's default 3 x 1/13-octave smoothing (not the headline c5 line)")
     ap.add_argument("--sample-ms", type=float, default=20.0, help="period of the NVML clock / power sampler during the timed region")
     a = ap.parse_args()
     if a.workload == "c4":
@@ -751,7 +752,7 @@ def run_c5(args, R, eng):
     d_caps = torch.from_numpy(np.asarray(caps)).cuda()
     d_res = torch.empty_like(d_caps)
     for _ in range(max(3, args.warmup)):
-        eng.deconvolve_batch_device(d_caps.data_ptr(), nb, n, sweep, d_res.data_ptr(), SR, False)
+        eng.deconvolve_batch_device(d_caps.data_ptr(), nb, n, sweep, d_res.data_ptr(), SR, args.smoothing)
     sampler = ClockSampler(R.local, args.sample_ms * 1e-3)
     if R.rank == 0:
         sampler.start()
@@ -760,7 +761,7 @@ def run_c5(args, R, eng):
     dev_ms, wall = [], []
     t_all = time.perf_counter()
     for _ in range(args.steps):                            # captures and results resident in HBM
-        eng.deconvolve_batch_device(d_caps.data_ptr(), nb, n, sweep, d_res.data_ptr(), SR, False)
+        eng.deconvolve_batch_device(d_caps.data_ptr(), nb, n, sweep, d_res.data_ptr(), SR, args.smoothing)
         dev_ms.append(eng.last_compute_ms())
     R.barrier()
     t_all = R.max(time.perf_counter() - t_all)
@@ -769,11 +770,11 @@ def run_c5(args, R, eng):
     sampler.stop()
     res_dev = d_res.cpu().numpy()
     for _ in range(2):                                     # e2e: pinned host captures in, pinned host IRs out
-        eng.deconvolve_batch(caps, sweep, SR, False, out=res)
+        eng.deconvolve_batch(caps, sweep, SR, args.smoothing, out=res)
     R.barrier()
     for _ in range(3):
         t0 = time.perf_counter()
-        eng.deconvolve_batch(caps, sweep, SR, False, out=res)
+        eng.deconvolve_batch(caps, sweep, SR, args.smoothing, out=res)
         wall.append(time.perf_counter() - t0)
     same_bits = bool(np.array_equal(res_dev, np.asarray(res)))
     dev = R.max(float(np.mean(dev_ms))) * 1e-3
@@ -788,7 +789,7 @@ def run_c5(args, R, eng):
         import oracle
         ref = oracle.Reference() if oracle.have_reference() else oracle.Oracle()
         for j in sorted({0, nb // 2, nb - 1}):
-            want = ref.deconvolve(np.array(caps[j]), sweep, SR, False)[0]
+            want = ref.deconvolve(np.array(caps[j]), sweep, SR, args.smoothing)[0]
             fs = max(1.0, float(np.abs(want).max()))
             chk["captures"].append(j)
             chk["max_abs_over_full_scale"] = max(chk["max_abs_over_full_scale"], float(np.abs(res[j] - want).max()) / fs)
@@ -807,7 +808,7 @@ def run_c5(args, R, eng):
         line = {"metric": metric, "value": total / dev if ok else None, "unit": unit, "n_gpus": R.world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "configs[4]: %d captures per GPU of a 2^20-sample exponential sine sweep (+ room IR, + noise) deconvolved by spectral division, N = 2^20" % nb,
-                           "captures_per_gpu": nb, "fft_points": n, "value_kind": "irb_deconvolve_batch_device: captures and results resident in HBM, CUDA-event time of the whole call",
+                           "captures_per_gpu": nb, "fft_points": n, "smoothing": bool(args.smoothing), "value_kind": "irb_deconvolve_batch_device: captures and results resident in HBM, CUDA-event time of the whole call",
                            "l2_policy": "inputs larger than L2 (%.1f GB per batch)" % (nb * n * 4 / 1e9), "tuning": args.tune},
                 "roofline": {"bound": "hbm", "kernel": "k_line_fft<512> (columns) + k_rowpair<1024> (rows, divide, inverse rows) + k_line_fft<512,INV>: the batch's kernel time as a whole",
                              "achieved": alg / dev / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / dev / 1e9 / peak, "peak_source": peak_src,
