@@ -174,7 +174,8 @@ inline dim3 grid1(long long n, int batch) { return dim3((unsigned) ((n + 255) / 
 // the running sum and its chunking (irb_spectral.cuh), plus per-spectrum scratch
 struct Smoother {
     DevBuf la, rs, lo, hi, ops, endq, kstart;
-    int M = 0, n_ops = 0, nchunks = 0;
+    int M = 0, n_ops = 0, nchunks = 0, la_n = 0;
+    bool fused = false;
     int init(int M_, int batch, double octave_fraction, double sample_rate, int log_avg, cudaStream_t st) {
         M = M_;
         const double fract_per_side = octave_fraction / 2.0;
@@ -183,7 +184,11 @@ struct Smoother {
         const double c_side = pow(2.0, fract_per_side);
         if (!(octave_fraction >= 0.0) || !(freq_per_bin > 0.0) || c_side * (double) M > 1.0e9) return fail(IRB_ERR_ARG, "averagingFilter: octave fraction %g / sample rate %g out of range", octave_fraction, sample_rate);
         int rc;
-        if ((rc = la.alloc(sizeof(float) * (size_t) (M + 1) * batch, false)) || (rc = rs.alloc(sizeof(float) * (size_t) (M + 1) * batch, false)) ||
+        // la: the log amplitudes every pass starts from (the fused kernel keeps one array per pass); rs: the recorded sums of the per-pass kernels
+        fused = log_avg && irbh::g_tuning.avg_fused;
+        la_n = batch;
+        if ((rc = la.alloc(sizeof(float) * (size_t) (M + 1) * batch * (fused ? irb::kAvgMaxPasses : 1), false)) ||
+            (!fused && (rc = rs.alloc(sizeof(float) * (size_t) (M + 1) * batch, false))) ||
             (rc = lo.alloc(sizeof(int) * (size_t) (M + 1), false)) || (rc = hi.alloc(sizeof(int) * (size_t) (M + 1), false)))
             return rc;
         irb::k_avg_windows<<<grid1(M + 1, 1), 256, 0, st>>>(lo.as<int>(), hi.as<int>(), M, freq_per_bin, c_side);
@@ -209,6 +214,15 @@ struct Smoother {
         const long long stride = M + 1;
         irb::k_avg_prepare<<<grid1(M + 1, batch), 256, 0, st>>>(S, s_stride, la.as<float>(), stride, M, log_avg);
         LAUNCHED();
+        if (log_avg && fused && passes >= 1 && passes <= irb::kAvgMaxPasses && batch <= la_n) {
+            const int smem = passes * irb::kAvgPassSmemBytes;
+            CK(cudaFuncSetAttribute(irb::k_avg_passes, cudaFuncAttributeMaxDynamicSharedMemorySize, irb::kAvgMaxPasses * irb::kAvgPassSmemBytes));
+            irb::k_avg_passes<<<batch, passes * irb::kAvgPassThreads, smem, st>>>(S, s_stride, la.as<float>(), stride, stride * la_n, ops.as<int>(), endq.as<int>(), kstart.as<int>(),
+                                                                                 lo.as<int>(), hi.as<int>(), nchunks, n_ops, M, passes, include_phase, include_ampl);
+            LAUNCHED();
+            return 0;
+        }
+        if (fused) return fail(IRB_ERR_ARG, "averagingFilter: %d passes over %d spectra do not fit the plan made for %d", passes, batch, la_n);
         for (int i = 0; i < passes; ++i) {
             if (log_avg) irb::k_avg_scan<<<batch, 32 + irb::kAvgProducers, 0, st>>>(la.as<float>(), stride, ops.as<int>(), endq.as<int>(), kstart.as<int>(), nchunks, n_ops, rs.as<float>(), stride, M);
             else irb::k_avg_linear_sum<<<grid1(M + 1, batch), 256, 0, st>>>(la.as<float>(), stride, lo.as<int>(), hi.as<int>(), rs.as<float>(), stride, M);
@@ -296,8 +310,10 @@ int irb_convolve_nonperiodic(const float* x, int ch_x, int len_x, const float* h
 // out: [batch][N], N = nextPowerOfTwo(max(len_num, len_den))
 // The batch runs in sub-batches through a three-stage pipeline (upload i+1 | kernels i | download i-1) over
 // double-buffered device memory; a sub-batch is small enough for its intermediate spectra to stay in the L2.
+// device_io: captures and results lie in device memory, so the smoothed path reports irb_last_compute_ms() as the device span from its
+// first to its last kernel (groups overlap); from host buffers it is the sum of the kernel sections' spans, copies excluded.
 static int deconvolve_batch_staged(const float* nums, int batch, int len_num, const float* den, int len_den, double sample_rate, int smoothing, int include_phase,
-                                   int include_amplitude, float* out) {
+                                   int include_amplitude, float* out, bool device_io = false) {
     if (!nums || !den || !out) return fail(IRB_ERR_ARG, "null argument");
     if (batch < 1 || len_num < 1 || len_den < 1) return fail(IRB_ERR_ARG, "empty input");
     int N = 0, rc;
@@ -309,9 +325,12 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
     struct Slot { DevBuf dn, Zn, dy, dy2, tmp; cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr, t0 = nullptr, t1 = nullptr;
                   bool dn_busy = false, dy_busy = false, timed = false;
                   ~Slot() { for (cudaEvent_t e : {ev_in, ev_done, ev_out, t0, t1}) if (e) cudaEventDestroy(e); } } slot[2];
-    DevBuf dd, Zd, Bd, Sd, dtmp, Sall;
-    Smoother sm;
-    irbh::StreamGuard sg, sg_in, sg_out;                 // after every buffer: an early return drains the streams before the buffers return to the pool
+    // smoothing runs in up to kLanes groups of captures at once, each on its own compute stream with its own spectrum array and
+    // smoother, so that one group's transforms and copies run under another group's running sums
+    constexpr int kLanes = 4;
+    struct Lane { DevBuf Sall; Smoother sm; cudaEvent_t t0 = nullptr, t1 = nullptr; ~Lane() { for (cudaEvent_t e : {t0, t1}) if (e) cudaEventDestroy(e); } } lane[kLanes];
+    DevBuf dd, Zd, Bd, Sd, dtmp;
+    irbh::StreamGuard sg, sg_in, sg_out, sg_lane[kLanes - 1];   // after every buffer: an early return drains the streams before the buffers return to the pool
     if ((rc = sg.create()) || (rc = sg_in.create()) || (rc = sg_out.create())) return rc;
     cudaStream_t st = sg.s;
     const long long lne = (len_num + 1) & ~1LL, lde = (len_den + 1) & ~1LL;
@@ -319,11 +338,13 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
     const int sub_pref = irbh::g_tuning.deconv_sub;
     int sub = sub_pref > 0 ? sub_pref : (int) std::max<long long>(1, (48LL << 20) / ((long long) sizeof(float2) * M));
     sub = std::min(sub, batch);
-    // smoothing: the running sum is one sequential chain per capture and costs the same few milliseconds per pass for 1 or
-    // 500 captures, so a whole GROUP of captures (about 5 GB of spectra and sums) is smoothed at once, between a first phase
-    // (upload | forward transform, split, divide) and a last phase (merge, inverse transform | download) that both run in
-    // sub-batches with their copies overlapped.
-    const int grp = smoothing ? (int) std::min<long long>(batch, std::max<long long>(sub, (5LL << 30) / (16LL * (M + 1)))) : batch;
+    // smoothing: the running sum is one sequential chain per capture and costs the same few milliseconds for 1 or 500 captures,
+    // so a whole GROUP of captures is smoothed at once, between a first phase (upload | forward transform, split, divide) and a
+    // last phase (merge, inverse transform | download) that both run in sub-batches with their copies overlapped; the batch is
+    // cut into kLanes groups (more, in rounds, when a group would exceed about 1.5 GB of spectra and sums) that run side by side.
+    const int lanes_pref = irbh::g_tuning.deconv_groups > 0 ? std::min(irbh::g_tuning.deconv_groups, kLanes) : kLanes;
+    const int grp = smoothing ? (int) std::min<long long>(batch, std::max<long long>(sub, std::min<long long>((batch + lanes_pref - 1) / lanes_pref, (3LL << 29) / (20LL * (M + 1))))) : batch;
+    const int ngroups = (batch + grp - 1) / grp, nlanes = std::min(ngroups, lanes_pref);
     const bool fused = plan.big() && !smoothing;
     const float smooth_per_avg = 1.0 / 13.0;                                          // fp/convolution.cpp:390 (a float there)
     const int nslots = batch > sub ? 2 : 1;
@@ -339,9 +360,20 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
     }
     if ((rc = dd.alloc(sizeof(float) * lde, true)) || (rc = Zd.alloc(sizeof(float2) * (size_t) M, false)) || (rc = dtmp.alloc(sizeof(float2) * (size_t) M, false))) return rc;
     if (fused && (rc = Bd.alloc(sizeof(float2) * (size_t) M, false))) return rc;
-    if (smoothing && ((rc = Sd.alloc(sizeof(float2) * (size_t) (M + 1), false)) || (rc = Sall.alloc(sizeof(float2) * (size_t) (M + 1) * grp, false)) ||
-                      (rc = sm.init(M, grp, (double) smooth_per_avg, sample_rate, 1, st))))
-        return rc;
+    cudaStream_t lst[kLanes] = {st, st, st, st};
+    cudaEvent_t ev_den = nullptr, ev_join[kLanes] = {};
+    struct EvGuard { cudaEvent_t& d; cudaEvent_t* j; ~EvGuard() { if (d) cudaEventDestroy(d); for (int i = 0; i < kLanes; ++i) if (j[i]) cudaEventDestroy(j[i]); } } evg{ev_den, ev_join};
+    if (smoothing) {
+        if ((rc = Sd.alloc(sizeof(float2) * (size_t) (M + 1), false))) return rc;
+        CK(cudaEventCreateWithFlags(&ev_den, cudaEventDisableTiming));
+        for (int l = 0; l < nlanes; ++l) {
+            if (l && (rc = sg_lane[l - 1].create())) return rc;
+            if (l) lst[l] = sg_lane[l - 1].s;
+            if ((rc = lane[l].Sall.alloc(sizeof(float2) * (size_t) (M + 1) * grp, false)) || (rc = lane[l].sm.init(M, grp, (double) smooth_per_avg, sample_rate, 1, lst[l]))) return rc;
+            CK(cudaEventCreate(&lane[l].t0)); CK(cudaEventCreate(&lane[l].t1));
+            CK(cudaEventCreateWithFlags(&ev_join[l], cudaEventDisableTiming));
+        }
+    }
     irbh::set_last_compute_ms(0.0);
     // the denominator's spectrum, once
     CK(cudaMemcpyAsync(dd.p, den, sizeof(float) * len_den, cudaMemcpyDefault, st));
@@ -355,9 +387,6 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
         }
     }
     double total_ms = 0.0;
-    cudaEvent_t sm0 = nullptr, sm1 = nullptr;
-    struct EvGuard { cudaEvent_t& a; cudaEvent_t& b; ~EvGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg{sm0, sm1};
-    if (smoothing) { CK(cudaEventCreate(&sm0)); CK(cudaEventCreate(&sm1)); }
     auto collect = [&](Slot& q) -> int {          // kernel time of the section that last used this slot
         if (!q.timed) return 0;
         CK(cudaEventSynchronize(q.t1));
@@ -367,24 +396,24 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
         q.timed = false;
         return 0;
     };
-    // upload of a sub-batch into q.dn (after the kernels that last read it), and the compute stream waiting for it
-    auto upload = [&](Slot& q, int b0, int nb) -> int {
+    // upload of a sub-batch into q.dn (after the kernels that last used the slot), and the compute stream cs waiting for it
+    auto upload = [&](Slot& q, int b0, int nb, cudaStream_t cs) -> int {
         if (q.dn_busy) CK(cudaStreamWaitEvent(sg_in.s, q.ev_done, 0));
         CK(cudaMemcpy2DAsync(q.dn.p, sizeof(float) * lne, nums + (size_t) b0 * len_num, sizeof(float) * len_num, sizeof(float) * len_num, nb, cudaMemcpyDefault, sg_in.s));
         CK(cudaEventRecord(q.ev_in, sg_in.s));
-        CK(cudaStreamWaitEvent(st, q.ev_in, 0));
+        CK(cudaStreamWaitEvent(cs, q.ev_in, 0));
         return 0;
     };
     // inverse-transformed sub-batch in q.dy -> (half swap) -> host
-    auto download = [&](Slot& q, int b0, int nb) -> int {
+    auto download = [&](Slot& q, int b0, int nb, cudaStream_t cs) -> int {
         const float* res = q.dy.as<float>();
         if (!include_phase) {                                                        // ir::shifteroo, fp/convolution.cpp:400
-            irb::k_shifteroo<<<grid1(N, nb), 256, 0, st>>>(q.dy.as<float>(), q.dy2.as<float>(), N, N);
+            irb::k_shifteroo<<<grid1(N, nb), 256, 0, cs>>>(q.dy.as<float>(), q.dy2.as<float>(), N, N);
             LAUNCHED();
             res = q.dy2.as<float>();
         }
-        CK(cudaEventRecord(q.t1, st));
-        CK(cudaEventRecord(q.ev_done, st));
+        CK(cudaEventRecord(q.t1, cs));
+        CK(cudaEventRecord(q.ev_done, cs));
         CK(cudaStreamWaitEvent(sg_out.s, q.ev_done, 0));
         CK(cudaMemcpyAsync(out + (size_t) b0 * N, res, sizeof(float) * (size_t) N * nb, cudaMemcpyDefault, sg_out.s));
         CK(cudaEventRecord(q.ev_out, sg_out.s));
@@ -392,13 +421,12 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
         return 0;
     };
     int it = 0;
-    for (int g0 = 0; g0 < batch; g0 += grp) {
-        const int gn = std::min(grp, batch - g0);
-        for (int b0 = g0; b0 < g0 + gn; b0 += sub, ++it) {                           // first phase (the only one without smoothing)
+    if (!smoothing) {
+        for (int b0 = 0; b0 < batch; b0 += sub, ++it) {
             Slot& q = slot[it % nslots];
-            const int nb = std::min(sub, g0 + gn - b0);
-            if ((rc = collect(q)) || (rc = upload(q, b0, nb))) return rc;
-            if (!smoothing && q.dy_busy) CK(cudaStreamWaitEvent(st, q.ev_out, 0));   // the previous download has drained q.dy
+            const int nb = std::min(sub, batch - b0);
+            if ((rc = collect(q)) || (rc = upload(q, b0, nb, st))) return rc;
+            if (q.dy_busy) CK(cudaStreamWaitEvent(st, q.ev_out, 0));                  // the previous download has drained q.dy
             CK(cudaEventRecord(q.t0, st));
             q.timed = true;
             if (fused) {
@@ -407,46 +435,96 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
                     return rc;
             } else {
                 if ((rc = plan.run(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), M, q.tmp.as<float2>(), nb, false, 1.0f, st))) return rc;
-                if (!smoothing) {
-                    irb::k_spec_fused<true><<<grid1(M / 2 + 1, nb), 256, 0, st>>>(q.Zn.as<float2>(), M, Zd.as<float2>(), 0, q.Zn.as<float2>(), M, M, plan.WN);
-                    LAUNCHED();
-                    if ((rc = plan.run(q.Zn.p, M, -1, q.dy.as<float2>(), M, q.tmp.as<float2>(), nb, true, 1.0f / (float) N, st))) return rc;
-                } else {
-                    float2* Sg = Sall.as<float2>() + (size_t) (b0 - g0) * (M + 1);
-                    irb::k_spec_split<<<grid1(M + 1, nb), 256, 0, st>>>(q.Zn.as<float2>(), M, Sg, M + 1, M, 0, plan.WN);
-                    LAUNCHED();
-                    irb::k_spec_binop<true><<<grid1(M + 1, nb), 256, 0, st>>>(Sg, M + 1, Sd.as<float2>(), 0, M);
-                    LAUNCHED();
-                }
+                irb::k_spec_fused<true><<<grid1(M / 2 + 1, nb), 256, 0, st>>>(q.Zn.as<float2>(), M, Zd.as<float2>(), 0, q.Zn.as<float2>(), M, M, plan.WN);
+                LAUNCHED();
+                if ((rc = plan.run(q.Zn.p, M, -1, q.dy.as<float2>(), M, q.tmp.as<float2>(), nb, true, 1.0f / (float) N, st))) return rc;
             }
-            if (!smoothing) { if ((rc = download(q, b0, nb))) return rc; }
-            else { CK(cudaEventRecord(q.t1, st)); CK(cudaEventRecord(q.ev_done, st)); }
+            if ((rc = download(q, b0, nb, st))) return rc;
             q.dn_busy = true;
         }
-        if (!smoothing) continue;
-        CK(cudaEventRecord(sm0, st));
-        if ((rc = sm.run(Sall.as<float2>(), M + 1, gn, 3, 1, include_phase, include_amplitude, st))) return rc;
-        CK(cudaEventRecord(sm1, st));
-        for (int b0 = g0; b0 < g0 + gn; b0 += sub, ++it) {                           // last phase
-            Slot& q = slot[it % nslots];
-            const int nb = std::min(sub, g0 + gn - b0);
-            if ((rc = collect(q))) return rc;
-            if (q.dy_busy) CK(cudaStreamWaitEvent(st, q.ev_out, 0));
-            CK(cudaEventRecord(q.t0, st));
-            q.timed = true;
-            irb::k_spec_merge<<<grid1(M, nb), 256, 0, st>>>(Sall.as<float2>() + (size_t) (b0 - g0) * (M + 1), M + 1, q.Zn.as<float2>(), M, M, plan.WN);
-            LAUNCHED();
-            if ((rc = plan.run(q.Zn.p, M, -1, q.dy.as<float2>(), M, q.tmp.as<float2>(), nb, true, 1.0f / (float) N, st))) return rc;
-            if ((rc = download(q, b0, nb))) return rc;
+        CK(cudaStreamSynchronize(sg_out.s));
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < nslots; ++i) if ((rc = collect(slot[i]))) return rc;
+        irbh::set_last_compute_ms(total_ms);
+        return 0;
+    }
+    // ---- smoothing: groups of captures side by side, one lane (stream, spectrum array, smoother) each; rounds of nlanes groups ----
+    bool slot_used[2] = {false, false};
+    cudaEvent_t w0 = nullptr, w1 = nullptr;
+    struct WallGuard { cudaEvent_t& a; cudaEvent_t& b; ~WallGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } wall_guard{w0, w1};
+    CK(cudaEventCreate(&w0)); CK(cudaEventCreate(&w1));
+    CK(cudaEventRecord(w0, st));
+    CK(cudaEventRecord(ev_den, st));
+    for (int l = 1; l < nlanes; ++l) CK(cudaStreamWaitEvent(lst[l], ev_den, 0));     // the denominator's spectrum
+    for (int r0 = 0; r0 < ngroups; r0 += nlanes) {
+        const int rn = std::min(nlanes, ngroups - r0);
+        for (int l = 0; l < rn; ++l) {                                               // first phase and the running sums of every group of the round
+            const int g0 = (r0 + l) * grp, gn = std::min(grp, batch - g0);
+            cudaStream_t cs = lst[l];
+            if (r0) {                                                                // the lane's previous group: its kernel time, then the lane is free
+                CK(cudaEventSynchronize(lane[l].t1));
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, lane[l].t0, lane[l].t1));
+                total_ms += ms;
+            }
+            for (int b0 = g0; b0 < g0 + gn; b0 += sub, ++it) {
+                Slot& q = slot[it % nslots];
+                const int nb = std::min(sub, g0 + gn - b0);
+                if ((rc = collect(q))) return rc;
+                if (slot_used[it % nslots]) CK(cudaStreamWaitEvent(cs, q.ev_done, 0));  // another lane's kernels may have used the slot last
+                if ((rc = upload(q, b0, nb, cs))) return rc;
+                CK(cudaEventRecord(q.t0, cs));
+                q.timed = true;
+                if ((rc = plan.run(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), M, q.tmp.as<float2>(), nb, false, 1.0f, cs))) return rc;
+                float2* Sg = lane[l].Sall.as<float2>() + (size_t) (b0 - g0) * (M + 1);
+                irb::k_spec_split<<<grid1(M + 1, nb), 256, 0, cs>>>(q.Zn.as<float2>(), M, Sg, M + 1, M, 0, plan.WN);
+                LAUNCHED();
+                irb::k_spec_binop<true><<<grid1(M + 1, nb), 256, 0, cs>>>(Sg, M + 1, Sd.as<float2>(), 0, M);
+                LAUNCHED();
+                CK(cudaEventRecord(q.t1, cs));
+                CK(cudaEventRecord(q.ev_done, cs));
+                q.dn_busy = true;
+                slot_used[it % nslots] = true;
+            }
+            CK(cudaEventRecord(lane[l].t0, cs));
+            if ((rc = lane[l].sm.run(lane[l].Sall.as<float2>(), M + 1, gn, 3, 1, include_phase, include_amplitude, cs))) return rc;
+            CK(cudaEventRecord(lane[l].t1, cs));
         }
-        CK(cudaEventSynchronize(sm1));
+        for (int l = 0; l < rn; ++l) {                                               // last phase
+            const int g0 = (r0 + l) * grp, gn = std::min(grp, batch - g0);
+            cudaStream_t cs = lst[l];
+            for (int b0 = g0; b0 < g0 + gn; b0 += sub, ++it) {
+                Slot& q = slot[it % nslots];
+                const int nb = std::min(sub, g0 + gn - b0);
+                if ((rc = collect(q))) return rc;
+                CK(cudaStreamWaitEvent(cs, q.ev_done, 0));
+                if (q.dy_busy) CK(cudaStreamWaitEvent(cs, q.ev_out, 0));
+                CK(cudaEventRecord(q.t0, cs));
+                q.timed = true;
+                irb::k_spec_merge<<<grid1(M, nb), 256, 0, cs>>>(lane[l].Sall.as<float2>() + (size_t) (b0 - g0) * (M + 1), M + 1, q.Zn.as<float2>(), M, M, plan.WN);
+                LAUNCHED();
+                if ((rc = plan.run(q.Zn.p, M, -1, q.dy.as<float2>(), M, q.tmp.as<float2>(), nb, true, 1.0f / (float) N, cs))) return rc;
+                if ((rc = download(q, b0, nb, cs))) return rc;
+            }
+        }
+    }
+    for (int l = 1; l < nlanes; ++l) { CK(cudaEventRecord(ev_join[l], lst[l])); CK(cudaStreamWaitEvent(st, ev_join[l], 0)); }
+    CK(cudaEventRecord(ev_join[0], sg_out.s)); CK(cudaStreamWaitEvent(st, ev_join[0], 0));
+    CK(cudaEventRecord(w1, st));
+    CK(cudaStreamSynchronize(sg_out.s));
+    for (int l = 0; l < nlanes; ++l) CK(cudaStreamSynchronize(lst[l]));
+    for (int i = 0; i < nslots; ++i) if ((rc = collect(slot[i]))) return rc;
+    if (device_io) {
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, sm0, sm1));
+        CK(cudaEventElapsedTime(&ms, w0, w1));
+        irbh::set_last_compute_ms((double) ms);
+        return 0;
+    }
+    for (int l = 0; l < std::min(nlanes, ngroups); ++l) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, lane[l].t0, lane[l].t1));
         total_ms += ms;
     }
-    CK(cudaStreamSynchronize(sg_out.s));
-    CK(cudaStreamSynchronize(st));
-    for (int i = 0; i < nslots; ++i) if ((rc = collect(slot[i]))) return rc;
     irbh::set_last_compute_ms(total_ms);
     return 0;
 }
@@ -472,7 +550,7 @@ int irb_deconvolve_batch_device(const float* nums_dev, int batch, int len_num, c
     Plan plan;
     if ((rc = plan.init(dev, M))) return rc;
     if (!(plan.big() && !smoothing && include_phase && len_num % 2 == 0))
-        return deconvolve_batch_staged(nums_dev, batch, len_num, den, len_den, sample_rate, smoothing, include_phase, include_amplitude, out_dev);
+        return deconvolve_batch_staged(nums_dev, batch, len_num, den, len_den, sample_rate, smoothing, include_phase, include_amplitude, out_dev, true);
     constexpr int kStreams = 3;
     const int sub_pref = irbh::g_tuning.deconv_sub;
     int sub = sub_pref > 0 ? sub_pref : (int) std::max<long long>(1, (32LL << 20) / ((long long) sizeof(float2) * M));      // about 32 MB of spectra per sub-batch

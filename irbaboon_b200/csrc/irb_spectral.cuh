@@ -503,23 +503,153 @@ static __global__ void k_avg_linear_sum(const float* la, long long la_stride, co
     rs[blockIdx.y * rs_stride + k] = sum;
 }
 // (3) new amplitude = exp(sum / window length), bins rebuilt from it and the original phase (fp/convolution.cpp:518-543)
+// returns the rebuilt bin; shared by the per-pass kernel and the fused three-pass kernel so both execute the same arithmetic
+__device__ __forceinline__ float2 avg_rebuild_bin(float2 v, float sum, int lo_k, int hi_k, int log_avg, int include_phase, int include_ampl) {
+    const double len = (double) (hi_k - lo_k) + 1.0;
+    float ampl = (float) ((double) sum / len);
+    if (log_avg) ampl = expf(ampl);
+    ampl = round_1e16(ampl);
+    const float re = round_to_zero(v.x, 1e-11f), im = round_to_zero(v.y, 1e-11f);
+    float phase = atan2f(im, re);
+    if (!include_ampl) ampl = 1.0f;
+    if (!include_phase) phase = 0.0f;
+    return make_float2(ampl * cosf(phase), ampl * sinf(phase));
+}
 // next_la != nullptr: also the log amplitudes of the rebuilt bins, i.e. the next pass's step (1)
 static __global__ void k_avg_apply(float2* S, long long s_stride, const float* rs, long long rs_stride, const int* lo, const int* hi, int M, int log_avg,
                             int include_phase, int include_ampl, float* next_la, long long la_stride) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > M) return;
     float2* s = S + blockIdx.y * s_stride;
-    const double len = (double) (hi[k] - lo[k]) + 1.0;
-    float ampl = (float) ((double) rs[blockIdx.y * rs_stride + k] / len);
-    if (log_avg) ampl = expf(ampl);
-    ampl = round_1e16(ampl);
-    const float re = round_to_zero(s[k].x, 1e-11f), im = round_to_zero(s[k].y, 1e-11f);
-    float phase = atan2f(im, re);
-    if (!include_ampl) ampl = 1.0f;
-    if (!include_phase) phase = 0.0f;
-    const float2 nv = make_float2(ampl * cosf(phase), ampl * sinf(phase));
+    const float2 nv = avg_rebuild_bin(s[k], rs[blockIdx.y * rs_stride + k], lo[k], hi[k], log_avg, include_phase, include_ampl);
     s[k] = nv;
     if (next_la) next_la[blockIdx.y * la_stride + k] = avg_log_ampl(nv, log_avg);
+}
+
+// All passes of the log average in ONE launch.  Pass p + 1 needs the rebuilt bins of pass p only up to the upper window edge
+// hi[k] ~ 1.027 k of the bin it is working on, so the passes run as a wavefront inside one CTA per spectrum: each pass has its own
+// chain warp (lane 0 carries the dependent FADD sequence, as in k_avg_scan) and its own 128 producer threads, which gather the
+// operands of the pass's next chunk, rebuild the bins the previous chunk recorded (step 3) and publish, in shared memory, how far
+// the pass has got; the next pass's producers wait on that mark before they gather.  Three passes cost one pass plus 3 % instead
+// of three chain traversals and six elementwise kernels.  Same additions in the same order, same per-bin arithmetic.
+constexpr int kAvgMaxPasses = 3;
+constexpr int kAvgPassThreads = 32 + kAvgProducers;
+constexpr int kAvgPassSmemBytes = 4 * kAvgChunk * (int) sizeof(float);
+__device__ __forceinline__ void avg_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+static __global__ void __launch_bounds__(kAvgMaxPasses * kAvgPassThreads, 2)
+k_avg_passes(float2* S, long long s_stride, float* la, long long la_stride, long long la_pass_stride, const int* __restrict__ ops, const int* __restrict__ endq,
+             const int* __restrict__ kstart, const int* __restrict__ lo, const int* __restrict__ hi, int nchunks, int n_ops, int M, int passes, int include_phase,
+             int include_ampl) {
+    extern __shared__ __align__(16) unsigned char avg_raw[];
+    __shared__ volatile int applied[kAvgMaxPasses];                        // bins [0, applied[p]) of pass p are rebuilt and visible
+    if (threadIdx.x < kAvgMaxPasses) applied[threadIdx.x] = 0;
+    __syncthreads();
+    const int pass = threadIdx.x / kAvgPassThreads, tid = threadIdx.x % kAvgPassThreads, ptid = tid - 32;
+    if (pass >= passes) return;
+    float* mine = reinterpret_cast<float*>(avg_raw) + (size_t) pass * 4 * kAvgChunk;
+    auto s_val = [&](int c) { return mine + (c & 1) * kAvgChunk; };
+    auto s_sum = [&](int c) { return mine + (2 + (c & 1)) * kAvgChunk; };
+    const float* a = la + pass * la_pass_stride + blockIdx.x * la_stride;
+    float* a_next = pass + 1 < passes ? la + (pass + 1) * la_pass_stride + blockIdx.x * la_stride : nullptr;
+    float2* s = S + blockIdx.x * s_stride;
+    const float log_floor = logf(1e-16f);
+    constexpr int PER = kAvgChunk / kAvgProducers;
+    auto wait_for_previous_pass = [&](int c) {                             // every bin the operations of chunk c add is rebuilt
+        if (pass == 0) return;
+        int kn = __ldg(kstart + c + 1);
+        kn = kn < M ? kn : M;
+        int need = __ldg(hi + kn);
+        need = need < M ? need : M;
+        while (applied[pass - 1] <= need) __nanosleep(64);
+        __threadfence_block();
+    };
+    auto fill = [&](int c) {
+        float* dst = s_val(c);
+        const int j0 = c * kAvgChunk;
+        int code[PER];
+        float val[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int g = j0 + ptid + i * kAvgProducers;
+            code[i] = __ldg(ops + (g < n_ops ? g : n_ops - 1));
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int b = code[i] < 0 ? ~code[i] : code[i];
+            val[i] = a[b <= M ? b : 0];
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int g = j0 + ptid + i * kAvgProducers;
+            const int b = code[i] < 0 ? ~code[i] : code[i];
+            float v = b <= M ? val[i] : (b < 2 * M ? log_floor : 0.0f);
+            v = code[i] < 0 ? -v : v;
+            dst[ptid + i * kAvgProducers] = g < n_ops ? v : 0.0f;
+        }
+    };
+    auto rebuild = [&](int c) {                                            // step (3) for the bins chunk c recorded
+        const float* src = s_sum(c);
+        const int j0 = c * kAvgChunk, k0 = __ldg(kstart + c), k1 = __ldg(kstart + c + 1);
+        for (int kb = k0; kb < k1; kb += 4 * kAvgProducers) {
+            int e[4], l[4], h[4];
+            float2 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = kb + ptid + i * kAvgProducers, kk = k < k1 ? k : k0;
+                e[i] = __ldg(endq + kk); l[i] = __ldg(lo + kk); h[i] = __ldg(hi + kk);
+                v[i] = s[kk];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = kb + ptid + i * kAvgProducers;
+                if (k < k1) {
+                    const float2 nv = avg_rebuild_bin(v[i], src[e[i] - j0], l[i], h[i], 1, include_phase, include_ampl);
+                    s[k] = nv;
+                    if (a_next) a_next[k] = avg_log_ampl(nv, 1);
+                }
+            }
+        }
+        __threadfence_block();
+        avg_bar(1 + kAvgMaxPasses + pass, kAvgProducers);                  // the pass's producers only
+        if (ptid == 0) applied[pass] = k1;
+    };
+    if (tid >= 32) { wait_for_previous_pass(0); fill(0); }
+    avg_bar(1 + pass, kAvgPassThreads);
+    float running = 0.0f;
+    for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0) {
+            // operands are fetched 16 operations ahead so that the chain never waits for shared memory
+            const float4* v4 = reinterpret_cast<const float4*>(s_val(c));
+            float4* p4 = reinterpret_cast<float4*>(s_sum(c));
+            constexpr int D = 4;
+            float4 cur[D], nxt[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) cur[i] = v4[i];
+#pragma unroll 1
+            for (int j = 0; j < kAvgChunk / 4; j += D) {
+                if (j + D < kAvgChunk / 4) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) nxt[i] = v4[j + D + i];
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    float4 p;
+                    running += cur[i].x; p.x = running;
+                    running += cur[i].y; p.y = running;
+                    running += cur[i].z; p.z = running;
+                    running += cur[i].w; p.w = running;
+                    p4[j + i] = p;
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) cur[i] = nxt[i];
+            }
+        } else if (tid >= 32) {
+            if (c >= 1) rebuild(c - 1);
+            if (c + 1 < nchunks) { wait_for_previous_pass(c + 1); fill(c + 1); }
+        }
+        avg_bar(1 + pass, kAvgPassThreads);
+    }
+    if (tid >= 32) rebuild(nchunks - 1);
 }
 
 // out[i] = in[(i + h1) mod n] : ir::shifteroo (fp/ir.cpp:85-103), h1 = ceil(n/2)

@@ -139,6 +139,25 @@ def test_deconvolve_smoothed(eng, orc, n):
     _check(got, want)
 
 
+@pytest.mark.parametrize("n,flags", [(4096, (True, True)), (1 << 15, (True, True)), (1 << 15, (False, True)), (1 << 17, (True, True))])
+def test_smoothing_wavefront_launch_equals_the_per_pass_kernels_bit_for_bit(eng, orc, n, flags):
+    """All three smoothing passes in one launch (k_avg_passes, passes running as a wavefront inside a CTA) execute the same
+    additions in the same order and the same per-bin arithmetic as one k_avg_scan + k_avg_apply per pass."""
+    sweep, h, cap = _capture(orc, n, n // 8, 3)
+    caps = np.stack([cap * np.float32(0.25 + 0.5 * j) + synth.white_noise(1200 + j, 0, n) * np.float32(1e-3) for j in range(5)])
+    got = eng.deconvolve_batch(caps, sweep, 48000.0, True, *flags)
+    spec = orc.fft_transform(cap[:4096] if n > 4096 else cap)
+    one = eng.averaging_filter(spec, 1.0 / 13.0, 48000.0, True, *flags)
+    try:
+        eng.set_tuning("avg_fused", 0)
+        want = eng.deconvolve_batch(caps, sweep, 48000.0, True, *flags)
+        one_want = eng.averaging_filter(spec, 1.0 / 13.0, 48000.0, True, *flags)
+    finally:
+        eng.set_tuning("avg_fused", 1)
+    assert np.array_equal(got, want) and np.array_equal(one, one_want)
+    assert np.isfinite(got).all() and np.abs(got).max() > 0
+
+
 def test_deconvolve_batch_equals_singles(eng, orc):
     n = 8192
     sweep, _, _ = _capture(orc, n, 100, 0)
