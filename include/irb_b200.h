@@ -117,7 +117,8 @@ int irb_engine_submit(irb_engine* e, const float* in_host, float* out_host, int 
 int irb_engine_wait(irb_engine* e);
 
 /* Per-step device timing with CUDA events on the engine's stream: whole block step (k_fwd + k_mac) and the
- * FDL-MAC kernel alone.  set_timing(1) clears the record; get_timings returns the number of steps copied. */
+ * FDL-MAC kernel alone (on a one-launch block step the two are the same pair of events: no event is recorded in between).
+ * set_timing(1) clears the record; get_timings returns the number of steps copied. */
 int irb_engine_set_timing(irb_engine* e, int enable);
 int irb_engine_get_timings(irb_engine* e, float* step_ms, float* mac_ms, int max_steps);
 

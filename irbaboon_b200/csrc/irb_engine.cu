@@ -386,6 +386,7 @@ struct irb_engine {
     // optional per-step device timing: events before k_fwd, before k_mac, after k_mac
     bool timing = false;
     std::vector<cudaEvent_t> tev;
+    std::vector<char> tev_mid;                           // step i recorded its middle event (a kernel ran before the MAC launch)
     int t_rec = 0;
     std::vector<cudaEvent_t> ev_grp;                 // single large block: per channel group "uploaded" / "computed"
     unsigned long long pipe_seq = 0;                 // blocks that went through the multi-block pipeline (staging slot = seq & 1)
@@ -529,9 +530,13 @@ int engine_step_device(irb_engine* e, const float* in_dev, float* out_dev) {
     const bool rec = e->timing && e->t_rec < kTimingCap;
     if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec], e->stream));
     const bool fused = step_is_fused(e);
+    const long long launched = g_launches.load();
     int rc = engine_launch_fwd(e, in_dev, !fused, true, 0, e->active);
     if (rc) return rc;
-    if (rec) CK(cudaEventRecord(e->tev[3 * e->t_rec + 1], e->stream));
+    // the middle event only where a kernel ran before the MAC launch: on a one-launch step it would add its own 2-3 us to the step
+    const bool mid = rec && g_launches.load() != launched;
+    if (rec) e->tev_mid[e->t_rec] = mid;
+    if (mid) CK(cudaEventRecord(e->tev[3 * e->t_rec + 1], e->stream));
     if ((rc = engine_launch_mac(e, out_dev, 0, fused ? in_dev : nullptr, 0, e->active))) return rc;
     if (rec) { CK(cudaEventRecord(e->tev[3 * e->t_rec + 2], e->stream)); e->t_rec++; }
     return 0;
@@ -983,6 +988,7 @@ int irb_engine_set_timing(irb_engine* e, int enable) {
     CK(cudaStreamSynchronize(e->stream));
     if (enable && e->tev.empty()) {
         e->tev.resize(3 * (size_t) kTimingCap, nullptr);
+        e->tev_mid.assign((size_t) kTimingCap, 0);
         for (auto& ev : e->tev) CK(cudaEventCreate(&ev));
     }
     e->timing = enable != 0;
@@ -997,7 +1003,7 @@ int irb_engine_get_timings(irb_engine* e, float* step_ms, float* mac_ms, int max
     const int n = e->t_rec < max_steps ? e->t_rec : max_steps;
     for (int i = 0; i < n; ++i) {
         if (step_ms) CK(cudaEventElapsedTime(step_ms + i, e->tev[3 * i], e->tev[3 * i + 2]));
-        if (mac_ms) CK(cudaEventElapsedTime(mac_ms + i, e->tev[3 * i + 1], e->tev[3 * i + 2]));
+        if (mac_ms) CK(cudaEventElapsedTime(mac_ms + i, e->tev[3 * i + (e->tev_mid[i] ? 1 : 0)], e->tev[3 * i + 2]));
     }
     return n;
 }
