@@ -59,7 +59,7 @@ int* tuning_field(const char* name) {
     irbh::Tuning& t = irbh::g_tuning;
     struct { const char* n; int* p; } tab[] = {
         {"mac_persistent", &t.mac_persistent}, {"fuse_split", &t.fuse_split}, {"mac_tma", &t.mac_tma}, {"mac_wide", &t.mac_wide}, {"mac_u", &t.mac_u}, {"fdl_plain", &t.fdl_plain},
-        {"producer_sleep_ns", &t.producer_sleep_ns}, {"no_graph", &t.no_graph}, {"deconv_sub", &t.deconv_sub}, {"deconv_streams", &t.deconv_streams}, {"avg_fused", &t.avg_fused}, {"deconv_groups", &t.deconv_groups}, {"release_fence", &t.release_fence}, {"release_dep", &t.release_dep},
+        {"producer_sleep_ns", &t.producer_sleep_ns}, {"no_graph", &t.no_graph}, {"deconv_sub", &t.deconv_sub}, {"deconv_streams", &t.deconv_streams}, {"avg_fused", &t.avg_fused}, {"deconv_groups", &t.deconv_groups}, {"deconv_group_cap", &t.deconv_group_cap}, {"release_fence", &t.release_fence}, {"release_dep", &t.release_dep},
         {"persistent_ctas", &t.persistent_ctas}, {"unit_narrowing", &t.unit_narrowing}, {"ir_replicas", &t.ir_replicas}, {"stagger_ns", &t.stagger_ns}, {"ring_stages", &t.ring_stages}};
     if (name) for (auto& e : tab) if (!strcmp(e.n, name)) return e.p;
     return nullptr;

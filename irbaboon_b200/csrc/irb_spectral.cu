@@ -324,11 +324,18 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
     if ((rc = plan.init(dev, M))) return rc;
     struct Slot { DevBuf dn, Zn, dy, dy2, tmp; cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr, t0 = nullptr, t1 = nullptr;
                   bool dn_busy = false, dy_busy = false, timed = false;
-                  ~Slot() { for (cudaEvent_t e : {ev_in, ev_done, ev_out, t0, t1}) if (e) cudaEventDestroy(e); } } slot[2];
+                  ~Slot() { for (cudaEvent_t e : {ev_in, ev_done, ev_out, t0, t1}) if (e) cudaEventDestroy(e); } } slot[4];   // [2], [3]: the smoothing path's last phase
     // smoothing runs in up to kLanes groups of captures at once, each on its own compute stream with its own spectrum array and
     // smoother, so that one group's transforms and copies run under another group's running sums
     constexpr int kLanes = 4;
-    struct Lane { DevBuf Sall; Smoother sm; cudaEvent_t t0 = nullptr, t1 = nullptr; ~Lane() { for (cudaEvent_t e : {t0, t1}) if (e) cudaEventDestroy(e); } } lane[kLanes];
+    struct Lane { DevBuf Sall; Smoother sm; } lane[kLanes];
+    struct Spans {                                       // one pair of timing events per kernel section, read back when everything has drained
+        std::vector<cudaEvent_t> ev;
+        ~Spans() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+        int open(cudaStream_t s) { cudaEvent_t e0 = nullptr, e1 = nullptr; CK(cudaEventCreate(&e0)); ev.push_back(e0); CK(cudaEventCreate(&e1)); ev.push_back(e1); CK(cudaEventRecord(e0, s)); return 0; }
+        int close(cudaStream_t s) { CK(cudaEventRecord(ev.back(), s)); return 0; }
+        int total(double* ms) { *ms = 0.0; for (size_t i = 0; i + 1 < ev.size(); i += 2) { float t = 0.f; CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1])); *ms += t; } return 0; }
+    } spans;
     DevBuf dd, Zd, Bd, Sd, dtmp;
     irbh::StreamGuard sg, sg_in, sg_out, sg_lane[kLanes - 1];   // after every buffer: an early return drains the streams before the buffers return to the pool
     if ((rc = sg.create()) || (rc = sg_in.create()) || (rc = sg_out.create())) return rc;
@@ -343,18 +350,20 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
     // last phase (merge, inverse transform | download) that both run in sub-batches with their copies overlapped; the batch is
     // cut into kLanes groups (more, in rounds, when a group would exceed about 1.5 GB of spectra and sums) that run side by side.
     const int lanes_pref = irbh::g_tuning.deconv_groups > 0 ? std::min(irbh::g_tuning.deconv_groups, kLanes) : kLanes;
-    const int grp = smoothing ? (int) std::min<long long>(batch, std::max<long long>(sub, std::min<long long>((batch + lanes_pref - 1) / lanes_pref, (3LL << 29) / (20LL * (M + 1))))) : batch;
+    const long long grp_cap = irbh::g_tuning.deconv_group_cap > 0 ? irbh::g_tuning.deconv_group_cap : (3LL << 29) / (20LL * (M + 1));
+    const int grp = smoothing ? (int) std::min<long long>(batch, std::max<long long>(sub, std::min<long long>((batch + lanes_pref - 1) / lanes_pref, grp_cap))) : batch;
     const int ngroups = (batch + grp - 1) / grp, nlanes = std::min(ngroups, lanes_pref);
     const bool fused = plan.big() && !smoothing;
     const float smooth_per_avg = 1.0 / 13.0;                                          // fp/convolution.cpp:390 (a float there)
     const int nslots = batch > sub ? 2 : 1;
-    for (int i = 0; i < nslots; ++i) {
-        Slot& q = slot[i];
-        if ((rc = q.dn.alloc(sizeof(float) * lne * sub, true)) || (rc = q.Zn.alloc(sizeof(float2) * (size_t) M * sub, false)) ||
-            (rc = q.dy.alloc(sizeof(float2) * (size_t) M * sub, false)))
+    for (int i = 0; i < (smoothing ? 2 * nslots : nslots); ++i) {
+        Slot& q = slot[i < nslots ? i : 2 + (i - nslots)];
+        const bool first = i < nslots, last = !smoothing || !first;                // which phase(s) of the pipeline the slot serves
+        if ((first && (rc = q.dn.alloc(sizeof(float) * lne * sub, true))) || (rc = q.Zn.alloc(sizeof(float2) * (size_t) M * sub, false)) ||
+            (last && (rc = q.dy.alloc(sizeof(float2) * (size_t) M * sub, false))))
             return rc;
         if (!fused && (rc = q.tmp.alloc(sizeof(float2) * (size_t) M * sub, false))) return rc;
-        if (!include_phase && (rc = q.dy2.alloc(sizeof(float) * (size_t) N * sub, false))) return rc;
+        if (last && !include_phase && (rc = q.dy2.alloc(sizeof(float) * (size_t) N * sub, false))) return rc;
         CK(cudaEventCreateWithFlags(&q.ev_in, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&q.ev_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&q.ev_out, cudaEventDisableTiming)); CK(cudaEventCreate(&q.t0)); CK(cudaEventCreate(&q.t1));
     }
@@ -370,7 +379,6 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
             if (l && (rc = sg_lane[l - 1].create())) return rc;
             if (l) lst[l] = sg_lane[l - 1].s;
             if ((rc = lane[l].Sall.alloc(sizeof(float2) * (size_t) (M + 1) * grp, false)) || (rc = lane[l].sm.init(M, grp, (double) smooth_per_avg, sample_rate, 1, lst[l]))) return rc;
-            CK(cudaEventCreate(&lane[l].t0)); CK(cudaEventCreate(&lane[l].t1));
             CK(cudaEventCreateWithFlags(&ev_join[l], cudaEventDisableTiming));
         }
     }
@@ -412,7 +420,8 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
             LAUNCHED();
             res = q.dy2.as<float>();
         }
-        CK(cudaEventRecord(q.t1, cs));
+        if (smoothing) { int rc2 = spans.close(cs); if (rc2) return rc2; }
+        else CK(cudaEventRecord(q.t1, cs));
         CK(cudaEventRecord(q.ev_done, cs));
         CK(cudaStreamWaitEvent(sg_out.s, q.ev_done, 0));
         CK(cudaMemcpyAsync(out + (size_t) b0 * N, res, sizeof(float) * (size_t) N * nb, cudaMemcpyDefault, sg_out.s));
@@ -448,63 +457,57 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
         irbh::set_last_compute_ms(total_ms);
         return 0;
     }
-    // ---- smoothing: groups of captures side by side, one lane (stream, spectrum array, smoother) each; rounds of nlanes groups ----
-    bool slot_used[2] = {false, false};
+    // ---- smoothing: groups of captures side by side, one lane (stream, spectrum array, smoother) each; rounds of nlanes groups.
+    // Nothing below blocks the host: the first phase and the last phase have their own staging slots, slot and lane reuse is ordered by
+    // events on the device, and the kernel sections' timing events are read when everything has drained -- so the downloads of the first
+    // group start as soon as its running sums are done, under the uploads of the later groups. ----
+    bool slot_used[4] = {false, false, false, false};
     cudaEvent_t w0 = nullptr, w1 = nullptr;
     struct WallGuard { cudaEvent_t& a; cudaEvent_t& b; ~WallGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } wall_guard{w0, w1};
     CK(cudaEventCreate(&w0)); CK(cudaEventCreate(&w1));
     CK(cudaEventRecord(w0, st));
     CK(cudaEventRecord(ev_den, st));
     for (int l = 1; l < nlanes; ++l) CK(cudaStreamWaitEvent(lst[l], ev_den, 0));     // the denominator's spectrum
+    int it_last = 0;
     for (int r0 = 0; r0 < ngroups; r0 += nlanes) {
         const int rn = std::min(nlanes, ngroups - r0);
         for (int l = 0; l < rn; ++l) {                                               // first phase and the running sums of every group of the round
             const int g0 = (r0 + l) * grp, gn = std::min(grp, batch - g0);
             cudaStream_t cs = lst[l];
-            if (r0) {                                                                // the lane's previous group: its kernel time, then the lane is free
-                CK(cudaEventSynchronize(lane[l].t1));
-                float ms = 0.f;
-                CK(cudaEventElapsedTime(&ms, lane[l].t0, lane[l].t1));
-                total_ms += ms;
-            }
             for (int b0 = g0; b0 < g0 + gn; b0 += sub, ++it) {
-                Slot& q = slot[it % nslots];
+                const int qi = it % nslots;
+                Slot& q = slot[qi];
                 const int nb = std::min(sub, g0 + gn - b0);
-                if ((rc = collect(q))) return rc;
-                if (slot_used[it % nslots]) CK(cudaStreamWaitEvent(cs, q.ev_done, 0));  // another lane's kernels may have used the slot last
-                if ((rc = upload(q, b0, nb, cs))) return rc;
-                CK(cudaEventRecord(q.t0, cs));
-                q.timed = true;
+                if (slot_used[qi]) CK(cudaStreamWaitEvent(cs, q.ev_done, 0));          // another lane's kernels may have used the slot last
+                if ((rc = upload(q, b0, nb, cs)) || (rc = spans.open(cs))) return rc;
                 if ((rc = plan.run(q.dn.p, lne / 2, len_num, q.Zn.as<float2>(), M, q.tmp.as<float2>(), nb, false, 1.0f, cs))) return rc;
                 float2* Sg = lane[l].Sall.as<float2>() + (size_t) (b0 - g0) * (M + 1);
                 irb::k_spec_split<<<grid1(M + 1, nb), 256, 0, cs>>>(q.Zn.as<float2>(), M, Sg, M + 1, M, 0, plan.WN);
                 LAUNCHED();
                 irb::k_spec_binop<true><<<grid1(M + 1, nb), 256, 0, cs>>>(Sg, M + 1, Sd.as<float2>(), 0, M);
                 LAUNCHED();
-                CK(cudaEventRecord(q.t1, cs));
+                if ((rc = spans.close(cs))) return rc;
                 CK(cudaEventRecord(q.ev_done, cs));
                 q.dn_busy = true;
-                slot_used[it % nslots] = true;
+                slot_used[qi] = true;
             }
-            CK(cudaEventRecord(lane[l].t0, cs));
-            if ((rc = lane[l].sm.run(lane[l].Sall.as<float2>(), M + 1, gn, 3, 1, include_phase, include_amplitude, cs))) return rc;
-            CK(cudaEventRecord(lane[l].t1, cs));
+            if ((rc = spans.open(cs)) || (rc = lane[l].sm.run(lane[l].Sall.as<float2>(), M + 1, gn, 3, 1, include_phase, include_amplitude, cs)) || (rc = spans.close(cs))) return rc;
         }
         for (int l = 0; l < rn; ++l) {                                               // last phase
             const int g0 = (r0 + l) * grp, gn = std::min(grp, batch - g0);
             cudaStream_t cs = lst[l];
-            for (int b0 = g0; b0 < g0 + gn; b0 += sub, ++it) {
-                Slot& q = slot[it % nslots];
+            for (int b0 = g0; b0 < g0 + gn; b0 += sub, ++it_last) {
+                const int qi = 2 + it_last % nslots;
+                Slot& q = slot[qi];
                 const int nb = std::min(sub, g0 + gn - b0);
-                if ((rc = collect(q))) return rc;
-                CK(cudaStreamWaitEvent(cs, q.ev_done, 0));
+                if (slot_used[qi]) CK(cudaStreamWaitEvent(cs, q.ev_done, 0));
                 if (q.dy_busy) CK(cudaStreamWaitEvent(cs, q.ev_out, 0));
-                CK(cudaEventRecord(q.t0, cs));
-                q.timed = true;
+                if ((rc = spans.open(cs))) return rc;
                 irb::k_spec_merge<<<grid1(M, nb), 256, 0, cs>>>(lane[l].Sall.as<float2>() + (size_t) (b0 - g0) * (M + 1), M + 1, q.Zn.as<float2>(), M, M, plan.WN);
                 LAUNCHED();
                 if ((rc = plan.run(q.Zn.p, M, -1, q.dy.as<float2>(), M, q.tmp.as<float2>(), nb, true, 1.0f / (float) N, cs))) return rc;
-                if ((rc = download(q, b0, nb, cs))) return rc;
+                if ((rc = download(q, b0, nb, cs))) return rc;                        // closes the section
+                slot_used[qi] = true;
             }
         }
     }
@@ -513,18 +516,13 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
     CK(cudaEventRecord(w1, st));
     CK(cudaStreamSynchronize(sg_out.s));
     for (int l = 0; l < nlanes; ++l) CK(cudaStreamSynchronize(lst[l]));
-    for (int i = 0; i < nslots; ++i) if ((rc = collect(slot[i]))) return rc;
     if (device_io) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, w0, w1));
         irbh::set_last_compute_ms((double) ms);
         return 0;
     }
-    for (int l = 0; l < std::min(nlanes, ngroups); ++l) {
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, lane[l].t0, lane[l].t1));
-        total_ms += ms;
-    }
+    if ((rc = spans.total(&total_ms))) return rc;
     irbh::set_last_compute_ms(total_ms);
     return 0;
 }

@@ -18,6 +18,7 @@ struct Tuning {
     int deconv_sub = 0;          // captures per sub-batch of irb_deconvolve_batch (0: about 48 MB of spectra)
     int avg_fused = 1;           // log-average smoothing: all passes in one wavefront launch (0: one scan + one rebuild kernel per pass)
     int deconv_groups = 0;       // smoothed batch deconvolution: groups of captures smoothed side by side (0: four)
+    int deconv_group_cap = 0;    // smoothed batch deconvolution: most captures per group (0: about 1.5 GB of spectra and sums)
     int deconv_streams = 0;      // irb_deconvolve_batch_device: compute streams the sub-batches alternate between (0: two)
     int release_fence = 1;       // fence.proxy.async between the last ld.shared of a ring stage and its release
     int release_dep = 1;         // the release also carries a data dependency on the values read (0 + 0 = the unguarded round-1 form: sanitizer experiments only)

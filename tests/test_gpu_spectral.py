@@ -158,6 +158,28 @@ def test_smoothing_wavefront_launch_equals_the_per_pass_kernels_bit_for_bit(eng,
     assert np.isfinite(got).all() and np.abs(got).max() > 0
 
 
+@pytest.mark.parametrize("groups,gcap,phase", [(0, 0, True), (2, 0, True), (3, 0, False), (1, 0, True), (0, 2, True), (2, 2, False)])
+def test_smoothed_batch_in_groups_side_by_side_equals_singles(eng, orc, groups, gcap, phase):
+    """The smoothed batch is cut into groups that run side by side on their own streams (and in rounds when there are more groups
+    than lanes), each group in sub-batches with separate staging for its first and last phase: every capture must come out exactly
+    as it does alone, whatever the cut."""
+    n, nb = 1 << 14, 11
+    sweep, h, cap = _capture(orc, n, n // 8, 4)
+    caps = np.stack([cap * np.float32(0.3 + 0.1 * j) + synth.white_noise(1300 + j, 0, n) * np.float32(1e-3) for j in range(nb)])
+    singles = np.stack([eng.deconvolve(caps[j], sweep, 48000.0, True, phase)[0] for j in range(nb)])
+    try:
+        eng.set_tuning("deconv_sub", 2)                      # sub-batches of 2 captures: groups of 3 (2 + 1), or of 6 / 4 / 11 captures
+        eng.set_tuning("deconv_groups", groups)
+        eng.set_tuning("deconv_group_cap", gcap)             # 2: six groups of 2 captures -> rounds of 4 (or 2) lanes, lanes reused
+        got = eng.deconvolve_batch(caps, sweep, 48000.0, True, phase)
+    finally:
+        eng.set_tuning("deconv_sub", 0)
+        eng.set_tuning("deconv_groups", 0)
+        eng.set_tuning("deconv_group_cap", 0)
+    assert np.array_equal(got, singles)
+    _check(got[nb - 1:nb], orc.deconvolve(caps[nb - 1], sweep, 48000.0, True, phase))
+
+
 def test_deconvolve_batch_equals_singles(eng, orc):
     n = 8192
     sweep, _, _ = _capture(orc, n, 100, 0)
