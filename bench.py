@@ -810,7 +810,9 @@ def run_c5(args, R, eng):
                 "config": {"workload": "configs[4]: %d captures per GPU of a 2^20-sample exponential sine sweep (+ room IR, + noise) deconvolved by spectral division, N = 2^20" % nb,
                            "captures_per_gpu": nb, "fft_points": n, "smoothing": bool(args.smoothing), "value_kind": "irb_deconvolve_batch_device: captures and results resident in HBM, CUDA-event time of the whole call",
                            "l2_policy": "inputs larger than L2 (%.1f GB per batch)" % (nb * n * 4 / 1e9), "tuning": args.tune},
-                "roofline": {"bound": "hbm", "kernel": "k_line_fft<512> (columns) + k_rowpair<1024> (rows, divide, inverse rows) + k_line_fft<512,INV>: the batch's kernel time as a whole",
+                "roofline": {"bound": "hbm", "kernel": ("k_line_fft / k_spec_* (transforms, split, divide, merge) + k_avg_passes (three log-average passes as a wavefront, one CTA per capture: "
+                                                        "bound by the reference's sequential running sum and the per-bin rebuild arithmetic, not by HBM): the batch's device time as a whole") if args.smoothing else
+                             "k_line_fft<512> (columns) + k_rowpair<1024> (rows, divide, inverse rows) + k_line_fft<512,INV>: the batch's kernel time as a whole",
                              "achieved": alg / dev / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / dev / 1e9 / peak, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg, "kernel_ms": dev * 1e3, "three_pass_bytes": three_pass, "frac_at_three_pass_bytes": three_pass / dev / 1e9 / peak,
                              "traffic": None},
