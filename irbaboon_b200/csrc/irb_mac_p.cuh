@@ -12,9 +12,10 @@
 //     (NS stages of 16 KB FDL + the IR partition(s)).  The FFT tile is the FDL area of the stage the compute warps consumed last:
 //     they keep that one stage back through the epilogue and the next unit's prologue and release it afterwards, the
 //     producer meanwhile fills the other NS-1 stages;
-//   * no wave quantisation: the units of a launch are sized on the host so that the LAST partial wave runs on units of
-//     fewer rows (ROWS/2, ROWS/4 ...; a narrow unit streams only its rows' part of every FDL slot piece), so a launch takes
-//     ceil(rows / CTAs) row-times instead of ceil(tiles / CTAs) tile-times;
+//   * less wave quantisation: CTAs take units as they finish, so a launch ends when the last unit does instead of after
+//     ceil(tiles / CTAs) lock-step waves.  The host can also size the LAST partial wave as units of fewer rows (ROWS/2, ROWS/4 ...;
+//     unit_n[1..3], tuning knob unit_narrowing); that form is bit-exact but measured slower (a narrow unit has proportionally less
+//     in flight), so it is off by default and every unit is a full tile;
 //   * PERROW = true replaces the register-staged per-stream-IR kernel (BASELINE configs[3]): every row of a unit stages its
 //     own IR partition per ring stage, FDL and IR both through TMA, the forward transform fused -- one launch per block step.
 // The fmaf sequence per bin is the one of k_mac / k_mac_tma / k_fwd: results are bit-identical to the two-launch form.
