@@ -505,15 +505,19 @@ static __global__ void k_avg_linear_sum(const float* la, long long la_stride, co
 // (3) new amplitude = exp(sum / window length), bins rebuilt from it and the original phase (fp/convolution.cpp:518-543)
 // returns the rebuilt bin; shared by the per-pass kernel and the fused three-pass kernel so both execute the same arithmetic
 __device__ __forceinline__ float2 avg_rebuild_bin(float2 v, float sum, int lo_k, int hi_k, int log_avg, int include_phase, int include_ampl) {
-    const double len = (double) (hi_k - lo_k) + 1.0;
-    float ampl = (float) ((double) sum / len);
+    // the reference divides in double and rounds to float: (float) ((double) sum / len).  With both operands exactly representable in
+    // float (the window length is an integer below 2^24) that is the correctly rounded float quotient -- double carries more than
+    // 2 x 24 + 2 bits, so the second rounding cannot change the result -- i.e. IEEE float division, which is what `/` compiles to here.
+    float ampl = sum / (float) (hi_k - lo_k + 1);
     if (log_avg) ampl = expf(ampl);
     ampl = round_1e16(ampl);
     const float re = round_to_zero(v.x, 1e-11f), im = round_to_zero(v.y, 1e-11f);
     float phase = atan2f(im, re);
     if (!include_ampl) ampl = 1.0f;
     if (!include_phase) phase = 0.0f;
-    return make_float2(ampl * cosf(phase), ampl * sinf(phase));
+    float sn, cs;
+    sincosf(phase, &sn, &cs);                                            // one argument reduction for both; same values as sinf / cosf
+    return make_float2(ampl * cs, ampl * sn);
 }
 // next_la != nullptr: also the log amplitudes of the rebuilt bins, i.e. the next pass's step (1)
 static __global__ void k_avg_apply(float2* S, long long s_stride, const float* rs, long long rs_stride, const int* lo, const int* hi, int M, int log_avg,
