@@ -327,7 +327,7 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
                   ~Slot() { for (cudaEvent_t e : {ev_in, ev_done, ev_out, t0, t1}) if (e) cudaEventDestroy(e); } } slot[4];   // [2], [3]: the smoothing path's last phase
     // smoothing runs in up to kLanes groups of captures at once, each on its own compute stream with its own spectrum array and
     // smoother, so that one group's transforms and copies run under another group's running sums
-    constexpr int kLanes = 4;
+    constexpr int kLanes = 8, kLanesDefault = 4;
     struct Lane { DevBuf Sall; Smoother sm; } lane[kLanes];
     struct Spans {                                       // one pair of timing events per kernel section, read back when everything has drained
         std::vector<cudaEvent_t> ev;
@@ -349,7 +349,7 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
     // so a whole GROUP of captures is smoothed at once, between a first phase (upload | forward transform, split, divide) and a
     // last phase (merge, inverse transform | download) that both run in sub-batches with their copies overlapped; the batch is
     // cut into kLanes groups (more, in rounds, when a group would exceed about 1.5 GB of spectra and sums) that run side by side.
-    const int lanes_pref = irbh::g_tuning.deconv_groups > 0 ? std::min(irbh::g_tuning.deconv_groups, kLanes) : kLanes;
+    const int lanes_pref = irbh::g_tuning.deconv_groups > 0 ? std::min(irbh::g_tuning.deconv_groups, kLanes) : kLanesDefault;
     const long long grp_cap = irbh::g_tuning.deconv_group_cap > 0 ? irbh::g_tuning.deconv_group_cap : (3LL << 29) / (20LL * (M + 1));
     const int grp = smoothing ? (int) std::min<long long>(batch, std::max<long long>(sub, std::min<long long>((batch + lanes_pref - 1) / lanes_pref, grp_cap))) : batch;
     const int ngroups = (batch + grp - 1) / grp, nlanes = std::min(ngroups, lanes_pref);
@@ -369,7 +369,8 @@ static int deconvolve_batch_staged(const float* nums, int batch, int len_num, co
     }
     if ((rc = dd.alloc(sizeof(float) * lde, true)) || (rc = Zd.alloc(sizeof(float2) * (size_t) M, false)) || (rc = dtmp.alloc(sizeof(float2) * (size_t) M, false))) return rc;
     if (fused && (rc = Bd.alloc(sizeof(float2) * (size_t) M, false))) return rc;
-    cudaStream_t lst[kLanes] = {st, st, st, st};
+    cudaStream_t lst[kLanes];
+    for (int l = 0; l < kLanes; ++l) lst[l] = st;
     cudaEvent_t ev_den = nullptr, ev_join[kLanes] = {};
     struct EvGuard { cudaEvent_t& d; cudaEvent_t* j; ~EvGuard() { if (d) cudaEventDestroy(d); for (int i = 0; i < kLanes; ++i) if (j[i]) cudaEventDestroy(j[i]); } } evg{ev_den, ev_join};
     if (smoothing) {
