@@ -82,11 +82,23 @@ class ClockSampler:
     def __init__(self, index, period_s=0.005):
         self.index, self.period, self.rows, self.stop_flag, self.thread, self.proc = index, period_s, [], False, None, None
         self.h = None
+        self.smi_id = str(index)
+        bus = None
+        try:                                                 # CUDA device `index` of this process by PCI address: NVML and nvidia-smi count
+            import torch                                     # the physical GPUs, which differs under CUDA_VISIBLE_DEVICES
+            pr = torch.cuda.get_device_properties(index)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            self.smi_id = bus
+        except Exception:
+            bus = None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode() if bus else b"")
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.h = None
@@ -99,7 +111,7 @@ class ClockSampler:
         q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.smi_id, "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
