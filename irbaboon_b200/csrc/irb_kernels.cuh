@@ -325,19 +325,18 @@ __device__ __forceinline__ const float2* ir_replica(const MacArgs& a) {
 // Time-domain epilogue of a tile whose accumulated packed spectra sit in shared memory, row r at tile + r*M
 // (r < rows_in_tile): packed merge -> inverse M-point FFT -> x 1/N -> overlap-add -> output block
 // (fp/convolution.cpp:206-230).  Called by all kThreads compute threads.
-template <int M>
+// phase time stamp of the latency path (measurement aid: a null pointer in every product launch)
+__device__ __forceinline__ void stamp(const MacArgs& a, int i) {
+    if (a.stamps && blockIdx.x < 64 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.stamps[blockIdx.x * 16 + i] = t; }
+}
+
+// LAT (the few-row latency kernel, which has registers to spare): the overlap values are requested before the merge and the
+// transform instead of after them, and the phases are time-stamped when a stamp buffer is set.
+template <int M, bool LAT = false>
 __device__ __forceinline__ void inv_epilogue(const MacArgs& a, float2* tile, int tid, int row0, int rows_in_tile) {
     using T = Tile<M>;
     const int rf = tid / T::TPF, t = tid % T::TPF;
     float2* srow = tile + rf * M;
-    float2 v[kPts];
-#pragma unroll
-    for (int j = 0; j < kPts; ++j) {
-        const int k = t + j * T::TPF;
-        v[j] = real_merge(srow[k], srow[(M - k) & (M - 1)], root<false>(a.W, k), k);
-    }
-    fft_run<M, true>(v, t, srow, a.W);
-    const float scale = 1.0f / (float) (2 * M);      // the 1/N of performRealOnlyInverseTransform
     const int row = row0 + rf;
     const bool live = rf < rows_in_tile && row < a.n_rows;
     const int chan = live ? row / a.blocks_per_chan : 0, blk = live ? row % a.blocks_per_chan : 0;
@@ -346,27 +345,52 @@ __device__ __forceinline__ void inv_epilogue(const MacArgs& a, float2* tile, int
     float* outp = a.out + chan * a.out_chan_stride + (long long) blk * a.B;
     float* ovp = a.ov ? a.ov + (long long) chan * a.B : nullptr;
     float* tailp = a.tail ? a.tail + (long long) row * a.B : nullptr;
-    // fp/convolution.cpp:210-213: y[i] += overlap[i]; overlap[i] = y[B + i]
+    // The overlap of the previous block, all 2 x kPts values of a thread requested back to back (predicated loads, no branches:
+    // one load per basic block used to cost one L2 latency EACH, 1.8 us on the latency path).
+    const bool has_ov = live && ovp != nullptr;
+    float ovv[2 * kPts];
+    auto load_overlap = [&]() {
+#pragma unroll
+        for (int j = 0; j < kPts; ++j) {
+            const int m = 2 * (t + j * T::TPF);
+            ovv[2 * j] = (has_ov && m < a.B) ? ovp[m] : 0.0f;
+            ovv[2 * j + 1] = (has_ov && m + 1 < a.B) ? ovp[m + 1] : 0.0f;
+        }
+    };
+    if constexpr (LAT) load_overlap();
+    float2 v[kPts];
 #pragma unroll
     for (int j = 0; j < kPts; ++j) {
-        v[j].x *= scale; v[j].y *= scale;
-        const int m = 2 * (t + j * T::TPF);
-        if (live && ovp) {
-            if (m < a.B) v[j].x += ovp[m];
-            if (m + 1 < a.B) v[j].y += ovp[m + 1];
-        }
+        const int k = t + j * T::TPF;
+        v[j] = real_merge(srow[k], srow[(M - k) & (M - 1)], root<false>(a.W, k), k);
     }
+    if constexpr (LAT) stamp(a, 10);
+    fft_run<M, true>(v, t, srow, a.W);
+    if constexpr (LAT) stamp(a, 11);
+    if constexpr (!LAT) load_overlap();
+    const float scale = 1.0f / (float) (2 * M);      // the 1/N of performRealOnlyInverseTransform
+    // fp/convolution.cpp:210-213: y[i] += overlap[i]; overlap[i] = y[B + i]   (a product rounded, then a sum rounded: no FMA)
+#pragma unroll
+    for (int j = 0; j < kPts; ++j) {
+        const int m = 2 * (t + j * T::TPF);
+        v[j].x = __fmul_rn(v[j].x, scale); v[j].y = __fmul_rn(v[j].y, scale);
+        if (has_ov && m < a.B) v[j].x = __fadd_rn(v[j].x, ovv[2 * j]);
+        if (has_ov && m + 1 < a.B) v[j].y = __fadd_rn(v[j].y, ovv[2 * j + 1]);
+    }
+    if constexpr (LAT) stamp(a, 12);
     if (a.ov) bar_compute();                           // all overlap reads precede the overlap writes
+    if constexpr (LAT) stamp(a, 13);
     if (live) {
 #pragma unroll
         for (int j = 0; j < kPts; ++j) {
             const int m = 2 * (t + j * T::TPF);
             const float val[2] = {v[j].x, v[j].y};
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < 2; ++e) {                   // one predicated store per sample: output block, or the next overlap / the tail
                 const int mm = m + e;
-                if (mm < a.B) { if (mm < olen) outp[mm] = val[e]; }
-                else if (mm < 2 * a.B) { if (ovp) ovp[mm - a.B] = val[e]; else tailp[mm - a.B] = val[e]; }
+                const bool first = mm < a.B;
+                float* dst = first ? outp + mm : (ovp ? ovp : tailp) + (mm - a.B);
+                if (first ? mm < olen : mm < 2 * a.B) *dst = val[e];
             }
         }
     }
@@ -377,11 +401,6 @@ __device__ __forceinline__ long long fdl_row_offset(const MacArgs& a, int chan, 
     return (chan / grp) * a.fdl_chan_stride + (long long) (chan % grp) * M;
 }
 template <int M> __device__ __forceinline__ long long fdl_slot_stride(const MacArgs& a) { return a.fdl_slot_stride ? a.fdl_slot_stride : M; }
-
-// phase time stamp of the latency path (measurement aid: a null pointer in every product launch)
-__device__ __forceinline__ void stamp(const MacArgs& a, int i) {
-    if (a.stamps && blockIdx.x < 64 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.stamps[blockIdx.x * 16 + i] = t; }
-}
 
 // consumer release of a TMA-filled ring stage by the warp's elected lane (after the warp-wide fence.proxy.async + __syncwarp)
 __device__ __forceinline__ void mbar_release_stage(uint64_t* b, uint32_t dep, const MacArgs& a) {
@@ -1137,7 +1156,7 @@ __global__ void __launch_bounds__(kThreads + 32, 1) k_mac_slots(const MacArgs a)
         }
     }
     if constexpr (INV) {
-        inv_epilogue<M>(a, fin, tid, row0, rpt);
+        inv_epilogue<M, true>(a, fin, tid, row0, rpt);
     } else {
         for (int o = tid; o < rpt * (M / 2); o += kThreads) {
             const int row = row0 + o / (M / 2);
