@@ -91,3 +91,17 @@ def test_capacity_ladder_never_aborts():
     p99_at, calls = _fake_gpu(4.0e-4, 0.0)                                 # a GPU four times slower: jumps to the estimate, then verifies
     S, log, failed = b.capacity_search(p99_at, 98304, period, 300)
     assert not failed and 22528 <= S <= 26624 and len(calls) <= 6
+
+
+def test_clock_sampler_degrades_without_a_gpu():
+    """No NVML / no CUDA device (this container): the sampler constructs, starts, stops and reports that it saw nothing --
+    the bench line then says so instead of inventing clocks."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    b = _bench_module()
+    s = b.ClockSampler(0, 0.005)
+    s.start()
+    s.stop()
+    out = s.summary()
+    assert out["sm_mhz"] is None and out["reasons"] == ["no samples"] and s.near(0.0) is None
